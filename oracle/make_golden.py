@@ -1,0 +1,177 @@
+"""TEST INFRASTRUCTURE ONLY - generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (where /root/reference exists):
+
+    python -m oracle.make_golden            # writes tests/golden/
+
+The reference has no tests or golden vectors of its own, so these files are the
+pinned known answers for the hot path: they are produced by the reference's own code
+(`sampling_ihqgpt`, `iHQGPT.sampling_step`, `cutoff_topk_logits`, `cutoff_topp_probs`) on CPU, fp32,
+on weights that `oracle.hq_oracle.make_params(cfg, seed, init)` regenerates deterministically (same
+torch build on the GPU box), so only the tiny outputs are committed.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+from oracle import hq_oracle as O
+from oracle import ref_shim as R
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+LOGIT_POSITIONS = [0, 1, 2, 31, 63]
+
+
+def reference_sample_rows(model, sos, max_seq_len, capture=None, **kw):
+    """The 40-line outer loop of sampling.py:178-237 re-driven here so that every row can carry its
+    own class (`sos = model.sos(labels).unsqueeze(1)`); each position calls the reference's
+    `iHQGPT.sampling_step` unchanged."""
+    codes_top = codes_bot = past = None
+    B = sos.shape[0]
+    for cnt in range(max_seq_len):
+        if codes_top is None:
+            ct = cb = pos = None
+        else:
+            ct = codes_top[:, cnt - 1:cnt]
+            cb = codes_bot[:, cnt - 1, :]
+            pos = torch.full((B, 1), cnt - 1, dtype=torch.long)
+        if capture is not None:
+            capture["cnt"] = cnt
+        code_top, code_bot, present = model.sampling_step(sos=sos, codes_t=ct, codes_b=cb, pos_codes=pos,
+                                                          use_fp16=False, past=past, **kw)
+        present = torch.stack(present).clone()
+        past = [present] if past is None else past + [present]
+        codes_top = code_top if codes_top is None else torch.cat([codes_top, code_top], 1)
+        codes_bot = code_bot if codes_bot is None else torch.cat([codes_bot, code_bot], 1)
+    return codes_top, codes_bot
+
+
+def run_with_logit_capture(model, sos, max_seq_len, **kw):
+    cap = {"cnt": 0, "top": {}, "bot": {}}
+    h1 = model.head_top.register_forward_hook(
+        lambda m, i, o: cap["top"].__setitem__(cap["cnt"], o.detach().clone().reshape(o.shape[0], -1)))
+    h2 = model.head_bot.register_forward_hook(
+        lambda m, i, o: cap["bot"].__setitem__(cap["cnt"], o.detach().clone()))
+    try:
+        ct, cb = reference_sample_rows(model, sos, max_seq_len, capture=cap, **kw)
+    finally:
+        h1.remove()
+        h2.remove()
+    lg = []
+    for p in LOGIT_POSITIONS:
+        if p < max_seq_len:
+            lg.append(torch.cat([cap["top"][p].unsqueeze(1), cap["bot"][p]], dim=1))   # [B,5,V]
+    return ct, cb, torch.stack(lg, dim=1)                                               # [B,P,5,V]
+
+
+def min_margin(logits):
+    top2 = torch.topk(logits, 2, dim=-1).values
+    return float((top2[..., 0] - top2[..., 1]).min())
+
+
+def full_run_margin(cfg, P, cond, B):
+    """Smallest top-1/top-2 logit gap over ALL 320*B greedy decisions of the run (computed with the
+    oracle, which is bit-identical to the reference on CPU).  The seeds below were picked so that this
+    margin is >= 1e-4: an fp32 GPU run (different summation order, ~1e-6 error) then cannot flip an
+    argmax, which is what makes 'bit-exact greedy code grids' a meaningful assertion."""
+    _, _, lg = O.sample(P, cfg, cond, B, top_k_top=1, top_k_bot=1, return_logits=True)
+    return min_margin(lg)
+
+
+def meta(cfg, seed, init, **extra):
+    d = dict(config=cfg.to_dict(), seed=seed, init=init, torch=torch.__version__,
+             reference="kakaobrain/hqtransformer (read-only tree at /root/reference)")
+    d.update(extra)
+    return np.array(json.dumps(d))
+
+
+GREEDY = dict(top_k_top=1, top_p_top=1.0, top_k_bot=1, top_p_bot=1.0, softmax_temperature=[1.0, 1.0])
+
+
+def golden_cls(cfg, name, seed, init, labels):
+    P = O.make_params(cfg, seed=seed, init=init)
+    model = R.build_reference_model(cfg, P)
+    labels_t = torch.tensor(labels, dtype=torch.long)
+    sos = model.sos(labels_t).unsqueeze(1)
+    ct, cb, lg = run_with_logit_capture(model, sos, 64, **GREEDY)
+    # the reference's own driver: one scalar class for the whole batch (sampling.py:183-186)
+    ct_s, cb_s = R.reference_sample(model, len(labels), int(labels[-1]), max_seq_len=64, **GREEDY)
+    assert torch.equal(ct_s[0], ct[-1]) and torch.equal(cb_s[0], cb[-1])
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name),
+                        meta=meta(cfg, seed, init, labels=list(labels), logit_positions=LOGIT_POSITIONS,
+                                  min_logit_margin=full_run_margin(cfg, P, labels_t, len(labels))),
+                        labels=np.asarray(labels, dtype=np.int64),
+                        codes_top=ct.numpy(), codes_bot=cb.numpy(),
+                        codes_top_scalar_class=ct_s.numpy(), codes_bot_scalar_class=cb_s.numpy(),
+                        logits=lg.numpy().astype(np.float32))
+    print(name, "min greedy margin over the run", full_run_margin(cfg, P, labels_t, len(labels)))
+
+
+def golden_txt(cfg, name, seed, init, B):
+    P = O.make_params(cfg, seed=seed, init=init)
+    model = R.build_reference_model(cfg, P)
+    g = torch.Generator().manual_seed(seed + 1000)
+    ids = torch.randint(0, cfg.vocab_txt, (B, cfg.ctx_len_txt), generator=g)
+    ct, cb = R.reference_sample(model, 1, ids, max_seq_len=64, **GREEDY)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name),
+                        meta=meta(cfg, seed, init, min_logit_margin=full_run_margin(cfg, P, ids, B)),
+                        text_ids=ids.numpy(), codes_top=ct.numpy(), codes_bot=cb.numpy())
+    print(name, "done")
+
+
+def golden_uncond(cfg, name, seed, init, B):
+    P = O.make_params(cfg, seed=seed, init=init)
+    model = R.build_reference_model(cfg, P)
+    torch.manual_seed(seed + 7)
+    kw = dict(top_k_top=8, top_p_top=0.9, top_k_bot=16, top_p_bot=0.95, softmax_temperature=[0.9, 1.1])
+    ct, cb = R.reference_sample(model, B, None, max_seq_len=64, **kw)     # stochastic, global torch RNG
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name), meta=meta(cfg, seed, init, torch_seed=seed + 7, **kw),
+                        codes_top=ct.numpy(), codes_bot=cb.numpy())
+    print(name, "done")
+
+
+def golden_filters(name):
+    """Known answers of cutoff_topk_logits / cutoff_topp_probs (sampling.py:12-37) incl. ties."""
+    _, S = R.import_reference()
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    logits = torch.randn(6, 512, generator=g)
+    logits[1, 100] = logits[1, 7] = logits[1].max() + 1.0                   # tie at the max
+    logits[2, :] = torch.round(logits[2, :] * 2) / 2                        # heavy ties everywhere
+    for k in (1, 2, 5, 64, 512):
+        out[f"topk_{k}"] = S.cutoff_topk_logits(logits.clone(), k).numpy()
+    out["topk_in"] = logits.numpy()
+    probs = torch.softmax(torch.randn(6, 512, generator=g) * 2.0, dim=-1)
+    probs[0, :4] = torch.tensor([0.5, 0.3, 0.15, 0.05]) * probs[0, :4].sum() / 1.0
+    small = torch.tensor([[0.5, 0.3, 0.15, 0.05], [0.25, 0.25, 0.25, 0.25], [0.97, 0.01, 0.01, 0.01]])
+    for p in (0.5, 0.8, 0.95, 1.0):
+        out[f"topp_{p}"] = S.cutoff_topp_probs(probs.clone(), p).numpy()
+        out[f"topp_small_{p}"] = S.cutoff_topp_probs(small.clone(), p).numpy()
+    out["topp_in"] = probs.numpy()
+    out["topp_small_in"] = small.numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name), meta=np.array(json.dumps(dict(torch=torch.__version__))), **out)
+    print(name, "done")
+
+
+def main():
+    if not R.reference_available():
+        print("reference tree absent - goldens can only be generated in the build container", file=sys.stderr)
+        return 1
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    golden_cls(O.SMALL, "small_cls_greedy.npz", seed=5, init="rich", labels=[0, 1, 2, 3])
+    golden_cls(O.TINY, "tiny_cls_greedy.npz", seed=7, init="reference", labels=[9, 4, 4, 0, 7])
+    golden_txt(O.HQConfig(**{**O.TINY.to_dict(), "cond": "txt"}), "tiny_txt_greedy.npz", seed=2, init="rich", B=3)
+    golden_uncond(O.HQConfig(**{**O.TINY.to_dict(), "cond": "uncond"}), "tiny_uncond_stochastic.npz", seed=3,
+                  init="rich", B=4)
+    golden_filters("filters.npz")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

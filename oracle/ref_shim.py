@@ -1,0 +1,96 @@
+"""TEST INFRASTRUCTURE ONLY - imports the *unmodified* reference sampler from /root/reference.
+
+The reference (kakaobrain/hqtransformer) is pure Python; its `hqvae.models` package pulls in
+`pytorch_lightning` and `omegaconf`, neither of which is installed here.  This shim
+registers bare package objects so that only the four hot-path modules are executed:
+
+    hqvae/models/stage2/hierarchical_ar.py   (iHQGPT)
+    hqvae/models/stage2/layers.py            (Block / ParallelBlock / MultiHeadSelfAttention)
+    hqvae/utils/sampling.py                  (sampling_ihqgpt, cutoff_topk_logits, cutoff_topp_probs)
+
+Nothing is copied: the modules are executed from where they lie.  `/root/reference` exists only in
+the build container, so this file is used by `oracle/make_golden.py` and by the `not gpu` tests that
+pin the oracle against the live reference (they skip when the tree is absent).  It must never be
+imported by the product package, `bench.py` or any `-m gpu` test.
+"""
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("HQ_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "hqvae", "models", "stage2", "hierarchical_ar.py"))
+
+
+def import_reference():
+    """Returns (iHQGPT class, reference `hqvae.utils.sampling` module)."""
+    if not reference_available():
+        raise ImportError(f"reference tree not found under {REFERENCE_ROOT}")
+    if "omegaconf" not in sys.modules:
+        om = types.ModuleType("omegaconf")
+
+        class OmegaConf:  # only used in annotations by hierarchical_ar.py:15,32
+            pass
+
+        om.OmegaConf = OmegaConf
+        sys.modules["omegaconf"] = om
+    for name, rel in (("hqvae", "hqvae"),
+                      ("hqvae.models", "hqvae/models"),
+                      ("hqvae.models.stage2", "hqvae/models/stage2"),
+                      ("hqvae.utils", "hqvae/utils")):
+        if name not in sys.modules:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [os.path.join(REFERENCE_ROOT, rel)]  # do NOT run the package __init__
+            sys.modules[name] = pkg
+    from hqvae.models.stage2.hierarchical_ar import iHQGPT  # noqa: E402
+    from hqvae.utils import sampling as ref_sampling  # noqa: E402
+    return iHQGPT, ref_sampling
+
+
+def make_hparams(embed_dim, n_layers, n_heads, n_classes=None, ctx_len_img=64, ctx_len_txt=64,
+                 embedding_type="transformer1"):
+    """Field set of hqvae/utils/config2.py:49-71 (Stage2Hparams) as a SimpleNamespace."""
+    return types.SimpleNamespace(
+        embed_dim=embed_dim, n_layers=n_layers, n_heads=n_heads, n_dense_layers=n_layers,
+        ctx_len=None, ctx_len_img=ctx_len_img, ctx_len_txt=ctx_len_txt,
+        embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0, mlp_bias=True, attn_bias=True,
+        gelu_use_approx=False, use_head_txt=True, n_classes=n_classes, causal_attn=None,
+        embedding_type=embedding_type, position_embedding="1d", bottom_head_type="linear",
+        use_random_order=False, rate_random_order=1.0)
+
+
+def build_reference_model(cfg, state_dict):
+    """Instantiate the reference iHQGPT for an `oracle.hq_oracle.HQConfig` and load `state_dict`."""
+    import contextlib
+    import io
+    iHQGPT, _ = import_reference()
+    hp = make_hparams(cfg.embed_dim, cfg.n_layers, cfg.n_heads, n_classes=cfg.n_classes,
+                      ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt)
+    hp_dec = make_hparams(cfg.embed_dim, cfg.n_layers_depth, cfg.n_heads, n_classes=cfg.n_classes,
+                          ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = iHQGPT(vocab_size_top=cfg.vocab_top, vocab_size_bot=cfg.vocab_bot,
+                       vocab_size_txt=cfg.vocab_txt, ratio_bot2top=4,
+                       use_cls_cond=(cfg.cond == "cls"), use_txt_cond=(cfg.cond == "txt"),
+                       model_type="parallel", hparams=hp, hparams_dec=hp_dec)
+    missing = model.load_state_dict(state_dict, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return model.eval()
+
+
+def reference_sample(model, num_candidates, cond, **kw):
+    """Run the reference's own `sampling_ihqgpt` (utils/sampling.py:164-237) on CPU.
+
+    The reference hard-codes `.cuda()` at sampling.py:184,188; on a CPU-only box that call is
+    neutralised for the duration of the run (tensor stays where it is)."""
+    import torch
+    _, ref_sampling = import_reference()
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        return ref_sampling.sampling_ihqgpt(model, num_candidates=num_candidates, cond=cond,
+                                            is_tqdm=False, use_fp16=False, **kw)
+    finally:
+        torch.Tensor.cuda = saved
