@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the HQ-Transformer hierarchical sampling loop (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+A "step" is one pass of the hot path over one batch: `sampling_ihqgpt` for `--batch` images per GPU, all 64 top
+positions (320 codes per image), random-init weights of the named architecture (the reference's own
+`measure_throughput` protocol: config only, no checkpoint; top-k/top-p None, T = 1, measure_throughput/__main__.py:93-104).
+Weak scaling: the per-GPU batch is fixed, ranks share nothing but one final all-gather of the code grids.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "images_per_sec_sampled_256x256"
+UNIT = "images/s"
+CONFIGS = {"imagenet_l12": "imagenet_l12.yaml", "imagenet_l24": "imagenet_l24.yaml", "imagenet_l42": "imagenet_l42.yaml",
+           "cc15m_l12": "cc15m_l12.yaml"}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--model", default="imagenet_l12", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--top-k", type=int, default=0, help="0 = None (measure_throughput protocol)")
+    ap.add_argument("--top-p", type=float, default=0.0, help="0 = None")
+    ap.add_argument("--temperature", type=float, default=1.0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-table", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=16)
+    ap.add_argument("--cpu-positions", type=int, default=4)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples `nvidia-smi` SM clocks and throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port; /root/reference does not exist on the GPU box) on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(model_name: str, batch: int, positions: int, steps: int, warmup: int):
+    """images/s of the reference sampling algorithm on the host CPU: oracle/hq_oracle.py (fp32, torch CPU kernels with
+    every host thread) run for `positions` of the 64 top positions on `batch` images; rate extrapolated linearly in
+    positions (per-position cost is weight-bound and nearly flat in the cache length at these sizes)."""
+    import torch
+    from oracle import hq_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = {"imagenet_l12": O.IMAGENET_L12, "imagenet_l24": O.IMAGENET_L24, "imagenet_l42": O.IMAGENET_L42,
+           "cc15m_l12": O.CC15M_L12}[model_name]
+    P = O.make_params(cfg, seed=0, init="reference")
+    g = torch.Generator().manual_seed(0)
+    if cfg.cond == "txt":
+        cond = torch.randint(0, cfg.vocab_txt, (batch, cfg.ctx_len_txt), generator=g)
+    else:
+        cond = torch.randint(0, cfg.n_classes, (batch,), generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.sample(P, cfg, cond, batch, max_seq_len=positions, generator=g)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    rate = batch * (positions / 64.0) / sec
+    return rate, sec, cores, (f"{model_name} fp32, oracle port of the reference sampler, batch {batch}, {positions} of 64 top "
+                              f"positions per step (rate scaled by {positions}/64), {len(times)} timed steps")
+
+
+def run_reference_arm(args, rank: int):
+    if rank != 0:
+        return
+    rate, sec, cores, sample = cpu_reference_rate(args.model, args.cpu_batch, args.cpu_positions, max(1, min(args.steps, 3)),
+                                                  min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.model} class-conditional sampling, CPU bounded sample", "model": args.model},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def kernel_table(eng, B, D, L, Ld, V, peaks):
+    """Per-kernel-family launch durations measured live with CUDA events (L2 evicted between launches) and the
+    per-position time model built from them.  Returns (table, dominant roofline dict)."""
+    rows = []
+    fam = [("gemm_qkv", 0, 3 * D, D), ("gemm_proj", 1, D, D), ("gemm_fc1", 2, 4 * D, D), ("gemm_fc2", 3, D, 4 * D)]
+    # launches per top position: spatial L at M=B, depth pass 0 Ld at M=B (qkv without q), depth pass 1 Ld at M=4B
+    for name, kind, N, K in fam:
+        for M, count in ((B, L + Ld), (4 * B, Ld)):
+            us = eng.bench_gemm(kind, M, iters=12)
+            flops = 2.0 * M * N * K
+            wbytes = N * K * 2.0
+            rows.append({"kernel": f"{name}_M{M}", "us": us, "launches_per_position": count,
+                         "tflops": flops / us * 1e-6, "frac_tensor": flops / us * 1e-6 / peaks["bf16_tflops"],
+                         "weight_gbs": wbytes / us * 1e-3, "frac_hbm": wbytes / us * 1e-3 / peaks["hbm_gbs"],
+                         "flops": flops, "bytes": wbytes + M * (N + K) * 2.0})
+    for M in (B, 4 * B):
+        us = eng.bench_gemm(4, M, iters=12)
+        flops = 2.0 * M * V * D
+        rows.append({"kernel": f"gemm_head_M{M}", "us": us, "launches_per_position": 1, "tflops": flops / us * 1e-6,
+                     "frac_tensor": flops / us * 1e-6 / peaks["bf16_tflops"], "weight_gbs": V * D * 2.0 / us * 1e-3,
+                     "frac_hbm": V * D * 2.0 / us * 1e-3 / peaks["hbm_gbs"], "flops": flops,
+                     "bytes": V * D * 2.0 + M * D * 2.0 + M * V * 4.0})
+    for n_keys in (16, 32, 64):
+        us = eng.bench_attention(B, n_keys, iters=48)
+        byt = B * (2.0 * n_keys * D * 2 + 2 * D * 2)          # K + V rows of the cache, q in, out
+        rows.append({"kernel": f"attention_decode_t{n_keys}", "us": us, "launches_per_position": L if n_keys == 32 else 0,
+                     "gbs": byt / us * 1e-3, "frac_hbm": byt / us * 1e-3 / peaks["hbm_gbs"], "bytes": byt})
+    return rows
+
+
+def run_graft_arm(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    import hqtransformer_b200 as H
+    from hqtransformer_b200.distributed import gather_codes
+    from hqtransformer_b200.engine import SamplingParams
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    cfg_path = os.path.join(ROOT, "hqtransformer_b200", "configs", CONFIGS[args.model])
+    model = H.ImageGPT2.from_config(cfg_path, device=local_rank, precision="bf16", max_batch=B,
+                                    use_cuda_graph=not args.no_graph).eval()
+    s2 = model.stage2
+    eng = s2.engine("bf16")
+    g = torch.Generator().manual_seed(1234 + rank)
+    if s2.use_txt_cond:
+        cond_host = torch.randint(0, s2.vocab_size_txt, (B, s2.ctx_len_txt), generator=g)
+    else:
+        cond_host = torch.randint(0, s2.n_classes, (B,), generator=g)       # one class per row
+    cond_dev = cond_host.to(dev)
+    S = 64
+    kw = dict(top_k_top=args.top_k or None, top_k_bot=args.top_k or None, top_p_top=args.top_p or None,
+              top_p_bot=args.top_p or None, softmax_temperature=[args.temperature, args.temperature],
+              use_fp16=True, max_seq_len=S, is_tqdm=False)
+
+    def step(i):
+        ct, cb = H.sampling_ihqgpt(s2, B, cond_dev, seed=i, row_offset=rank * B, **kw)
+        if world > 1:
+            ct, cb = gather_codes(ct, cb, world * B)     # the path's only collective: all-gather of the code grids
+        return ct, cb
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(args.steps):
+        ct, cb = step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = eng.last_launch_count * args.steps
+    assert int(ct.min()) >= 0 and int(ct.max()) < s2.vocab_size_top and tuple(ct.shape) == (world * B, S)
+
+    # ---- end to end through the C-ABI host call: pinned host buffers, H2D of the conditioning and D2H of the grids
+    #      inside the timed region ----
+    cond_pin = cond_host.clone().pin_memory()
+    ct_pin = torch.empty(B, S, dtype=torch.int64).pin_memory()
+    cb_pin = torch.empty(B, S, 4, dtype=torch.int64).pin_memory()
+    sp = SamplingParams(args.top_k or None, args.top_p or None, args.top_k or None, args.top_p or None,
+                        args.temperature, args.temperature, seed=0, row_offset=rank * B)
+
+    def e2e_step(i):
+        sp.seed = i
+        eng.run(batch=B, seq_len=S, pos_begin=0, pos_end=S, sampling=sp, cond=cond_pin, codes_top=ct_pin,
+                codes_bot=cb_pin, host=True)
+
+    e2e_step(0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(1 + i)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    h2d = cond_pin.numel() * 8 + 48
+    d2h = ct_pin.numel() * 8 + cb_pin.numel() * 8
+
+    peaks = load_peaks()
+    line = {"metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.model}: class-conditional HQ-Transformer sampling, 64 top positions x (1 top + 4 bottom "
+                                   f"codes), batch {B} per GPU, random-init weights, top_k={args.top_k or None} "
+                                   f"top_p={args.top_p or None} T={args.temperature}",
+                       "model": args.model, "batch_per_gpu": B, "global_batch": world * B, "positions": S,
+                       "parallelism": f"batch-sharded x{world}, one all-gather of code grids",
+                       "cuda_graph": not args.no_graph,
+                       "l2": "working set (weights + KV cache > 2 GB) exceeds the 126 MB L2; no explicit flush"},
+            "ms_per_top_position": ms / args.steps / S,
+            "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks, "device_bytes": eng.device_bytes}
+
+    if rank == 0:
+        D, L, Ld, V = s2.embed_dim, s2.n_layers, s2.n_layers_depth, s2.vocab_size_top
+        if not args.no_kernel_table:
+            rows = kernel_table(eng, B, D, L, Ld, V, peaks)
+            model_us = sum(r["us"] * r["launches_per_position"] for r in rows)
+            dom = max(rows, key=lambda r: r["us"] * r["launches_per_position"])
+            if dom["kernel"].startswith("gemm"):
+                line["roofline"] = {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_tflops"],
+                                    "unit": "TFLOP/s", "frac": dom["frac_tensor"], "traffic": None, "kernel": dom["kernel"],
+                                    "peak_source": peaks["source"] + ", burst (kernel timed alone)"}
+            else:
+                line["roofline"] = {"bound": "hbm", "achieved": dom["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": dom["frac_hbm"], "traffic": None, "kernel": dom["kernel"],
+                                    "peak_source": peaks["source"]}
+            line["kernels"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()
+                                if k not in ("flops", "bytes")} for r in rows]
+            line["kernel_model_us_per_position"] = model_us
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sec, cores, sample = cpu_reference_rate(args.model, args.cpu_batch, args.cpu_positions, 1, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run so that `python bench.py --gpus N` works
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), __file__] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    run_graft_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1081 @@
+// libhqgraft engine: context, parameter registry (reference state_dict names -> engine layout),
+// the per-position kernel sequence of the HQ sampling loop, CUDA-graph replay, and the C ABI of
+// include/hqgraft.h.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/hqgraft.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace hq;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+struct hq_ctx;
+static void set_err(hq_ctx* ctx, const char* fmt, ...);
+
+#define HQ_CUDA(ctx, call)                                                                       \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      set_err(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return HQ_ERR_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct Weight {          // a GEMM weight [N, K] in the precision's storage type
+  void* ptr = nullptr;
+  int N = 0, K = 0;
+  CUtensorMap map;       // bf16 only: [N, K], box {64, 64}, SWIZZLE_128B
+};
+struct ABuf {            // a GEMM A operand buffer [rows_pad, K]
+  void* ptr = nullptr;
+  int rows = 0, K = 0;
+  CUtensorMap map;       // bf16 only: box {64, 128}
+};
+struct BlockW {
+  Weight qkv, proj, fc1, fc2;
+  float *bqkv, *bproj, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b;
+};
+struct ParamSlot {
+  void* dst = nullptr;
+  int dst_is_weight = 0;   // 1: stored in the GEMM storage type (bf16 | fp32); 0: fp32
+  std::vector<int64_t> shape;
+  bool loaded = false;
+  bool ignored = false;    // accepted for strict loading, never read by the sampler
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct GraphKey {
+  int B, S, p0, p1, forced_top, forced_bot, sos_override;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(B, S, p0, p1, forced_top, forced_bot, sos_override) <
+           std::tie(o.B, o.S, o.p0, o.p1, o.forced_top, o.forced_bot, o.sos_override);
+  }
+};
+
+struct hq_ctx {
+  hq_config cfg;
+  int device = 0, max_batch = 0;
+  bool bf16 = true;
+  int D = 0, nh = 0, L = 0, Ld = 0, Vt = 0, Vb = 0, Vmax = 0, T0 = 1, Tc = 0, Smax = 0;
+  size_t wsize = 2;  // bytes per GEMM weight / activation element
+  std::string err;
+  std::vector<void*> allocs;       // parameters (live as long as the ctx)
+  std::vector<void*> act_allocs;   // batch-sized state (re-made by hq_reserve_batch)
+  bool alloc_act = false;
+  size_t device_bytes = 0, act_bytes = 0;
+  std::map<std::string, ParamSlot> params;
+  PFN_encodeTiled encode = nullptr;
+
+  std::vector<BlockW> blocks, depths;
+  Weight head_top, head_bot;
+  float *sos_table = nullptr, *sos_depth = nullptr;
+  float *E_top = nullptr, *E_bot = nullptr, *P_emb = nullptr, *P_top = nullptr;
+  float *E_txt = nullptr, *P_txt = nullptr;
+  float *E_top_depth = nullptr, *P_depth = nullptr;
+  float *lnf_g = nullptr, *lnf_b = nullptr, *lnt_g = nullptr, *lnt_b = nullptr, *lnb_g = nullptr, *lnb_b = nullptr;
+
+  // activations / state
+  ABuf h, att, mlp;
+  void* q = nullptr;
+  float *x = nullptr, *yd = nullptr, *logits = nullptr;
+  void *kc = nullptr, *vc = nullptr, *kd = nullptr, *vd = nullptr;
+  int64_t *cond = nullptr, *codes_top = nullptr, *codes_bot = nullptr;
+  float* sos_override = nullptr;
+  hq_sampling_params* d_sp = nullptr;
+
+  cudaStream_t own_stream = nullptr;
+  struct GraphEntry { cudaGraphExec_t exec; int64_t launches; };
+  std::map<GraphKey, GraphEntry> graphs;
+  int64_t launches = 0;
+  int64_t last_launches = 0;
+  cudaError_t launch_err = cudaSuccess;
+};
+
+static void set_err(hq_ctx* ctx, const char* fmt, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (ctx) ctx->err = buf;
+}
+
+static int dev_alloc(hq_ctx* ctx, void** p, size_t bytes) {
+  bytes = (bytes + 255) & ~static_cast<size_t>(255);
+  HQ_CUDA(ctx, cudaMalloc(p, bytes));
+  HQ_CUDA(ctx, cudaMemset(*p, 0, bytes));
+  if (ctx->alloc_act) {
+    ctx->act_allocs.push_back(*p);
+    ctx->act_bytes += bytes;
+  } else {
+    ctx->allocs.push_back(*p);
+    ctx->device_bytes += bytes;
+  }
+  return HQ_OK;
+}
+
+static int make_map(hq_ctx* ctx, CUtensorMap* m, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_err(ctx, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", static_cast<int>(r),
+            static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols));
+    return HQ_ERR_CUDA;
+  }
+  return HQ_OK;
+}
+
+static int alloc_weight(hq_ctx* ctx, Weight* w, int N, int K) {
+  w->N = N;
+  w->K = K;
+  int rc = dev_alloc(ctx, &w->ptr, static_cast<size_t>(N) * K * ctx->wsize);
+  if (rc) return rc;
+  if (ctx->bf16) return make_map(ctx, &w->map, w->ptr, N, K, 64);
+  return HQ_OK;
+}
+static int alloc_abuf(hq_ctx* ctx, ABuf* a, int rows, int K) {
+  a->rows = (rows + 127) / 128 * 128;
+  a->K = K;
+  int rc = dev_alloc(ctx, &a->ptr, static_cast<size_t>(a->rows) * K * ctx->wsize);
+  if (rc) return rc;
+  if (ctx->bf16) return make_map(ctx, &a->map, a->ptr, a->rows, K, 128);
+  return HQ_OK;
+}
+static int alloc_f32(hq_ctx* ctx, float** p, size_t n) { return dev_alloc(ctx, reinterpret_cast<void**>(p), n * 4); }
+
+static void reg(hq_ctx* ctx, const std::string& name, void* dst, int is_weight, std::vector<int64_t> shape,
+                bool ignored = false) {
+  ParamSlot s;
+  s.dst = dst;
+  s.dst_is_weight = is_weight;
+  s.shape = shape;
+  s.ignored = ignored;
+  ctx->params[name] = s;
+}
+
+static int build_block(hq_ctx* ctx, BlockW* b, const std::string& prefix) {
+  const int D = ctx->D;
+  int rc;
+  if ((rc = alloc_weight(ctx, &b->qkv, 3 * D, D))) return rc;
+  if ((rc = alloc_weight(ctx, &b->proj, D, D))) return rc;
+  if ((rc = alloc_weight(ctx, &b->fc1, 4 * D, D))) return rc;
+  if ((rc = alloc_weight(ctx, &b->fc2, D, 4 * D))) return rc;
+  if ((rc = alloc_f32(ctx, &b->bqkv, 3 * D))) return rc;
+  if ((rc = alloc_f32(ctx, &b->bproj, D))) return rc;
+  if ((rc = alloc_f32(ctx, &b->b1, 4 * D))) return rc;
+  if ((rc = alloc_f32(ctx, &b->b2, D))) return rc;
+  float** lns[4] = {&b->ln1g, &b->ln1b, &b->ln2g, &b->ln2b};
+  for (auto p : lns)
+    if ((rc = alloc_f32(ctx, p, D))) return rc;
+  const size_t wsz = ctx->wsize;
+  char* wq = static_cast<char*>(b->qkv.ptr);
+  // fused [q; k; v] rows (layers.py:43-50 keeps three separate nn.Linear modules)
+  reg(ctx, prefix + ".attn.query.weight", wq, 1, {D, D});
+  reg(ctx, prefix + ".attn.key.weight", wq + static_cast<size_t>(D) * D * wsz, 1, {D, D});
+  reg(ctx, prefix + ".attn.value.weight", wq + static_cast<size_t>(2) * D * D * wsz, 1, {D, D});
+  reg(ctx, prefix + ".attn.query.bias", b->bqkv, 0, {D});
+  reg(ctx, prefix + ".attn.key.bias", b->bqkv + D, 0, {D});
+  reg(ctx, prefix + ".attn.value.bias", b->bqkv + 2 * D, 0, {D});
+  reg(ctx, prefix + ".attn.proj.weight", b->proj.ptr, 1, {D, D});
+  reg(ctx, prefix + ".attn.proj.bias", b->bproj, 0, {D});
+  reg(ctx, prefix + ".mlp.0.weight", b->fc1.ptr, 1, {4 * D, D});
+  reg(ctx, prefix + ".mlp.0.bias", b->b1, 0, {4 * D});
+  reg(ctx, prefix + ".mlp.2.weight", b->fc2.ptr, 1, {D, 4 * D});
+  reg(ctx, prefix + ".mlp.2.bias", b->b2, 0, {D});
+  reg(ctx, prefix + ".ln1.weight", b->ln1g, 0, {D});
+  reg(ctx, prefix + ".ln1.bias", b->ln1b, 0, {D});
+  reg(ctx, prefix + ".ln2.weight", b->ln2g, 0, {D});
+  reg(ctx, prefix + ".ln2.bias", b->ln2b, 0, {D});
+  return HQ_OK;
+}
+
+template <typename K>
+static int set_smem(hq_ctx* ctx, K kernel, int bytes) {
+  HQ_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return HQ_OK;
+}
+
+static int set_gemm_attrs(hq_ctx* ctx) {
+  int rc;
+#define HQ_SET(BN, EPI) \
+  if ((rc = set_smem(ctx, gemm_tc_kernel<BN, EPI, bf16>, TcCfg<BN>::SMEM_BYTES))) return rc;
+  HQ_SET(64, EPI_QKV) HQ_SET(64, EPI_RESID) HQ_SET(64, EPI_GELU) HQ_SET(64, EPI_F32)
+  HQ_SET(128, EPI_QKV) HQ_SET(128, EPI_RESID) HQ_SET(128, EPI_GELU) HQ_SET(128, EPI_F32)
+#undef HQ_SET
+  return HQ_OK;
+}
+
+static int get_encode_fn(hq_ctx* ctx, PFN_encodeTiled* fn) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  HQ_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+  if (p == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_err(ctx, "cuTensorMapEncodeTiled not available from the driver");
+    return HQ_ERR_CUDA;
+  }
+  *fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return HQ_OK;
+}
+
+static int check_device(hq_ctx* ctx, int device) {
+  int n = 0;
+  HQ_CUDA(ctx, cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) {
+    set_err(ctx, "device %d out of range (%d visible)", device, n);
+    return HQ_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  HQ_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_err(ctx, "libhqgraft is built for sm_100a only; device %d is sm_%d%d (no fallback path)", device, prop.major,
+            prop.minor);
+    return HQ_ERR_UNSUPPORTED;
+  }
+  return HQ_OK;
+}
+
+static void free_activations(hq_ctx* ctx);
+static int reserve_impl(hq_ctx* ctx, int max_batch);
+
+extern "C" int hq_abi_version(void) { return HQ_ABI_VERSION; }
+
+extern "C" const char* hq_last_error(const hq_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int hq_destroy(hq_ctx* ctx) {
+  if (!ctx) return HQ_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  free_activations(ctx);
+  for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return HQ_OK;
+}
+
+static void free_activations(hq_ctx* ctx) {
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
+  ctx->graphs.clear();
+  for (void* p : ctx->act_allocs) cudaFree(p);
+  ctx->act_allocs.clear();
+  ctx->act_bytes = 0;
+}
+
+// batch-sized state: activations, KV cache [L][B][Tc][D] x2, depth KV [Ld][B][5][D] x2, code buffers
+static int reserve_impl(hq_ctx* ctx, int max_batch) {
+  int rc;
+  if (max_batch < 1) {
+    set_err(ctx, "max_batch must be >= 1");
+    return HQ_ERR_INVALID;
+  }
+  HQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  HQ_CUDA(ctx, cudaDeviceSynchronize());
+  free_activations(ctx);
+  ctx->max_batch = max_batch;
+  ctx->alloc_act = true;
+  struct Guard { hq_ctx* c; ~Guard() { c->alloc_act = false; } } guard{ctx};
+  const int D = ctx->D;
+  const int B = max_batch;
+  const int Mx = B * ctx->T0;                       // rows of the spatial residual stream (prefill for text)
+  const int Mmax = (4 * B > Mx) ? 4 * B : Mx;
+  if ((rc = alloc_abuf(ctx, &ctx->h, Mmax, D))) return rc;
+  if ((rc = alloc_abuf(ctx, &ctx->att, Mmax, D))) return rc;
+  if ((rc = alloc_abuf(ctx, &ctx->mlp, Mmax, 4 * D))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->q, static_cast<size_t>(Mmax) * D * ctx->wsize))) return rc;
+  if ((rc = alloc_f32(ctx, &ctx->x, static_cast<size_t>(Mx) * D))) return rc;
+  if ((rc = alloc_f32(ctx, &ctx->yd, static_cast<size_t>(4) * B * D))) return rc;
+  if ((rc = alloc_f32(ctx, &ctx->logits, static_cast<size_t>(4) * B * ctx->Vmax))) return rc;
+  const size_t kvn = static_cast<size_t>(ctx->L) * B * ctx->Tc * D * ctx->wsize;
+  if ((rc = dev_alloc(ctx, &ctx->kc, kvn))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->vc, kvn))) return rc;
+  const size_t kdn = static_cast<size_t>(ctx->Ld) * B * 5 * D * ctx->wsize;
+  if ((rc = dev_alloc(ctx, &ctx->kd, kdn))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->vd, kdn))) return rc;
+  if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->cond), static_cast<size_t>(B) * ctx->T0 * 8))) return rc;
+  if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->codes_top), static_cast<size_t>(B) * ctx->Smax * 8))) return rc;
+  if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->codes_bot), static_cast<size_t>(B) * ctx->Smax * 32))) return rc;
+  if ((rc = alloc_f32(ctx, &ctx->sos_override, static_cast<size_t>(Mx) * D))) return rc;
+  if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->d_sp), sizeof(hq_sampling_params)))) return rc;
+  return HQ_OK;
+}
+
+static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_batch) {
+  int rc;
+  if ((rc = check_device(ctx, device))) return rc;
+  HQ_CUDA(ctx, cudaSetDevice(device));
+  ctx->cfg = *cfg;
+  ctx->device = device;
+  ctx->max_batch = max_batch;
+  ctx->bf16 = cfg->precision == HQ_PREC_BF16;
+  ctx->wsize = ctx->bf16 ? 2 : 4;
+  const int D = ctx->D = cfg->embed_dim;
+  ctx->nh = cfg->n_heads;
+  ctx->L = cfg->n_layers;
+  ctx->Ld = cfg->n_layers_depth;
+  ctx->Vt = cfg->vocab_top;
+  ctx->Vb = cfg->vocab_bot;
+  ctx->Vmax = ctx->Vt > ctx->Vb ? ctx->Vt : ctx->Vb;
+  ctx->Smax = cfg->max_seq_len;
+  const bool txt = cfg->cond_kind == HQ_COND_TXT;
+  ctx->T0 = txt ? cfg->ctx_len_txt : 1;
+  ctx->Tc = ctx->T0 + ctx->Smax - 1;
+  if (max_batch < 1 || D < 64 || D % 64 != 0 || ctx->nh * 64 != D) {
+    set_err(ctx, "unsupported shape: embed_dim=%d n_heads=%d (head size must be 64), max_batch=%d", D, ctx->nh, max_batch);
+    return HQ_ERR_UNSUPPORTED;
+  }
+  if (ctx->Vt % 64 != 0 || ctx->Vb % 64 != 0 || ctx->Vmax > 32768) {
+    set_err(ctx, "unsupported vocabulary sizes %d / %d (multiples of 64, <= 32768)", ctx->Vt, ctx->Vb);
+    return HQ_ERR_UNSUPPORTED;
+  }
+  if (ctx->Tc > ATT_MAX_KEYS || ctx->Smax < 1 || ctx->Smax > cfg->ctx_len_img) {
+    set_err(ctx, "unsupported lengths: max_seq_len=%d ctx_len_img=%d ctx_len_txt=%d (cache length %d > %d)", ctx->Smax,
+            cfg->ctx_len_img, cfg->ctx_len_txt, ctx->Tc, ATT_MAX_KEYS);
+    return HQ_ERR_UNSUPPORTED;
+  }
+  if (cfg->cond_kind < 0 || cfg->cond_kind > 2 || cfg->precision < 0 || cfg->precision > 1) {
+    set_err(ctx, "bad cond_kind / precision");
+    return HQ_ERR_INVALID;
+  }
+  if (ctx->bf16) {
+    if ((rc = get_encode_fn(ctx, &ctx->encode))) return rc;
+    if ((rc = set_gemm_attrs(ctx))) return rc;
+  }
+  HQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+
+  // ---- parameters ----
+  ctx->blocks.resize(ctx->L);
+  ctx->depths.resize(ctx->Ld);
+  for (int i = 0; i < ctx->L; ++i)
+    if ((rc = build_block(ctx, &ctx->blocks[i], "blocks." + std::to_string(i)))) return rc;
+  for (int i = 0; i < ctx->Ld; ++i)
+    if ((rc = build_block(ctx, &ctx->depths[i], "depths." + std::to_string(i)))) return rc;
+  if ((rc = alloc_weight(ctx, &ctx->head_top, ctx->Vt, D))) return rc;
+  if ((rc = alloc_weight(ctx, &ctx->head_bot, ctx->Vb, D))) return rc;
+  reg(ctx, "head_top.weight", ctx->head_top.ptr, 1, {ctx->Vt, D});
+  reg(ctx, "head_bot.weight", ctx->head_bot.ptr, 1, {ctx->Vb, D});
+  struct F32P { const char* name; float** p; std::vector<int64_t> shape; };
+  std::vector<F32P> f32s = {
+      {"sos_depth", &ctx->sos_depth, {1, 1, D}},
+      {"tok_emb_top.weight", &ctx->E_top, {ctx->Vt, D}},
+      {"tok_emb_bot.weight", &ctx->E_bot, {ctx->Vb, D}},
+      {"pos_emb_emb.weight", &ctx->P_emb, {5, D}},
+      {"pos_emb_top.weight", &ctx->P_top, {cfg->ctx_len_img, D}},
+      {"tok_emb_top_depth.weight", &ctx->E_top_depth, {ctx->Vt, D}},
+      {"pos_emb_depth.weight", &ctx->P_depth, {5, D}},
+      {"ln_f.weight", &ctx->lnf_g, {D}}, {"ln_f.bias", &ctx->lnf_b, {D}},
+      {"ln_top.weight", &ctx->lnt_g, {D}}, {"ln_top.bias", &ctx->lnt_b, {D}},
+      {"ln_bot.weight", &ctx->lnb_g, {D}}, {"ln_bot.bias", &ctx->lnb_b, {D}},
+  };
+  if (cfg->cond_kind == HQ_COND_CLS) f32s.push_back({"sos.weight", &ctx->sos_table, {cfg->n_classes, D}});
+  if (cfg->cond_kind == HQ_COND_UNCOND) f32s.push_back({"sos", &ctx->sos_table, {1, 1, D}});
+  if (txt) {
+    f32s.push_back({"tok_emb_txt.weight", &ctx->E_txt, {cfg->vocab_txt, D}});
+    f32s.push_back({"pos_emb_txt.weight", &ctx->P_txt, {cfg->ctx_len_txt, D}});
+  }
+  for (auto& f : f32s) {
+    size_t n = 1;
+    for (auto s : f.shape) n *= static_cast<size_t>(s);
+    if ((rc = alloc_f32(ctx, f.p, n))) return rc;
+    reg(ctx, f.name, *f.p, 0, f.shape);
+  }
+  // present in the reference state_dict, never read when sampling model_type='parallel' 
+  reg(ctx, "tok_emb_bot_depth.weight", nullptr, 0, {ctx->Vb, D}, true);
+  if (txt) {
+    reg(ctx, "head_txt.weight", nullptr, 0, {cfg->vocab_txt, D}, true);
+    reg(ctx, "ln_txt.weight", nullptr, 0, {D}, true);
+    reg(ctx, "ln_txt.bias", nullptr, 0, {D}, true);
+  }
+
+  return reserve_impl(ctx, max_batch);
+}
+
+extern "C" int hq_create(const hq_config* cfg, int device, int max_batch, hq_ctx** out) {
+  if (!cfg || !out) {
+    set_err(nullptr, "hq_create: null argument");
+    return HQ_ERR_INVALID;
+  }
+  *out = nullptr;
+  hq_ctx* ctx = new hq_ctx();
+  int rc = create_impl(ctx, cfg, device, max_batch);
+  if (rc != HQ_OK) {
+    g_last_error = ctx->err;
+    free_activations(ctx);
+    for (void* p : ctx->allocs) cudaFree(p);
+      if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return rc;
+  }
+  *out = ctx;
+  return HQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameter loading
+// ------------------------------------------------------------------------------------------------
+template <typename S, typename Dt>
+__global__ void convert_kernel(const S* __restrict__ s, Dt* __restrict__ d, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float v;
+    if (sizeof(S) == 4) v = *reinterpret_cast<const float*>(&s[i]);
+    else if (std::is_same<S, bf16>::value) v = __bfloat162float(*reinterpret_cast<const bf16*>(&s[i]));
+    else v = __half2float(*reinterpret_cast<const __half*>(&s[i]));
+    if (sizeof(Dt) == 4) *reinterpret_cast<float*>(&d[i]) = v;
+    else *reinterpret_cast<bf16*>(&d[i]) = __float2bfloat16_rn(v);
+  }
+}
+
+template <typename S>
+static void launch_convert(const void* src, void* dst, bool dst_bf16, size_t n) {
+  const int grid = static_cast<int>((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
+  if (dst_bf16) convert_kernel<S, bf16><<<grid, 256>>>(static_cast<const S*>(src), static_cast<bf16*>(dst), n);
+  else convert_kernel<S, float><<<grid, 256>>>(static_cast<const S*>(src), static_cast<float*>(dst), n);
+}
+
+extern "C" int hq_load_param(hq_ctx* ctx, const char* name, const void* data, int dtype, const int64_t* shape, int ndim,
+                             int is_device) {
+  if (!ctx || !name || !data || !shape) {
+    set_err(ctx, "hq_load_param: null argument");
+    return HQ_ERR_INVALID;
+  }
+  HQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  auto it = ctx->params.find(name);
+  if (it == ctx->params.end()) {
+    set_err(ctx, "unexpected key in state_dict: \"%s\"", name);
+    return HQ_ERR_INVALID;
+  }
+  ParamSlot& s = it->second;
+  bool ok = static_cast<size_t>(ndim) == s.shape.size();
+  for (int i = 0; ok && i < ndim; ++i) ok = shape[i] == s.shape[i];
+  if (!ok) {
+    std::string want, got;
+    for (auto v : s.shape) want += std::to_string(v) + ",";
+    for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+    set_err(ctx, "size mismatch for %s: expected [%s] got [%s]", name, want.c_str(), got.c_str());
+    return HQ_ERR_INVALID;
+  }
+  if (dtype < HQ_F32 || dtype > HQ_F16) {
+    set_err(ctx, "bad dtype %d for %s", dtype, name);
+    return HQ_ERR_INVALID;
+  }
+  s.loaded = true;
+  if (s.ignored) return HQ_OK;
+  size_t n = 1;
+  for (auto v : s.shape) n *= static_cast<size_t>(v);
+  const size_t esz = dtype == HQ_F32 ? 4 : 2;
+  const void* src = data;
+  void* staged = nullptr;
+  if (!is_device) {
+    HQ_CUDA(ctx, cudaMalloc(&staged, n * esz));
+    cudaError_t e = cudaMemcpy(staged, data, n * esz, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(staged);
+      set_err(ctx, "cudaMemcpy H2D failed for %s: %s", name, cudaGetErrorString(e));
+      return HQ_ERR_CUDA;
+    }
+    src = staged;
+  }
+  const bool dst_bf16 = s.dst_is_weight && ctx->bf16;
+  if (dtype == HQ_F32) launch_convert<float>(src, s.dst, dst_bf16, n);
+  else if (dtype == HQ_BF16) launch_convert<bf16>(src, s.dst, dst_bf16, n);
+  else launch_convert<__half>(src, s.dst, dst_bf16, n);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (staged) cudaFree(staged);
+  if (e != cudaSuccess) {
+    set_err(ctx, "parameter conversion failed for %s: %s", name, cudaGetErrorString(e));
+    return HQ_ERR_CUDA;
+  }
+  return HQ_OK;
+}
+
+extern "C" int hq_params_complete(hq_ctx* ctx) {
+  if (!ctx) return HQ_ERR_INVALID;
+  std::string missing;
+  int n = 0;
+  for (auto& kv : ctx->params)
+    if (!kv.second.loaded && !kv.second.ignored) {
+      if (n < 8) missing += (n ? ", " : "") + kv.first;
+      ++n;
+    }
+  if (n) {
+    set_err(ctx, "missing %d key(s) in state_dict: %s%s", n, missing.c_str(), n > 8 ? ", ..." : "");
+    return HQ_ERR_STATE;
+  }
+  return HQ_OK;
+}
+
+extern "C" int hq_reserve_batch(hq_ctx* ctx, int max_batch) {
+  if (!ctx) return HQ_ERR_INVALID;
+  return reserve_impl(ctx, max_batch);
+}
+extern "C" int hq_max_batch(const hq_ctx* ctx) { return ctx ? ctx->max_batch : 0; }
+
+extern "C" int64_t hq_last_launch_count(const hq_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+extern "C" size_t hq_device_bytes(const hq_ctx* ctx) { return ctx ? ctx->device_bytes + ctx->act_bytes : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static inline void note_launch(hq_ctx* ctx) {
+  ++ctx->launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess && ctx->launch_err == cudaSuccess) ctx->launch_err = e;
+}
+
+template <int EPI, typename AT>
+static void gemm(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
+                 const EpiParams<AT>& ep);
+
+template <int EPI>
+static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mW, int w_row_off, int M,
+                      int N, int K, const EpiParams<bf16>& ep) {
+  const int mt = (M + 127) / 128;
+  const bool wide = (N % 128 == 0) && (mt * (N / 128) >= 120);
+  if (wide) {
+    dim3 grid(N / 128, mt);
+    gemm_tc_kernel<128, EPI, bf16><<<grid, 192, TcCfg<128>::SMEM_BYTES, st>>>(mA, mW, M, N, K, w_row_off, ep);
+  } else {
+    dim3 grid(N / 64, mt);
+    gemm_tc_kernel<64, EPI, bf16><<<grid, 192, TcCfg<64>::SMEM_BYTES, st>>>(mA, mW, M, N, K, w_row_off, ep);
+  }
+  note_launch(ctx);
+}
+
+template <int EPI>
+static void gemm_f32(hq_ctx* ctx, cudaStream_t st, const float* A, const float* W, int M, int N, int K,
+                     const EpiParams<float>& ep) {
+  dim3 grid((N + 127) / 128, (M + 63) / 64);
+  gemm_simt_kernel<EPI><<<grid, 256, 0, st>>>(A, W, M, N, K, ep);
+  note_launch(ctx);
+}
+
+template <int EPI>
+static void gemm_any(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
+                     const EpiParams<bf16>& ep) {
+  gemm_bf16<EPI>(ctx, st, A.map, W.map, w_row_off, M, N, K, ep);
+}
+template <int EPI>
+static void gemm_any(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
+                     const EpiParams<float>& ep) {
+  gemm_f32<EPI>(ctx, st, static_cast<const float*>(A.ptr),
+                static_cast<const float*>(W.ptr) + static_cast<size_t>(w_row_off) * K, M, N, K, ep);
+}
+
+template <typename AT>
+static void layernorm_act(hq_ctx* ctx, cudaStream_t st, const float* x, const float* g, const float* b, AT* out,
+                          int rows) {
+  layernorm_kernel<AT><<<(rows + 3) / 4, 128, 0, st>>>(x, g, b, nullptr, out, rows, ctx->D, 1, 0);
+  note_launch(ctx);
+}
+
+template <typename AT>
+static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, const AT* V, AT* out, int M, int Tq,
+                      int t_stride, int kbase, int causal) {
+  const int items = M * ctx->nh;
+  attention_kernel<AT><<<(items + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(q, K, V, out, M, ctx->nh, ctx->D,
+                                                                                       Tq, t_stride, kbase, causal);
+  note_launch(ctx);
+}
+
+static void launch_sample(hq_ctx* ctx, cudaStream_t st, const SampleArgs& a) {
+  if (a.V <= 256 * SMP_IPT) sample_kernel<256><<<a.R, 256, 0, st>>>(a);
+  else sample_kernel<1024><<<a.R, 1024, 0, st>>>(a);
+  note_launch(ctx);
+}
+
+// One transformer block (layers.py:324-328 / 371-375) on residual stream `x` [M, D].
+//   mode 0: spatial decode / prefill  - q, k, v; attention over the spatial cache
+//   mode 1: depth pass 0              - k, v only (softmax over one key == identity, a = v)
+//   mode 2: depth pass 1              - q, k, v; 4 queries over the 5 depth keys
+template <typename AT>
+static void run_block(hq_ctx* ctx, cudaStream_t st, const BlockW& w, float* x, int M, int mode, AT* kdst, AT* vdst,
+                      int rpb, int t_stride, int t0, int n_keys_base, int causal) {
+  const int D = ctx->D;
+  AT* h = static_cast<AT*>(ctx->h.ptr);
+  AT* att = static_cast<AT*>(ctx->att.ptr);
+  AT* mlp = static_cast<AT*>(ctx->mlp.ptr);
+  AT* q = static_cast<AT*>(ctx->q);
+  layernorm_act<AT>(ctx, st, x, w.ln1g, w.ln1b, h, M);
+  EpiParams<AT> ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.q = q; ep.kdst = kdst; ep.vdst = vdst; ep.D = D; ep.rpb = rpb; ep.t_stride = t_stride; ep.t0 = t0;
+  if (mode == 1) {
+    ep.bias = w.bqkv + D; ep.sec0 = 1; ep.vdup = att;
+    gemm_any<EPI_QKV>(ctx, st, ctx->h, w.qkv, D, M, 2 * D, D, ep);
+  } else {
+    ep.bias = w.bqkv; ep.sec0 = 0; ep.vdup = nullptr;
+    gemm_any<EPI_QKV>(ctx, st, ctx->h, w.qkv, 0, M, 3 * D, D, ep);
+    attention<AT>(ctx, st, q, kdst, vdst, att, M, rpb, t_stride, n_keys_base, causal);
+  }
+  EpiParams<AT> er;
+  memset(&er, 0, sizeof(er));
+  er.bias = w.bproj; er.x = x;
+  gemm_any<EPI_RESID>(ctx, st, ctx->att, w.proj, 0, M, D, D, er);
+  layernorm_act<AT>(ctx, st, x, w.ln2g, w.ln2b, h, M);
+  EpiParams<AT> eg;
+  memset(&eg, 0, sizeof(eg));
+  eg.bias = w.b1; eg.out = mlp;
+  gemm_any<EPI_GELU>(ctx, st, ctx->h, w.fc1, 0, M, 4 * D, D, eg);
+  EpiParams<AT> e2;
+  memset(&e2, 0, sizeof(e2));
+  e2.bias = w.b2; e2.x = x;
+  gemm_any<EPI_RESID>(ctx, st, ctx->mlp, w.fc2, 0, M, D, 4 * D, e2);
+}
+
+struct RunFlags {
+  int forced_top, forced_bot, sos_override;
+  float* logits_out;
+};
+
+// One top position: spatial step, depth pass 0, draw top, depth pass 1, draw 4 bottoms.
+template <typename AT>
+static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, const RunFlags& f) {
+  const int D = ctx->D, T0 = ctx->T0, Tc = ctx->Tc;
+  const bool txt = ctx->cfg.cond_kind == HQ_COND_TXT;
+  const bool prefill = txt && pos == 0;
+  const int M = prefill ? B * T0 : B;
+  AT* kc = static_cast<AT*>(ctx->kc);
+  AT* vc = static_cast<AT*>(ctx->vc);
+  AT* kd = static_cast<AT*>(ctx->kd);
+  AT* vd = static_cast<AT*>(ctx->vd);
+  AT* h = static_cast<AT*>(ctx->h.ptr);
+  const size_t lstride = static_cast<size_t>(ctx->max_batch) * Tc * D;
+  const size_t dstride = static_cast<size_t>(ctx->max_batch) * 5 * D;
+
+  // ---- K1: input token(s) ----
+  if (prefill) {
+    embed_txt_kernel<<<M, 128, 0, st>>>(ctx->x, f.sos_override ? ctx->sos_override : nullptr, ctx->cond, ctx->E_txt,
+                                        ctx->P_txt, T0, D);
+  } else {
+    EmbedArgs ea;
+    ea.x = ctx->x; ea.sos_table = ctx->sos_table; ea.sos_override = f.sos_override ? ctx->sos_override : nullptr;
+    ea.cond = ctx->cond; ea.E_top = ctx->E_top; ea.E_bot = ctx->E_bot; ea.P_top = ctx->P_top; ea.P_emb = ctx->P_emb;
+    ea.codes_top = ctx->codes_top; ea.codes_bot = ctx->codes_bot; ea.D = D; ea.S = S; ea.pos = pos;
+    ea.cond_kind = ctx->cfg.cond_kind;
+    embed_kernel<<<B, 128, 0, st>>>(ea);
+  }
+  note_launch(ctx);
+
+  // ---- spatial transformer: L blocks over the KV cache ----
+  const int tok = (pos == 0) ? 0 : T0 + pos - 1;     // cache slot of this position's (first) token
+  for (int l = 0; l < ctx->L; ++l) {
+    if (prefill) run_block<AT>(ctx, st, ctx->blocks[l], ctx->x, M, 0, kc + l * lstride, vc + l * lstride, T0, Tc, 0, 0, 1);
+    else run_block<AT>(ctx, st, ctx->blocks[l], ctx->x, M, 0, kc + l * lstride, vc + l * lstride, 1, Tc, tok, tok + 1, 0);
+  }
+  // ---- hs = ln_f(x) (last prefix row for text), depth start token y = hs + sos_depth ----
+  layernorm_kernel<float><<<(B + 3) / 4, 128, 0, st>>>(ctx->x, ctx->lnf_g, ctx->lnf_b, ctx->sos_depth, ctx->yd, B, D,
+                                                        prefill ? T0 : 1, prefill ? T0 - 1 : 0);
+  note_launch(ctx);
+
+  // ---- depth pass 0 -> top logits ----
+  for (int l = 0; l < ctx->Ld; ++l)
+    run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, B, 1, kd + l * dstride, vd + l * dstride, 1, 5, 0, 1, 0);
+  layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnt_g, ctx->lnt_b, h, B);
+  {
+    EpiParams<AT> e;
+    memset(&e, 0, sizeof(e));
+    e.outf = ctx->logits; e.ldo = ctx->Vmax;
+    gemm_any<EPI_F32>(ctx, st, ctx->h, ctx->head_top, 0, B, ctx->Vt, D, e);
+  }
+  SampleArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.logits = ctx->logits; sa.ldl = ctx->Vmax; sa.V = ctx->Vt; sa.R = B; sa.rows_per_b = 1; sa.slot0 = 0;
+  sa.sp = ctx->d_sp; sa.pos = pos; sa.S = S; sa.codes_top = ctx->codes_top; sa.codes_bot = ctx->codes_bot;
+  sa.forced = f.forced_top; sa.logits_out = f.logits_out; sa.Vmax = ctx->Vmax;
+  if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+
+  // ---- depth pass 1 -> 4 bottom logits ----
+  embed_depth_kernel<<<B, 128, 0, st>>>(ctx->yd, ctx->E_top_depth, ctx->P_depth, ctx->codes_top, S, pos, D);
+  note_launch(ctx);
+  for (int l = 0; l < ctx->Ld; ++l)
+    run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, 4 * B, 2, kd + l * dstride, vd + l * dstride, 4, 5, 1, 5, 0);
+  layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnb_g, ctx->lnb_b, h, 4 * B);
+  {
+    EpiParams<AT> e;
+    memset(&e, 0, sizeof(e));
+    e.outf = ctx->logits; e.ldo = ctx->Vmax;
+    gemm_any<EPI_F32>(ctx, st, ctx->h, ctx->head_bot, 0, 4 * B, ctx->Vb, D, e);
+  }
+  sa.V = ctx->Vb; sa.R = 4 * B; sa.rows_per_b = 4; sa.slot0 = 1; sa.forced = f.forced_bot;
+  if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+}
+
+static void run_range(hq_ctx* ctx, cudaStream_t st, int B, int S, int p0, int p1, const RunFlags& f) {
+  for (int pos = p0; pos < p1; ++pos) {
+    if (ctx->bf16) run_position<bf16>(ctx, st, B, S, pos, f);
+    else run_position<float>(ctx, st, B, S, pos, f);
+  }
+}
+
+static int validate_run(hq_ctx* ctx, const hq_run_args* a) {
+  if (!ctx || !a) return HQ_ERR_INVALID;
+  int rc = hq_params_complete(ctx);
+  if (rc) return rc;
+  if (a->batch < 1 || a->batch > ctx->max_batch) {
+    set_err(ctx, "batch %d outside [1, max_batch=%d]", a->batch, ctx->max_batch);
+    return HQ_ERR_INVALID;
+  }
+  if (a->seq_len < 1 || a->seq_len > ctx->Smax || a->pos_begin < 0 || a->pos_end > a->seq_len || a->pos_begin >= a->pos_end) {
+    set_err(ctx, "bad position range [%d, %d) for seq_len %d (max_seq_len %d)", a->pos_begin, a->pos_end, a->seq_len, ctx->Smax);
+    return HQ_ERR_INVALID;
+  }
+  if (!a->codes_top || !a->codes_bot) {
+    set_err(ctx, "codes_top / codes_bot must not be null");
+    return HQ_ERR_INVALID;
+  }
+  if (a->pos_begin == 0 && !a->sos && !a->cond && ctx->cfg.cond_kind != HQ_COND_UNCOND) {
+    set_err(ctx, "conditional model: `cond` (or `sos`) is required at pos_begin == 0");
+    return HQ_ERR_INVALID;
+  }
+  const hq_sampling_params& s = a->sampling;
+  if (!(s.temperature_top > 0.f) || !(s.temperature_bot > 0.f)) {
+    set_err(ctx, "softmax temperatures must be > 0 (got %g, %g)", s.temperature_top, s.temperature_bot);
+    return HQ_ERR_INVALID;
+  }
+  return HQ_OK;
+}
+
+static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemcpyKind in_kind, cudaMemcpyKind out_kind) {
+  int rc = validate_run(ctx, a);
+  if (rc) return rc;
+  HQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int B = a->batch, S = a->seq_len, D = ctx->D, T0 = ctx->T0;
+  const size_t nt = static_cast<size_t>(B) * S * 8, nb = nt * 4;
+
+  // ---- stage inputs into ctx-owned buffers (what the captured graph reads) ----
+  // pageable source: the runtime stages it before returning, so back-to-back calls cannot race on it
+  HQ_CUDA(ctx, cudaMemcpyAsync(ctx->d_sp, &a->sampling, sizeof(hq_sampling_params), cudaMemcpyHostToDevice, st));
+  if (a->pos_begin == 0) {
+    if (a->cond && ctx->cfg.cond_kind != HQ_COND_UNCOND)
+      HQ_CUDA(ctx, cudaMemcpyAsync(ctx->cond, a->cond, static_cast<size_t>(B) * T0 * 8, in_kind, st));
+    if (a->sos)
+      HQ_CUDA(ctx, cudaMemcpyAsync(ctx->sos_override, a->sos, static_cast<size_t>(B) * T0 * D * 4, in_kind, st));
+  } else {
+    HQ_CUDA(ctx, cudaMemcpyAsync(ctx->codes_top, a->codes_top, nt, in_kind, st));
+    HQ_CUDA(ctx, cudaMemcpyAsync(ctx->codes_bot, a->codes_bot, nb, in_kind, st));
+  }
+  if (a->given_top) HQ_CUDA(ctx, cudaMemcpyAsync(ctx->codes_top, a->given_top, nt, in_kind, st));
+  if (a->given_bot) HQ_CUDA(ctx, cudaMemcpyAsync(ctx->codes_bot, a->given_bot, nb, in_kind, st));
+
+  RunFlags f;
+  f.forced_top = a->given_top != nullptr;
+  f.forced_bot = a->given_bot != nullptr;
+  f.sos_override = a->sos != nullptr;
+  f.logits_out = nullptr;
+  float* dev_logits = nullptr;
+  const size_t nlog = static_cast<size_t>(B) * S * 5 * ctx->Vmax * 4;
+  if (a->logits) {
+    if (out_kind == cudaMemcpyDeviceToHost) {
+      HQ_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&dev_logits), nlog));
+      HQ_CUDA(ctx, cudaMemsetAsync(dev_logits, 0, nlog, st));
+      f.logits_out = dev_logits;
+    } else {
+      f.logits_out = a->logits;
+    }
+  }
+
+  ctx->launches = 0;
+  ctx->launch_err = cudaSuccess;
+  const bool use_graph = ctx->cfg.use_cuda_graph && f.logits_out == nullptr;
+  if (use_graph) {
+    GraphKey key{B, S, a->pos_begin, a->pos_end, f.forced_top, f.forced_bot, f.sos_override};
+    auto it = ctx->graphs.find(key);
+    if (it == ctx->graphs.end()) {
+      cudaGraph_t graph = nullptr;
+      HQ_CUDA(ctx, cudaStreamBeginCapture(ctx->own_stream, cudaStreamCaptureModeThreadLocal));
+      run_range(ctx, ctx->own_stream, B, S, a->pos_begin, a->pos_end, f);
+      cudaError_t ce = cudaStreamEndCapture(ctx->own_stream, &graph);
+      if (ce != cudaSuccess || ctx->launch_err != cudaSuccess) {
+        set_err(ctx, "graph capture failed: %s / %s", cudaGetErrorString(ce), cudaGetErrorString(ctx->launch_err));
+        if (graph) cudaGraphDestroy(graph);
+        return HQ_ERR_CUDA;
+      }
+      cudaGraphExec_t exec = nullptr;
+      cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) {
+        set_err(ctx, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+        return HQ_ERR_CUDA;
+      }
+      it = ctx->graphs.emplace(key, hq_ctx::GraphEntry{exec, ctx->launches}).first;
+    }
+    HQ_CUDA(ctx, cudaGraphLaunch(it->second.exec, st));
+    ctx->last_launches = it->second.launches;
+  } else {
+    run_range(ctx, st, B, S, a->pos_begin, a->pos_end, f);
+    ctx->last_launches = ctx->launches;
+    if (ctx->launch_err != cudaSuccess) {
+      set_err(ctx, "kernel launch failed: %s", cudaGetErrorString(ctx->launch_err));
+      if (dev_logits) cudaFree(dev_logits);
+      return HQ_ERR_CUDA;
+    }
+  }
+
+  HQ_CUDA(ctx, cudaMemcpyAsync(a->codes_top, ctx->codes_top, nt, out_kind, st));
+  HQ_CUDA(ctx, cudaMemcpyAsync(a->codes_bot, ctx->codes_bot, nb, out_kind, st));
+  if (dev_logits) {
+    HQ_CUDA(ctx, cudaMemcpyAsync(a->logits, dev_logits, nlog, cudaMemcpyDeviceToHost, st));
+    HQ_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(dev_logits);
+  }
+  return HQ_OK;
+}
+
+extern "C" int hq_run(hq_ctx* ctx, const hq_run_args* args, void* stream) {
+  return run_impl(ctx, args, static_cast<cudaStream_t>(stream), cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);
+}
+
+extern "C" int hq_run_host(hq_ctx* ctx, const hq_run_args* args) {
+  if (!ctx) return HQ_ERR_INVALID;
+  int rc = run_impl(ctx, args, ctx->own_stream, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost);
+  if (rc) return rc;
+  HQ_CUDA(ctx, cudaStreamSynchronize(ctx->own_stream));
+  return HQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// test / measurement hooks
+// ------------------------------------------------------------------------------------------------
+extern "C" int hq_debug_gemm(int prec, const void* A, const void* W, float* C, int M, int N, int K, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  hq_ctx tmp;   // only used for error text + launch bookkeeping
+  if (M < 1 || N < 8 || K < 16) {
+    set_err(nullptr, "hq_debug_gemm: bad shape");
+    return HQ_ERR_INVALID;
+  }
+  if (prec == HQ_PREC_FP32) {
+    if (K % 16 != 0 || N % 8 != 0) {
+      set_err(nullptr, "hq_debug_gemm(fp32): K %% 16 and N %% 8 must be 0");
+      return HQ_ERR_INVALID;
+    }
+    EpiParams<float> e;
+    memset(&e, 0, sizeof(e));
+    e.outf = C; e.ldo = N;
+    gemm_f32<EPI_F32>(&tmp, st, static_cast<const float*>(A), static_cast<const float*>(W), M, N, K, e);
+  } else {
+    if (K % 64 != 0 || N % 64 != 0) {
+      set_err(nullptr, "hq_debug_gemm(bf16): K %% 64 and N %% 64 must be 0");
+      return HQ_ERR_INVALID;
+    }
+    int dev = 0;
+    HQ_CUDA(nullptr, cudaGetDevice(&dev));
+    int rc = check_device(&tmp, dev);
+    if (rc == HQ_OK) rc = get_encode_fn(&tmp, &tmp.encode);
+    if (rc == HQ_OK) rc = set_gemm_attrs(&tmp);
+    // A rows are padded to the 128-row tile by a zero-filled staging copy so that the TMA box never leaves the tensor
+    const int Mp = (M + 127) / 128 * 128;
+    void* Ap = nullptr;
+    if (rc == HQ_OK) {
+      HQ_CUDA(nullptr, cudaMalloc(&Ap, static_cast<size_t>(Mp) * K * 2));
+      cudaMemsetAsync(Ap, 0, static_cast<size_t>(Mp) * K * 2, st);
+      cudaMemcpyAsync(Ap, A, static_cast<size_t>(M) * K * 2, cudaMemcpyDeviceToDevice, st);
+    }
+    CUtensorMap mA, mW;
+    if (rc == HQ_OK) rc = make_map(&tmp, &mA, Ap, Mp, K, 128);
+    if (rc == HQ_OK) rc = make_map(&tmp, &mW, const_cast<void*>(W), N, K, 64);
+    if (rc == HQ_OK) {
+      EpiParams<bf16> e;
+      memset(&e, 0, sizeof(e));
+      e.outf = C; e.ldo = N;
+      gemm_bf16<EPI_F32>(&tmp, st, mA, mW, 0, M, N, K, e);
+    }
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (Ap) cudaFree(Ap);
+    if (rc != HQ_OK) {
+      g_last_error = tmp.err;
+      return rc;
+    }
+    if (se != cudaSuccess) {
+      set_err(nullptr, "hq_debug_gemm: %s", cudaGetErrorString(se));
+      return HQ_ERR_CUDA;
+    }
+  }
+  if (tmp.launch_err != cudaSuccess) {
+    set_err(nullptr, "hq_debug_gemm launch failed: %s", cudaGetErrorString(tmp.launch_err));
+    return HQ_ERR_CUDA;
+  }
+  return HQ_OK;
+}
+
+extern "C" int hq_debug_philox(uint64_t seed, const uint32_t counter[4], uint32_t out[4]) {
+  uint32_t o[4];
+  philox4x32_10(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), counter[0], counter[1], counter[2],
+                counter[3], o);
+  for (int i = 0; i < 4; ++i) out[i] = o[i];
+  return HQ_OK;
+}
+
+extern "C" int hq_debug_sample(const float* logits, int R, int V, float temperature, int top_k, float top_p,
+                               uint64_t seed, uint64_t row_offset, int position, int slot, int64_t* out_codes,
+                               float* out_probs, void* stream) {
+  if (!logits || !out_codes || R < 1 || V < 4 || V % 4 != 0 || V > 32768 || !(temperature > 0.f)) {
+    set_err(nullptr, "hq_debug_sample: bad argument");
+    return HQ_ERR_INVALID;
+  }
+  hq_ctx tmp;
+  SampleArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.logits = logits; sa.ldl = V; sa.V = V; sa.R = R; sa.rows_per_b = 1; sa.slot0 = slot; sa.sp = nullptr;
+  sa.pos = position; sa.S = 1; sa.flat_out = out_codes; sa.probs_out = out_probs; sa.Vmax = V;
+  sa.temperature = temperature; sa.top_p = top_p; sa.top_k = top_k; sa.seed = seed; sa.row_offset = row_offset;
+  launch_sample(&tmp, static_cast<cudaStream_t>(stream), sa);
+  if (tmp.launch_err != cudaSuccess) {
+    set_err(nullptr, "hq_debug_sample launch failed: %s", cudaGetErrorString(tmp.launch_err));
+    return HQ_ERR_CUDA;
+  }
+  return HQ_OK;
+}
+
+extern "C" int hq_bench_attention(hq_ctx* ctx, int B, int n_keys, int iters, float* usec, void* stream) {
+  if (!ctx || !usec || B < 1 || B > ctx->max_batch || n_keys < 1 || n_keys > ctx->Tc || iters < 1) {
+    set_err(ctx, "hq_bench_attention: bad argument");
+    return HQ_ERR_INVALID;
+  }
+  HQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e0, e1;
+  HQ_CUDA(ctx, cudaEventCreate(&e0));
+  HQ_CUDA(ctx, cudaEventCreate(&e1));
+  const size_t lstride = static_cast<size_t>(ctx->max_batch) * ctx->Tc * ctx->D;
+  ctx->launch_err = cudaSuccess;
+  auto launch = [&](int l) {
+    if (ctx->bf16) {
+      bf16* kc = static_cast<bf16*>(ctx->kc) + l * lstride;
+      bf16* vc = static_cast<bf16*>(ctx->vc) + l * lstride;
+      attention<bf16>(ctx, st, static_cast<bf16*>(ctx->q), kc, vc, static_cast<bf16*>(ctx->att.ptr), B, 1, ctx->Tc, n_keys, 0);
+    } else {
+      float* kc = static_cast<float*>(ctx->kc) + l * lstride;
+      float* vc = static_cast<float*>(ctx->vc) + l * lstride;
+      attention<float>(ctx, st, static_cast<float*>(ctx->q), kc, vc, static_cast<float*>(ctx->att.ptr), B, 1, ctx->Tc, n_keys, 0);
+    }
+  };
+  for (int i = 0; i < 3; ++i) launch(i % ctx->L);
+  HQ_CUDA(ctx, cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) launch(i % ctx->L);   // cycling layers: every launch reads a different cache slab
+  HQ_CUDA(ctx, cudaEventRecord(e1, st));
+  HQ_CUDA(ctx, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  HQ_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ctx->launch_err != cudaSuccess) {
+    set_err(ctx, "attention launch failed: %s", cudaGetErrorString(ctx->launch_err));
+    return HQ_ERR_CUDA;
+  }
+  *usec = ms * 1000.f / iters;
+  return HQ_OK;
+}
+
+// Times one GEMM family of the sampler in isolation (events on `stream`): kind 0 = qkv [3D, D], 1 = proj [D, D],
+// 2 = fc1 [4D, D], 3 = fc2 [D, 4D], 4 = head_top [V, D].  Successive launches cycle through the layers and a
+// 256 MB scratch write between launches evicts L2, so every launch streams its weights from HBM as in the real loop.
+extern "C" int hq_bench_gemm(hq_ctx* ctx, int kind, int M, int iters, float* usec, void* stream) {
+  if (!ctx || !usec || kind < 0 || kind > 4 || M < 1 || M > ctx->h.rows || iters < 1) {
+    set_err(ctx, "hq_bench_gemm: bad argument");
+    return HQ_ERR_INVALID;
+  }
+  HQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = ctx->D;
+  const size_t flush_bytes = static_cast<size_t>(256) << 20;
+  void* flush = nullptr;
+  HQ_CUDA(ctx, cudaMalloc(&flush, flush_bytes));
+  std::vector<cudaEvent_t> ev(2 * iters);
+  for (auto& e : ev) cudaEventCreate(&e);
+  ctx->launch_err = cudaSuccess;
+  auto launch = [&](int i) {
+    const BlockW& w = ctx->blocks[i % ctx->L];
+    if (ctx->bf16) {
+      EpiParams<bf16> e;
+      memset(&e, 0, sizeof(e));
+      if (kind == 0) {
+        e.bias = w.bqkv; e.q = static_cast<bf16*>(ctx->q); e.kdst = static_cast<bf16*>(ctx->kd); e.vdst = static_cast<bf16*>(ctx->vd);
+        e.D = D; e.rpb = 4; e.t_stride = 5; e.t0 = 1;
+        gemm_any<EPI_QKV>(ctx, st, ctx->h, w.qkv, 0, M, 3 * D, D, e);
+      } else if (kind == 1) {
+        e.bias = w.bproj; e.x = ctx->yd;
+        gemm_any<EPI_RESID>(ctx, st, ctx->att, w.proj, 0, M, D, D, e);
+      } else if (kind == 2) {
+        e.bias = w.b1; e.out = static_cast<bf16*>(ctx->mlp.ptr);
+        gemm_any<EPI_GELU>(ctx, st, ctx->h, w.fc1, 0, M, 4 * D, D, e);
+      } else if (kind == 3) {
+        e.bias = w.b2; e.x = ctx->yd;
+        gemm_any<EPI_RESID>(ctx, st, ctx->mlp, w.fc2, 0, M, D, 4 * D, e);
+      } else {
+        e.outf = ctx->logits; e.ldo = ctx->Vmax;
+        gemm_any<EPI_F32>(ctx, st, ctx->h, ctx->head_top, 0, M, ctx->Vt, D, e);
+      }
+    } else {
+      EpiParams<float> e;
+      memset(&e, 0, sizeof(e));
+      if (kind == 0) {
+        e.bias = w.bqkv; e.q = static_cast<float*>(ctx->q); e.kdst = static_cast<float*>(ctx->kd); e.vdst = static_cast<float*>(ctx->vd);
+        e.D = D; e.rpb = 4; e.t_stride = 5; e.t0 = 1;
+        gemm_any<EPI_QKV>(ctx, st, ctx->h, w.qkv, 0, M, 3 * D, D, e);
+      } else if (kind == 1) {
+        e.bias = w.bproj; e.x = ctx->yd;
+        gemm_any<EPI_RESID>(ctx, st, ctx->att, w.proj, 0, M, D, D, e);
+      } else if (kind == 2) {
+        e.bias = w.b1; e.out = static_cast<float*>(ctx->mlp.ptr);
+        gemm_any<EPI_GELU>(ctx, st, ctx->h, w.fc1, 0, M, 4 * D, D, e);
+      } else if (kind == 3) {
+        e.bias = w.b2; e.x = ctx->yd;
+        gemm_any<EPI_RESID>(ctx, st, ctx->mlp, w.fc2, 0, M, D, 4 * D, e);
+      } else {
+        e.outf = ctx->logits; e.ldo = ctx->Vmax;
+        gemm_any<EPI_F32>(ctx, st, ctx->h, ctx->head_top, 0, M, ctx->Vt, D, e);
+      }
+    }
+  };
+  // rows >= max_batch of kd/vd would be out of range for the qkv epilogue: clamp M for kind 0
+  if (kind == 0 && M > 4 * ctx->max_batch) M = 4 * ctx->max_batch;
+  for (int i = 0; i < 3; ++i) launch(i);
+  for (int i = 0; i < iters; ++i) {
+    cudaMemsetAsync(flush, i & 0xff, flush_bytes, st);
+    cudaEventRecord(ev[2 * i], st);
+    launch(i);
+    cudaEventRecord(ev[2 * i + 1], st);
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  double tot = 0.0;
+  for (int i = 0; i < iters; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
+    tot += ms;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  cudaFree(flush);
+  if (se != cudaSuccess || ctx->launch_err != cudaSuccess) {
+    set_err(ctx, "hq_bench_gemm: %s / %s", cudaGetErrorString(se), cudaGetErrorString(ctx->launch_err));
+    return HQ_ERR_CUDA;
+  }
+  *usec = static_cast<float>(tot * 1000.0 / iters);
+  return HQ_OK;
+}

@@ -1,0 +1,491 @@
+// Non-GEMM kernels of the HQ sampling loop: input embedding, LayerNorm, KV-cache attention,
+// fused temperature / top-k / top-p / Philox categorical draw.
+#pragma once
+
+#include "common.cuh"
+#include "../../include/hqgraft.h"
+
+namespace hq {
+
+// ------------------------------------------------------------------------------------------------
+// K1: spatial-transformer input token (hierarchical_ar.py:493-499, 506-544 with emb_blocks empty):
+//   pos == 0 : x[b] = sos row (class embedding / learned sos / caller-provided override)
+//   pos  > 0 : x[b] = mean_5( {E_top[c_t] + P_top[pos-1], E_bot[c_b0..3]} + P_emb[0..4] ), codes of pos-1
+// One CTA per batch row.
+// ------------------------------------------------------------------------------------------------
+struct EmbedArgs {
+  float* x;                 // [B, D]
+  const float* sos_table;   // cls: [n_classes, D]; uncond: [D]
+  const float* sos_override;// optional [B, D]
+  const int64_t* cond;      // cls: [B]
+  const float* E_top; const float* E_bot; const float* P_top; const float* P_emb;
+  const int64_t* codes_top; // [B, S]
+  const int64_t* codes_bot; // [B, S, 4]
+  int D, S, pos, cond_kind;
+};
+
+__global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a) {
+  const int b = blockIdx.x;
+  float4* xo = reinterpret_cast<float4*>(a.x + static_cast<size_t>(b) * a.D);
+  const int n4 = a.D / 4;
+  if (a.pos == 0) {
+    const float* src;
+    if (a.sos_override != nullptr) src = a.sos_override + static_cast<size_t>(b) * a.D;
+    else if (a.cond_kind == HQ_COND_CLS) src = a.sos_table + static_cast<size_t>(a.cond[b]) * a.D;
+    else src = a.sos_table;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) xo[i] = s4[i];
+    return;
+  }
+  const int p = a.pos - 1;
+  const int64_t ct = a.codes_top[static_cast<size_t>(b) * a.S + p];
+  const int64_t* cbp = a.codes_bot + (static_cast<size_t>(b) * a.S + p) * 4;
+  const float4* et = reinterpret_cast<const float4*>(a.E_top + static_cast<size_t>(ct) * a.D);
+  const float4* pt = reinterpret_cast<const float4*>(a.P_top + static_cast<size_t>(p) * a.D);
+  const float4* eb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) eb[j] = reinterpret_cast<const float4*>(a.E_bot + static_cast<size_t>(cbp[j]) * a.D);
+  const float4* pe = reinterpret_cast<const float4*>(a.P_emb);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 t = et[i], q = pt[i], e0 = pe[i];
+    float4 acc;
+    acc.x = (t.x + q.x) + e0.x; acc.y = (t.y + q.y) + e0.y; acc.z = (t.z + q.z) + e0.z; acc.w = (t.w + q.w) + e0.w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 e = eb[j][i], pj = pe[(j + 1) * n4 + i];
+      acc.x += e.x + pj.x; acc.y += e.y + pj.y; acc.z += e.z + pj.z; acc.w += e.w + pj.w;
+    }
+    acc.x /= 5.0f; acc.y /= 5.0f; acc.z /= 5.0f; acc.w /= 5.0f;
+    xo[i] = acc;
+  }
+}
+
+// text prefix embedding (sampling.py:187-190): x[b*T + t] = E_txt[ids[b, t]] + P_txt[t]
+__global__ void __launch_bounds__(128)
+embed_txt_kernel(float* x, const float* sos_override, const int64_t* ids, const float* E_txt, const float* P_txt,
+                 int T, int D) {
+  const int row = blockIdx.x;  // b*T + t
+  const int t = row % T;
+  float4* xo = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * D);
+  const int n4 = D / 4;
+  if (sos_override != nullptr) {
+    const float4* s4 = reinterpret_cast<const float4*>(sos_override + static_cast<size_t>(row) * D);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) xo[i] = s4[i];
+    return;
+  }
+  const float4* e = reinterpret_cast<const float4*>(E_txt + static_cast<size_t>(ids[row]) * D);
+  const float4* p = reinterpret_cast<const float4*>(P_txt + static_cast<size_t>(t) * D);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 a = e[i], c = p[i];
+    xo[i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+  }
+}
+
+// K11: depth pass-1 inputs (hierarchical_ar.py:701-703): y[b*4 + j] = E_top_depth[c_top[b]] + P_depth[j]
+__global__ void __launch_bounds__(128)
+embed_depth_kernel(float* y, const float* E_top_depth, const float* P_depth, const int64_t* codes_top, int S, int pos,
+                   int D) {
+  const int b = blockIdx.x;
+  const int64_t ct = codes_top[static_cast<size_t>(b) * S + pos];
+  const float4* e = reinterpret_cast<const float4*>(E_top_depth + static_cast<size_t>(ct) * D);
+  const float4* p = reinterpret_cast<const float4*>(P_depth);
+  const int n4 = D / 4;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 a = e[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 c = p[j * n4 + i];
+      reinterpret_cast<float4*>(y + (static_cast<size_t>(b) * 4 + j) * D)[i] =
+          make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: LayerNorm (eps 1e-5, affine), one warp per row, fp32 statistics (two-pass).
+//   out[r] = LN(x[r * in_mul + in_off]) * gamma + beta (+ add)        OutT = float | bf16
+// The (+ add) form produces the depth transformer's start token hs + sos_depth (hierarchical_ar.py:561, 685).
+// ------------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(128)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const float* __restrict__ add, OutT* __restrict__ out, int rows, int D, int in_mul, int in_off) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* xr = x + (static_cast<size_t>(r) * in_mul + in_off) * D;
+  float s = 0.f;
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + i);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + i);
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(D) + 1e-5f);
+  OutT* o = out + static_cast<size_t>(r) * D;
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + i);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + i);
+    const float4 bt = *reinterpret_cast<const float4*>(beta + i);
+    float y0 = (v.x - mean) * rstd * g.x + bt.x, y1 = (v.y - mean) * rstd * g.y + bt.y;
+    float y2 = (v.z - mean) * rstd * g.z + bt.z, y3 = (v.w - mean) * rstd * g.w + bt.w;
+    if (add != nullptr) {
+      const float4 ad = *reinterpret_cast<const float4*>(add + i);
+      y0 += ad.x; y1 += ad.y; y2 += ad.z; y3 += ad.w;
+    }
+    if (sizeof(OutT) == 4) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(o) + i) = make_float4(y0, y1, y2, y3);
+    } else {
+      uint2 u;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(o) + i) = u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: attention of new queries over cached keys/values (layers.py:93-187), head size 64.
+// One warp per (query row m, head h); 8 lanes x 16 B cover the 128-byte (bf16) head slice of one key, so a
+// warp-wide load touches 4 complete keys; fp32 scores / softmax / accumulation.
+//   b = m / Tq, i = m % Tq; keys of batch b live at rows b * t_stride + t of K / V (row pitch D)
+//   n_keys = causal ? kbase + i + 1 : kbase      (scores scaled by 1/8 = hs^-1/2, layers.py:102)
+// Used for: spatial decode (Tq = 1, kbase = t + 1), depth pass 1 (Tq = 4, kbase = 5), text prefill (causal).
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT_MAX_KEYS = 128;
+constexpr int ATT_WARPS = 8;
+
+template <typename AT>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_kernel(const AT* __restrict__ q, const AT* __restrict__ K, const AT* __restrict__ V, AT* __restrict__ out,
+                 int M, int n_heads, int D, int Tq, int t_stride, int kbase, int causal) {
+  __shared__ float sc[ATT_WARPS][ATT_MAX_KEYS];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * ATT_WARPS + w;
+  if (item >= M * n_heads) return;
+  const int m = item / n_heads, h = item % n_heads;
+  const int b = m / Tq, i = m % Tq;
+  const int n_keys = causal ? (kbase + i + 1) : kbase;
+  const int g = lane >> 3, c = lane & 7;
+
+  float qv[8];
+  load8(q + static_cast<size_t>(m) * D + h * 64 + c * 8, qv);
+  const AT* Kb = K + static_cast<size_t>(b) * t_stride * D + h * 64 + c * 8;
+  const AT* Vb = V + static_cast<size_t>(b) * t_stride * D + h * 64 + c * 8;
+
+#pragma unroll 4
+  for (int t = g; t < n_keys; t += 4) {
+    float kv[8];
+    load8_stream(Kb + static_cast<size_t>(t) * D, kv);
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s = fmaf(qv[e], kv[e] * 0.125f, s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (c == 0) sc[w][t] = s;
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int t = lane; t < n_keys; t += 32) mx = fmaxf(mx, sc[w][t]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int t = lane; t < n_keys; t += 32) {
+    const float e = expf(sc[w][t] - mx);
+    sc[w][t] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.0f / sum;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 4
+  for (int t = g; t < n_keys; t += 4) {
+    float vv[8];
+    load8_stream(Vb + static_cast<size_t>(t) * D, vv);
+    const float p = sc[w][t] * inv;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vv[e], acc[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+  }
+  if (g == 0) store8(out + static_cast<size_t>(m) * D + h * 64 + c * 8, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10: Sample(z; T, k, p) fused into one kernel per logits row (hierarchical_ar.py:762-785,
+// utils/sampling.py:12-37): z /= T; keep z >= k-th largest (ties kept); softmax; nucleus cut on the
+// *preceding* cumulative mass; renormalise; one categorical draw.
+// No sort: the k-th largest logit and the nucleus boundary are found by bitwise bisection on the
+// order-preserving integer image of the floats (32 block-wide count / mass reductions each); the draw is an
+// inverse-CDF walk in index order with ONE Philox4x32-10 uniform per row.
+// Thread t owns the contiguous slice [t * ipt, (t + 1) * ipt) of the row (registers).
+// ------------------------------------------------------------------------------------------------
+constexpr int SMP_IPT = 32;
+
+struct SampleArgs {
+  const float* logits;  // [R, ldl]
+  int ldl, V, R;
+  int rows_per_b;       // 1 (top) | 4 (bottom)
+  int slot0;            // 0 (top) | 1 (bottom): Philox slot / logits_out slot of the first row of a batch element
+  const hq_sampling_params* sp;  // device copy
+  int pos, S;
+  int64_t* codes_top;   // [B, S]      written when rows_per_b == 1
+  int64_t* codes_bot;   // [B, S, 4]   written when rows_per_b == 4
+  int forced;           // 1: codes are given (teacher forcing): leave them untouched
+  float* logits_out;    // optional [B, S, 5, Vmax]
+  int Vmax;
+  float* probs_out;     // optional [R, V] (debug)
+  int64_t* flat_out;    // optional [R] (debug)
+  // debug overrides (sp == nullptr)
+  float temperature, top_p; int top_k; uint64_t seed, row_offset;
+};
+
+__device__ __forceinline__ uint32_t float_order_key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T identity, T* scratch /*[33]*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();  // every thread has consumed scratch[32] of the previous reduction
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    T r = lane < nw ? scratch[lane] : identity;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = op(r, __shfl_xor_sync(0xffffffffu, r, o));
+    if (lane == 0) scratch[32] = r;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+struct OpSumF { __device__ float operator()(float a, float b) const { return a + b; } };
+struct OpMaxF { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct OpSumI { __device__ int operator()(int a, int b) const { return a + b; } };
+struct OpMaxI { __device__ int operator()(int a, int b) const { return a > b ? a : b; } };
+struct OpMinI { __device__ int operator()(int a, int b) const { return a < b ? a : b; } };
+
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR) sample_kernel(SampleArgs a) {
+  __shared__ float fscratch[33];
+  __shared__ int iscratch[33];
+  __shared__ float wsum[33];
+  const int r = blockIdx.x;
+  const int b = r / a.rows_per_b, jj = r % a.rows_per_b;
+  const int slot = a.slot0 + jj;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int V = a.V;
+  int ipt = (V + nthr - 1) / nthr;
+  ipt = (ipt + 3) & ~3;
+  const int base = tid * ipt;
+  const float* row = a.logits + static_cast<size_t>(r) * a.ldl;
+
+  float temperature, top_p; int top_k; uint64_t seed, row_offset;
+  if (a.sp != nullptr) {
+    const bool top = (a.rows_per_b == 1);
+    temperature = top ? a.sp->temperature_top : a.sp->temperature_bot;
+    top_p = top ? a.sp->top_p_top : a.sp->top_p_bot;
+    top_k = top ? a.sp->top_k_top : a.sp->top_k_bot;
+    seed = a.sp->seed; row_offset = a.sp->row_offset;
+  } else {
+    temperature = a.temperature; top_p = a.top_p; top_k = a.top_k; seed = a.seed; row_offset = a.row_offset;
+  }
+
+  float z[SMP_IPT];
+#pragma unroll
+  for (int i = 0; i < SMP_IPT; i += 4) {
+    float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (i < ipt && base + i < V) v = *reinterpret_cast<const float4*>(row + base + i);
+    z[i] = v.x; z[i + 1] = v.y; z[i + 2] = v.z; z[i + 3] = v.w;
+  }
+  if (a.logits_out != nullptr) {
+    float* lo = a.logits_out + ((static_cast<size_t>(b) * a.S + a.pos) * 5 + slot) * a.Vmax;
+#pragma unroll
+    for (int i = 0; i < SMP_IPT; ++i)
+      if (i < ipt && base + i < V) lo[base + i] = z[i];
+  }
+  if (a.forced) return;
+
+#pragma unroll
+  for (int i = 0; i < SMP_IPT; ++i) z[i] = z[i] / temperature;   // -inf padding stays -inf (T > 0)
+
+  int64_t* dst = a.flat_out != nullptr
+                     ? a.flat_out + r
+                     : (a.rows_per_b == 1 ? a.codes_top + static_cast<size_t>(b) * a.S + a.pos
+                                          : a.codes_bot + (static_cast<size_t>(b) * a.S + a.pos) * 4 + jj);
+
+  // ---- greedy: lowest index among the maxima ----
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < SMP_IPT; ++i) mx = fmaxf(mx, z[i]);
+  mx = block_reduce(mx, OpMaxF(), -INFINITY, fscratch);
+  if (top_k == 1) {
+    int idx = 0x7fffffff;
+#pragma unroll
+    for (int i = SMP_IPT - 1; i >= 0; --i)
+      if (i < ipt && base + i < V && z[i] == mx) idx = base + i;
+    idx = block_reduce(idx, OpMinI(), 0x7fffffff, iscratch);
+    if (tid == 0) *dst = idx;
+    if (a.probs_out != nullptr) {
+#pragma unroll
+      for (int i = 0; i < SMP_IPT; ++i)
+        if (i < ipt && base + i < V) a.probs_out[static_cast<size_t>(r) * V + base + i] = (base + i == idx) ? 1.f : 0.f;
+    }
+    return;
+  }
+
+  // ---- top-k: threshold = k-th largest value, ties kept (sampling.py:17-18) ----
+  if (top_k > 0 && top_k < V) {
+    uint32_t thr = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = thr | (1u << bit);
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < SMP_IPT; ++i) cnt += (float_order_key(z[i]) >= cand) ? 1 : 0;
+      cnt = block_reduce(cnt, OpSumI(), 0, iscratch);
+      if (cnt >= top_k) thr = cand;
+    }
+#pragma unroll
+    for (int i = 0; i < SMP_IPT; ++i)
+      if (float_order_key(z[i]) < thr) z[i] = -INFINITY;
+  }
+
+  // ---- softmax numerators (F.softmax, hierarchical_ar.py:765) ----
+  float wgt[SMP_IPT];
+  float lsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < SMP_IPT; ++i) {
+    wgt[i] = (z[i] == -INFINITY) ? 0.f : expf(z[i] - mx);
+    lsum += wgt[i];
+  }
+  const float Z = block_reduce(lsum, OpSumF(), 0.f, fscratch);
+  const float invZ = 1.0f / Z;
+#pragma unroll
+  for (int i = 0; i < SMP_IPT; ++i) wgt[i] *= invZ;   // probabilities
+
+  // ---- top-p (sampling.py:22-37): keep the smallest upper set {p_i >= c*} whose mass reaches p; among
+  //      entries equal to c* keep, in index order, those whose preceding cumulative mass is still < p ----
+  if (top_p > 0.f && top_p < 1.f) {
+    uint32_t cstar = 0;
+    for (int bit = 30; bit >= 0; --bit) {   // probabilities are non-negative: sign bit never set
+      const uint32_t cand = cstar | (1u << bit);
+      float mass = 0.f;
+#pragma unroll
+      for (int i = 0; i < SMP_IPT; ++i) mass += (__float_as_uint(wgt[i]) >= cand) ? wgt[i] : 0.f;
+      mass = block_reduce(mass, OpSumF(), 0.f, fscratch);
+      if (mass >= top_p) cstar = cand;
+    }
+    float above = 0.f;
+    int ties = 0;
+#pragma unroll
+    for (int i = 0; i < SMP_IPT; ++i) {
+      const uint32_t u = __float_as_uint(wgt[i]);
+      above += (u > cstar) ? wgt[i] : 0.f;
+      ties += (u == cstar && wgt[i] > 0.f) ? 1 : 0;
+    }
+    above = block_reduce(above, OpSumF(), 0.f, fscratch);
+    const int n_ties = block_reduce(ties, OpSumI(), 0, iscratch);
+    const float vstar = __uint_as_float(cstar);
+    int keep_ties = 0;   // number of boundary-valued entries whose preceding mass above + m * v* is < p
+    {
+      float cum = above;
+      while (keep_ties < n_ties && cum < top_p) { ++keep_ties; cum += vstar; }
+      if (keep_ties == 0) keep_ties = 1;   // the first sorted entry is always kept
+    }
+    // exclusive prefix of tie counts across threads (only matters when some ties are cut)
+    int tie_before = 0;
+    if (keep_ties < n_ties) {
+      const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+      int incl = ties;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      __syncthreads();
+      if (lane == 31) iscratch[w] = incl;
+      __syncthreads();
+      int woff = 0;
+      for (int k2 = 0; k2 < w && k2 < nw; ++k2) woff += iscratch[k2];
+      tie_before = woff + incl - ties;
+      __syncthreads();
+    }
+    float ksum = 0.f;
+#pragma unroll
+    for (int i = 0; i < SMP_IPT; ++i) {
+      const uint32_t u = __float_as_uint(wgt[i]);
+      bool keep = u > cstar;
+      if (u == cstar && wgt[i] > 0.f) { keep = tie_before < keep_ties; ++tie_before; }
+      if (!keep) wgt[i] = 0.f;
+      ksum += wgt[i];
+    }
+    ksum = block_reduce(ksum, OpSumF(), 0.f, fscratch);
+    const float inv = 1.0f / ksum;
+#pragma unroll
+    for (int i = 0; i < SMP_IPT; ++i) wgt[i] *= inv;   // renormalise (sampling.py:36)
+  }
+  if (a.probs_out != nullptr) {
+#pragma unroll
+    for (int i = 0; i < SMP_IPT; ++i)
+      if (i < ipt && base + i < V) a.probs_out[static_cast<size_t>(r) * V + base + i] = wgt[i];
+  }
+
+  // ---- categorical draw: inverse CDF in index order, one Philox uniform per row ----
+  float local = 0.f;
+#pragma unroll
+  for (int i = 0; i < SMP_IPT; ++i) local += wgt[i];
+  float excl, total;
+  {
+    const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
+    float incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    __syncthreads();
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    float woff = 0.f, tot = 0.f;
+    for (int k2 = 0; k2 < nw; ++k2) {
+      if (k2 < w) woff += wsum[k2];
+      tot += wsum[k2];
+    }
+    float prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) prev = 0.f;
+    excl = woff + prev;
+    total = tot;
+  }
+  const uint64_t grow = row_offset + static_cast<uint64_t>(b);
+  uint32_t rnd[4];
+  philox4x32_10(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(grow),
+                static_cast<uint32_t>(grow >> 32), static_cast<uint32_t>(a.pos), static_cast<uint32_t>(slot), rnd);
+  const float target = u01_from_bits(rnd[0]) * total;
+  int cand = -1;
+  float run = excl;
+#pragma unroll
+  for (int i = 0; i < SMP_IPT; ++i) {
+    if (wgt[i] > 0.f && run <= target) cand = base + i;
+    run += wgt[i];
+  }
+  cand = block_reduce(cand, OpMaxI(), -1, iscratch);
+  if (tid == 0) *dst = cand;
+}
+
+}  // namespace hq

@@ -1,0 +1,186 @@
+/*
+ * hqgraft.h - C ABI of libhqgraft.so: the B200 (sm_100a) engine behind HQ-Transformer's
+ * locally hierarchical autoregressive sampling loop.
+ *
+ * The reference (kakaobrain/hqtransformer) is pure Python and has no FFI; the boundary it exposes
+ * for this path is Python-level.  Each entry point below states which
+ * reference interface it stands behind (paths relative to the reference root).  The Python host
+ * (hqtransformer_b200/) binds these with ctypes and re-exposes the reference's own call
+ * signatures; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an int status (HQ_OK == 0); nothing throws across the boundary;
+ *     hq_last_error() gives the message of the last failure (per ctx, or global when ctx==NULL);
+ *   - plain pointers and sizes only; all tensors are caller-owned; device pointers must stay valid
+ *     until the work enqueued on `stream` has completed; hq_run is asynchronous on `stream`;
+ *   - a ctx belongs to one GPU and is not thread-safe;
+ *   - sm_100a only, no CPU fallback: hq_create fails on any other device.
+ */
+#ifndef HQGRAFT_H_
+#define HQGRAFT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HQ_ABI_VERSION 1
+
+enum hq_status {
+  HQ_OK = 0,
+  HQ_ERR_INVALID = 1,      /* bad argument / shape / name */
+  HQ_ERR_CUDA = 2,         /* CUDA runtime or driver error */
+  HQ_ERR_UNSUPPORTED = 3,  /* device is not sm_100, or config outside the supported envelope */
+  HQ_ERR_STATE = 4         /* call order (e.g. hq_run before every parameter was loaded) */
+};
+
+enum hq_cond_kind { HQ_COND_CLS = 0, HQ_COND_TXT = 1, HQ_COND_UNCOND = 2 };
+
+/* HQ_PREC_BF16: bf16 weights / GEMM inputs / KV cache, fp32 accumulate, residual, LayerNorm, softmax
+ *               (tcgen05 + TMA GEMMs) - what `use_fp16=True` selects in the reference
+ *               (torch.cuda.amp.autocast, hierarchical_ar.py:445).
+ * HQ_PREC_FP32: everything fp32 on CUDA cores - the reference's `use_fp16=False`; used for the
+ *               bit-exact greedy parity tests. */
+enum hq_precision { HQ_PREC_BF16 = 0, HQ_PREC_FP32 = 1 };
+
+enum hq_dtype { HQ_F32 = 0, HQ_BF16 = 1, HQ_F16 = 2 };
+
+/* Architecture of an iHQGPT(model_type='parallel', embedding_type='transformer1', position_embedding='1d')
+ * - constructor arguments at hqvae/models/stage2/hierarchical_ar.py:24-216, YAML fields at
+ * hqvae/utils/config2.py:49-105. */
+typedef struct hq_config {
+  int32_t embed_dim;       /* hparams.embed_dim (multiple of 64; head size must be 64) */
+  int32_t n_heads;         /* hparams.n_heads */
+  int32_t n_layers;        /* hparams.n_layers (spatial transformer) */
+  int32_t n_layers_depth;  /* hparams_dec.n_layers, 4 when hparams_dec is absent (:150-153) */
+  int32_t vocab_top;       /* vocab_size_top */
+  int32_t vocab_bot;       /* vocab_size_bot */
+  int32_t vocab_txt;       /* vocab_size_txt (HQ_COND_TXT only) */
+  int32_t n_classes;       /* hparams.n_classes (HQ_COND_CLS only) */
+  int32_t ctx_len_img;     /* rows of pos_emb_top */
+  int32_t ctx_len_txt;     /* text prefix length (HQ_COND_TXT only) */
+  int32_t cond_kind;       /* hq_cond_kind */
+  int32_t precision;       /* hq_precision */
+  int32_t max_seq_len;     /* number of top positions a run may cover (64 for 8x8) */
+  int32_t use_cuda_graph;  /* 1: capture each run shape once and replay it; 0: plain stream launches */
+} hq_config;
+
+/* Arguments of Sample(z; T, k, p) - hierarchical_ar.py:762-785 with utils/sampling.py:12-37.
+ * top_k <= 0 means None (no top-k cut); top_p <= 0 or >= 1 means no nucleus cut.
+ * top_k == 1 is greedy: the lowest index among the maxima (the reference draws randomly among
+ * exact ties).
+ * Every draw uses Philox4x32-10 keyed by `seed` with counter (row_offset + row, position, slot),
+ * so results do not depend on how a batch is sharded over GPUs. */
+typedef struct hq_sampling_params {
+  int32_t top_k_top;
+  int32_t top_k_bot;
+  float top_p_top;
+  float top_p_bot;
+  float temperature_top;   /* softmax_temperature[0] */
+  float temperature_bot;   /* softmax_temperature[1] */
+  uint64_t seed;
+  uint64_t row_offset;     /* global index of this shard's first row */
+} hq_sampling_params;
+
+/* One call of the sampling loop over top positions [pos_begin, pos_end).
+ * Replaces the body of `sampling_ihqgpt` (hqvae/utils/sampling.py:164-237) and, with
+ * pos_end == pos_begin + 1, one `iHQGPT.sampling_step` (hierarchical_ar.py:428-480).
+ * pos_begin == 0 starts a new batch (resets the KV cache); pos_begin > 0 continues the batch whose
+ * codes for positions < pos_begin are read from codes_top / codes_bot. */
+typedef struct hq_run_args {
+  int32_t batch;             /* B <= max_batch */
+  int32_t seq_len;           /* S: row stride of the code / logits arrays (<= max_seq_len) */
+  int32_t pos_begin;
+  int32_t pos_end;
+  const int64_t* cond;       /* [B] class ids | [B, ctx_len_txt] text ids | NULL (uncond) */
+  const float* sos;          /* optional [B, T0, D] fp32 start embedding overriding `cond`
+                                (T0 = ctx_len_txt for text, else 1) - the `sos` argument of
+                                sampling_step (hierarchical_ar.py:430) */
+  const int64_t* given_top;  /* optional [B, S]: forced top codes (given_top_code, sampling.py:205-208) */
+  const int64_t* given_bot;  /* optional [B, S, 4]: forced bottom codes (teacher forcing, parity only) */
+  int64_t* codes_top;        /* in/out [B, S] */
+  int64_t* codes_bot;        /* in/out [B, S, 4], within-stack order j = kh*2 + kw */
+  float* logits;             /* optional out [B, S, 5, max(vocab_top, vocab_bot)] raw head outputs */
+  hq_sampling_params sampling;
+} hq_run_args;
+
+typedef struct hq_ctx hq_ctx;
+
+int hq_abi_version(void);
+
+/* Message of the last failure on `ctx` (or of the last failed hq_create when ctx == NULL). */
+const char* hq_last_error(const hq_ctx* ctx);
+
+/* Allocates the weight arena, the KV cache ([L][B][T][D] keys and values), workspaces and TMA
+ * descriptors on `device` for batches of up to `max_batch` rows.
+ * Stands behind `iHQGPT.__init__` (hierarchical_ar.py:24-216) followed by `.to('cuda')`
+ * (sampling_hqmodel.py:80, measure_throughput/__main__.py:56). */
+int hq_create(const hq_config* cfg, int device, int max_batch, hq_ctx** out);
+
+int hq_destroy(hq_ctx* ctx);
+
+/* Re-sizes the batch-dependent state (KV cache, activations, code buffers) for batches of up to
+ * `max_batch` rows; parameters stay loaded.  The reference allocates this state implicitly on every
+ * call (`past` list of tensors, sampling.py:227-231); here it is explicit and reused. */
+int hq_reserve_batch(hq_ctx* ctx, int max_batch);
+int hq_max_batch(const hq_ctx* ctx);
+
+/* Copies one parameter into the engine layout (q/k/v fused to [3D, D]; GEMM weights cast to bf16 in
+ * HQ_PREC_BF16).  `name` is the reference state_dict key without the 'stage2.' prefix, e.g.
+ * "blocks.3.attn.query.weight", "depths.0.mlp.2.bias", "tok_emb_top.weight", "sos_depth", "head_bot.weight"
+ * (module definitions hierarchical_ar.py:63-209, layers.py:43-52, 290-317).
+ * Stands behind `load_state_dict(strict=True)` (sampling_hqmodel.py:79): unknown names and wrong
+ * shapes are errors.  `data` may be a host (is_device == 0) or device pointer; the call is synchronous. */
+int hq_load_param(hq_ctx* ctx, const char* name, const void* data, int dtype,
+                  const int64_t* shape, int ndim, int is_device);
+
+/* HQ_OK once every parameter the config requires has been loaded; otherwise HQ_ERR_STATE and
+ * hq_last_error() lists the missing names (strict=True semantics). */
+int hq_params_complete(hq_ctx* ctx);
+
+/* The sampling loop.  All pointers in `args` are DEVICE pointers; asynchronous on `stream`
+ * (a cudaStream_t; NULL = legacy default stream). */
+int hq_run(hq_ctx* ctx, const hq_run_args* args, void* stream);
+
+/* Same, but every pointer in `args` is a HOST pointer: inputs are copied host->device, the loop
+ * runs, and the code grids (and logits, if requested) are copied back before the call returns.
+ * This is the end-to-end call the reference scripts make (sampling_hqmodel.py:106-117 receives
+ * host-visible code tensors it then rearranges and pickles). */
+int hq_run_host(hq_ctx* ctx, const hq_run_args* args);
+
+/* Number of kernel launches enqueued by the last hq_run / hq_run_host (graph nodes when replayed). */
+int64_t hq_last_launch_count(const hq_ctx* ctx);
+
+/* Bytes of device memory owned by the ctx (weights + KV cache + workspaces). */
+size_t hq_device_bytes(const hq_ctx* ctx);
+
+/* ---- test / measurement hooks (used by tests/ and bench.py, not by the sampling entry points) ---- */
+
+/* C[M,N] = A[M,K] * W[N,K]^T through the same tcgen05/TMA kernel the sampler uses (prec == HQ_PREC_BF16,
+ * A and W bf16) or the fp32 CUDA-core kernel (HQ_PREC_FP32, A and W fp32); C fp32; device pointers. */
+int hq_debug_gemm(int prec, const void* A, const void* W, float* C, int M, int N, int K, void* stream);
+
+/* Philox4x32-10 block for (seed, counter) - known-answer test of the RNG; host pointers. */
+int hq_debug_philox(uint64_t seed, const uint32_t counter[4], uint32_t out[4]);
+
+/* Sample(z; T, k, p) on device logits [R, V] (fp32): writes int64 codes [R]; `slot` selects the
+ * Philox counter lane, row r uses counter (row_offset + r, position, slot). */
+int hq_debug_sample(const float* logits, int R, int V, float temperature, int top_k, float top_p,
+                    uint64_t seed, uint64_t row_offset, int position, int slot,
+                    int64_t* out_codes, float* out_probs /* optional [R, V] */, void* stream);
+
+/* Times the single-query KV-cache attention kernel alone at cache length `n_keys` for batch B on the
+ * ctx's cache (events on `stream`); returns mean microseconds over `iters` launches in *usec. */
+int hq_bench_attention(hq_ctx* ctx, int B, int n_keys, int iters, float* usec, void* stream);
+
+/* Times one GEMM family of the loop alone on the ctx's own weights and buffers: kind 0 = fused qkv [3D, D],
+ * 1 = attention proj [D, D], 2 = mlp fc1 [4D, D], 3 = mlp fc2 [D, 4D], 4 = head_top [V, D]; M rows.  L2 is evicted
+ * between launches (256 MB write) and layers are cycled, so weights stream from HBM as in the real loop. */
+int hq_bench_gemm(hq_ctx* ctx, int kind, int M, int iters, float* usec, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HQGRAFT_H_ */

@@ -1,0 +1,125 @@
+"""-m gpu: kernel-level parity (GEMM, Philox, Sample) through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hq_oracle as O
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 128), (256, 4608, 1536), (256, 1536, 6144),
+                                   (5, 256, 128), (20, 384, 128), (1024, 8192, 1536), (333, 1536, 1536), (64, 64, 512)])
+def test_gemm_tcgen05_matches_fp32_matmul(M, N, K):
+    """bf16 x bf16 -> fp32 through TMA + tcgen05: exact products, fp32 accumulation -> only summation-order error."""
+    from hqtransformer_b200.engine import debug_gemm
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    C = debug_gemm(A, W)
+    ref = A.double() @ W.double().t()
+    err = (C.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-5 * max(scale, 1.0) * (K / 64) ** 0.5 + 1e-5, (err, scale)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 128, 16), (5, 256, 128), (100, 1032, 256), (257, 384, 1536)])
+def test_gemm_fp32_matches_matmul(M, N, K):
+    from hqtransformer_b200.engine import debug_gemm
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, device="cuda")
+    W = torch.randn(N, K, generator=g, device="cuda") * 0.05
+    C = debug_gemm(A, W)
+    ref = A.double() @ W.double().t()
+    assert (C.double() - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1.0)
+
+
+def _ref_probs(logits, T, k, p):
+    z = logits / T
+    z = O.cutoff_topk_logits(z, k)
+    pr = torch.softmax(z, dim=-1)
+    return O.cutoff_topp_probs(pr, p)
+
+
+@pytest.mark.parametrize("V", [256, 1024, 8192])
+@pytest.mark.parametrize("T,k,p", [(1.0, None, None), (0.9, 64, None), (1.0, None, 0.9), (0.95, 100, 0.8),
+                                   (1.3, 2048, 0.95), (1.0, 5, 0.5)])
+def test_sample_probs_match_oracle_filters(V, T, k, p):
+    """Filtered + renormalised distribution of the fused kernel == cutoff_topk_logits/softmax/cutoff_topp_probs."""
+    from hqtransformer_b200.engine import debug_sample
+    if k is not None and k >= V:
+        pytest.skip("k >= V")
+    g = torch.Generator().manual_seed(V + (k or 0))
+    logits = torch.randn(16, V, generator=g) * 2.0
+    _, probs = debug_sample(logits.cuda(), T, k, p, seed=1, return_probs=True)
+    ref = _ref_probs(logits, T, k, p)
+    probs = probs.cpu()
+    assert torch.equal(probs > 0, ref > 0), "kept sets differ"
+    assert torch.allclose(probs, ref, rtol=2e-5, atol=1e-8)
+
+
+def test_sample_filters_match_reference_golden():
+    """Known answers produced by the reference's own cutoff_topk_logits / cutoff_topp_probs (tests/golden/filters.npz)."""
+    import hqtransformer_b200 as H
+    g, _ = load_golden("filters.npz")
+    x = torch.from_numpy(g["topk_in"]).cuda()
+    for k in (1, 2, 5, 64):
+        out = H.cutoff_topk_logits(x, k).cpu().numpy()
+        assert np.array_equal(np.isinf(out), np.isinf(g[f"topk_{k}"])), k
+        assert np.array_equal(out[~np.isinf(out)], g[f"topk_{k}"][~np.isinf(out)])
+    pin = torch.from_numpy(g["topp_in"]).cuda()
+    for p in (0.5, 0.8, 0.95):
+        out = H.cutoff_topp_probs(pin, p).cpu().numpy()
+        want = g[f"topp_{p}"]
+        assert np.array_equal(out > 0, want > 0), p
+        np.testing.assert_allclose(out, want, rtol=1e-4, atol=1e-9)
+    # 4-entry cases incl. exact ties at the nucleus boundary ([.25]*4, p=.5 keeps the first two in index order);
+    # (row 0, p=0.8) sits exactly on the boundary (0.5 + 0.3 vs 0.8 in fp32) and is left out
+    small = torch.from_numpy(g["topp_small_in"]).cuda()
+    for p, rows in ((0.5, [0, 1, 2]), (0.8, [1, 2]), (0.95, [0, 1, 2])):
+        out = H.cutoff_topp_probs(small, p).cpu().numpy()
+        np.testing.assert_allclose(out[rows], g[f"topp_small_{p}"][rows], rtol=1e-5, atol=1e-9)
+
+
+def test_sample_greedy_is_lowest_index_argmax():
+    from hqtransformer_b200.engine import debug_sample
+    logits = torch.randn(32, 1024)
+    logits[3, 700] = logits[3, 17] = 50.0        # exact tie: lowest index wins
+    codes = debug_sample(logits.cuda(), 1.0, 1, 1.0).cpu()
+    want = logits.argmax(-1)
+    want[3] = 17
+    assert torch.equal(codes, want)
+
+
+def test_sample_inverse_cdf_matches_host_restatement_and_frequencies():
+    """The draw is idx = first i with cumsum(p)_i > u * total, u from Philox4x32-10(seed; row, pos, slot).
+    (1) exact agreement with a numpy restatement using the same u; (2) chi-square of the empirical frequencies
+    against the filtered distribution (the reference's torch.multinomial samples the same distribution)."""
+    from hqtransformer_b200.engine import debug_philox, debug_sample
+    V, R = 256, 4096
+    g = torch.Generator().manual_seed(5)
+    row = torch.randn(1, V, generator=g) * 1.5
+    logits = row.repeat(R, 1).contiguous()
+    T, k, p = 0.9, 40, 0.9
+    codes, probs = debug_sample(logits.cuda(), T, k, p, seed=1234, row_offset=10, position=3, slot=2, return_probs=True)
+    codes, probs = codes.cpu().numpy(), probs.cpu().numpy().astype(np.float64)
+    # (1)
+    mism = 0
+    for r in range(0, R, 16):
+        u32 = debug_philox(1234, [10 + r, 0, 3, 2])[0]
+        u = ((u32 >> 9) + 0.5) / 8388608.0
+        cdf = np.cumsum(probs[r])
+        idx = int(np.searchsorted(cdf, u * cdf[-1], side="right"))
+        while probs[r][idx] == 0:
+            idx += 1
+        mism += int(idx != codes[r])
+    assert mism <= 1, mism      # fp32 vs fp64 prefix sums may disagree on a knife edge
+    # (2)
+    pr = probs[0] / probs[0].sum()
+    assert set(np.unique(codes)) <= set(np.nonzero(pr)[0])
+    counts = np.bincount(codes, minlength=V).astype(np.float64)
+    keep = pr * R >= 5
+    chi2 = (((counts - pr * R) ** 2)[keep] / (pr * R)[keep]).sum()
+    dof = keep.sum() - 1
+    assert chi2 < dof + 5 * (2 * dof) ** 0.5, (chi2, dof)
