@@ -1,0 +1,118 @@
+"""not gpu: the C-ABI library loads and exports every declared symbol; host-side logic (config loading, sharding,
+argument checks) behaves like the reference's; nothing here launches a kernel."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    import ctypes
+    from hqtransformer_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "hqgraft.h")).read()
+    declared = set(re.findall(r"^\s*(?:const\s+)?(?:int|int64_t|size_t|char\*|const char\*)\s+\*?(hq_[a-z_0-9]+)\s*\(", header, re.M))
+    assert len(declared) >= 17, declared
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} not exported"
+    assert lib.hq_abi_version() == _lib.ABI_VERSION
+    m = re.search(r"#define HQ_ABI_VERSION (\d+)", header)
+    assert int(m.group(1)) == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_header_sizes():
+    import ctypes
+    from hqtransformer_b200 import _lib
+    assert ctypes.sizeof(_lib.HQConfig) == 14 * 4
+    assert ctypes.sizeof(_lib.HQSamplingParams) == 40
+    assert ctypes.sizeof(_lib.HQRunArgs) == 16 + 7 * 8 + 40
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10 (the engine's counter-based RNG; host build of the same code)."""
+    from hqtransformer_b200.engine import debug_philox
+    assert debug_philox(0, [0, 0, 0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert debug_philox(0xffffffffffffffff, [0xffffffff] * 4) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert debug_philox(0x299f31d0a4093822, [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_create_fails_loudly_without_gpu():
+    import hqtransformer_b200 as H
+    with pytest.raises(H.HQError):
+        H.Engine(embed_dim=128, n_heads=2, n_layers=1, n_layers_depth=1, vocab_top=64, vocab_bot=64, n_classes=10,
+                 ctx_len_img=64, precision="fp32", max_batch=2)
+    with pytest.raises(ValueError, match="CUDA"):
+        H.Engine(embed_dim=128, n_heads=2, n_layers=1, n_layers_depth=1, vocab_top=64, vocab_bot=64, device="cpu")
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "hqtransformer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_config_loader_restates_reference_defaults():
+    import hqtransformer_b200 as H
+    from hqtransformer_b200.config import engine_kwargs
+    cfg = H.load_config(os.path.join(ROOT, "hqtransformer_b200", "configs", "imagenet_l12.yaml"))
+    s2 = cfg.stage2
+    assert s2.ratio_bot2top == 4 and s2.vocab_size_txt == 16384 and s2.hparams_dec is None      # config2.py:85-105
+    hp = s2.hparams
+    assert (hp.embed_dim, hp.n_layers, hp.n_heads, hp.ctx_len_img, hp.n_classes) == (1536, 12, 24, 256, 1000)
+    assert hp.position_embedding == "1d" and hp.mlp_bias and hp.attn_bias and hp.ctx_len_txt == 64   # config2.py:49-71
+    kw = engine_kwargs(cfg)
+    assert kw["model_type"] == "parallel" and kw["use_cls_cond"] and not kw["use_txt_cond"]
+    l42 = H.load_config(os.path.join(ROOT, "hqtransformer_b200", "configs", "imagenet_l42.yaml"))
+    assert l42.stage2.hparams.n_layers == 42 and l42.stage2.hparams_dec.n_layers == 6
+    with pytest.raises(KeyError):
+        H.merge_config({"stage2": {"type": "hq-transformer/parallel", "hparams": {"embed_dimm": 3}}})
+    with pytest.raises(NotImplementedError):
+        engine_kwargs(H.merge_config({"stage2": {"type": "top", "hparams": {}}}))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/configs"), reason="reference tree only exists in the build container")
+def test_reference_yaml_files_load_unchanged():
+    import hqtransformer_b200 as H
+    from hqtransformer_b200.config import engine_kwargs
+    base = "/root/reference/configs/master/stage2"
+    for rel, L, Ld in (("imagenet/hqtransformer-embtrans1-soft1-layer12-top8x8.yaml", 12, None),
+                       ("imagenet/hqtransformer-embtrans1-soft1-layer42-top8x8.yaml", 42, 6),
+                       ("cc15m/hqtransformer-embtrans1-soft1-layer12-top8x8-cc15m.yaml", 12, None)):
+        kw = engine_kwargs(H.load_config(os.path.join(base, rel)))
+        assert kw["hparams"].n_layers == L and (kw["hparams_dec"].n_layers if kw["hparams_dec"] else None) == Ld
+
+
+def test_shard_range_partitions_the_batch():
+    from hqtransformer_b200.distributed import shard_range
+    for B in (1, 7, 64, 256, 4096, 4097):
+        for W in (1, 2, 4, 8):
+            spans = [shard_range(B, r, W) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_sampling_params_marshalling():
+    from hqtransformer_b200.engine import SamplingParams
+    c = SamplingParams(top_k_top=None, top_p_top=None, top_k_bot=2048, top_p_bot=1.0, temperature_top=0.95,
+                       temperature_bot=0.9, seed=2 ** 64 + 5, row_offset=512).to_c()
+    assert (c.top_k_top, c.top_k_bot) == (0, 2048) and c.top_p_top == 0.0 and c.top_p_bot == 1.0
+    assert c.seed == 5 and c.row_offset == 512 and abs(c.temperature_top - 0.95) < 1e-7
+
+
+def test_graft_entry_build_is_idempotent():
+    import __graft_entry__ as G
+    G.build()
+    assert os.path.isfile(os.path.join(ROOT, "hqtransformer_b200", "libhqgraft.so"))
