@@ -180,16 +180,22 @@ attention_kernel(const AT* __restrict__ q, const AT* __restrict__ K, const AT* _
   const AT* Vb = V + static_cast<size_t>(b) * t_stride * D + h * 64 + c * 8;
 
 #pragma unroll 4
-  for (int t = g; t < n_keys; t += 4) {
+  for (int tb = 0; tb < n_keys; tb += 4) {     // warp-uniform trip count: the shuffles below need all 32 lanes
+    const int t = tb + g;
     float kv[8];
-    load8_stream(Kb + static_cast<size_t>(t) * D, kv);
+    if (t < n_keys) {
+      load8_stream(Kb + static_cast<size_t>(t) * D, kv);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) kv[e] = 0.f;
+    }
     float s = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) s = fmaf(qv[e], kv[e] * 0.125f, s);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (c == 0) sc[w][t] = s;
+    if (c == 0 && t < n_keys) sc[w][t] = s;
   }
   __syncwarp();
   float mx = -INFINITY;
