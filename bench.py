@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--top-p", type=float, default=0.0, help="0 = None")
     ap.add_argument("--temperature", type=float, default=1.0)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=16)
@@ -200,7 +201,7 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
     B = args.batch
     cfg_path = os.path.join(ROOT, "hqtransformer_b200", "configs", CONFIGS[args.model])
     model = H.ImageGPT2.from_config(cfg_path, device=local_rank, precision="bf16", max_batch=B,
-                                    use_cuda_graph=not args.no_graph).eval()
+                                    use_cuda_graph=not args.no_graph, use_pdl=not args.no_pdl).eval()
     s2 = model.stage2
     eng = s2.engine("bf16")
     g = torch.Generator().manual_seed(1234 + rank)
@@ -220,9 +221,15 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
             ct, cb = gather_codes(ct, cb, world * B)     # the path's only collective: all-gather of the code grids
         return ct, cb
 
+    def note(msg):
+        if rank == 0:
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+    note("model built; warming up")
     for i in range(args.warmup):
         step(i)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        note(f"warm-up step {i} done")
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank)
@@ -238,6 +245,7 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
         dist.barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
+    note(f"timed region done: {ms / args.steps:.1f} ms/step")
     launches = eng.last_launch_count * args.steps
     assert int(ct.min()) >= 0 and int(ct.max()) < s2.vocab_size_top and tuple(ct.shape) == (world * B, S)
 
@@ -256,6 +264,7 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
 
     e2e_step(0)
     torch.cuda.synchronize()
+    note("e2e warm-up done")
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -279,7 +288,7 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
                                    f"top_p={args.top_p or None} T={args.temperature}",
                        "model": args.model, "batch_per_gpu": B, "global_batch": world * B, "positions": S,
                        "parallelism": f"batch-sharded x{world}, one all-gather of code grids",
-                       "cuda_graph": not args.no_graph,
+                       "cuda_graph": not args.no_graph, "pdl": not args.no_pdl,
                        "l2": "working set (weights + KV cache > 2 GB) exceeds the 126 MB L2; no explicit flush"},
             "ms_per_top_position": ms / args.steps / S,
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

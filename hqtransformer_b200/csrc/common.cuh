@@ -117,6 +117,46 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          | (static_cast<uint32_t>(M >> 4) << 24);// m_dim
 }
 
+// ------------------------------------------------------------------------------------------------
+// Kernel timeline tracing (hq_trace_run): every loop kernel takes a launch id as its first parameter; when it is
+// >= 0, thread 0 of every CTA folds %globaltimer into [min start, max end] of that launch.  id < 0: no cost.
+// ------------------------------------------------------------------------------------------------
+__device__ unsigned long long* g_hq_trace = nullptr;
+
+struct TraceScope {
+  int id;
+  __device__ __forceinline__ explicit TraceScope(int i) : id(i) {
+#if defined(__CUDA_ARCH__)
+    if (id >= 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      atomicMin(&g_hq_trace[2 * id], t);
+    }
+#endif
+  }
+  __device__ __forceinline__ ~TraceScope() {
+#if defined(__CUDA_ARCH__)
+    if (id >= 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      atomicMax(&g_hq_trace[2 * id + 1], t);
+    }
+#endif
+  }
+};
+
+// Programmatic dependent launch: wait for the producer grid's memory / let the dependent grid start its prologue
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 #if defined(__CUDA_ARCH__)
 // ------------------------------------------------------------------------------------------------
 // mbarrier
@@ -243,6 +283,58 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): both CTAs of a 2-CTA cluster feed one tcgen05.mma of M = 256.
+// PTX forms as in cute/arch/copy_sm100_tma.hpp (SM100_TMA_2SM_LOAD_2D), cute/arch/tmem_allocator_sm100.hpp
+// (Allocator2Sm) and cutlass/arch/barrier.h (umma_arrive_multicast_2x1SM).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load into THIS CTA's shared memory whose transaction bytes are credited to the mbarrier at the same
+// offset in the pair's leader CTA (peer bit of the shared::cluster address cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (128 rows from each CTA) * B^T (N/2 rows from each CTA); issued by ONE thread of the leader
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of `cta_mask` once all prior tcgen05.mma of this thread completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
 #endif  // __CUDA_ARCH__
 
 }  // namespace hq

@@ -43,7 +43,8 @@ static void set_err(hq_ctx* ctx, const char* fmt, ...);
 struct Weight {          // a GEMM weight [N, K] in the precision's storage type
   void* ptr = nullptr;
   int N = 0, K = 0;
-  CUtensorMap map;       // bf16 only: [N, K], box {64, 64}, SWIZZLE_128B
+  CUtensorMap map;       // bf16 only: [N, K], box {64, 64}, SWIZZLE_128B (single-CTA kernel)
+  CUtensorMap map16;     // bf16 only: box {64, 16} (CTA-pair kernel: BN/32 loads per stage per CTA)
 };
 struct ABuf {            // a GEMM A operand buffer [rows_pad, K]
   void* ptr = nullptr;
@@ -67,10 +68,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct GraphKey {
-  int B, S, p0, p1, forced_top, forced_bot, sos_override;
+  int B, S, p0, p1, forced_top, forced_bot, sos_override, tracing;
   bool operator<(const GraphKey& o) const {
-    return std::tie(B, S, p0, p1, forced_top, forced_bot, sos_override) <
-           std::tie(o.B, o.S, o.p0, o.p1, o.forced_top, o.forced_bot, o.sos_override);
+    return std::tie(B, S, p0, p1, forced_top, forced_bot, sos_override, tracing) <
+           std::tie(o.B, o.S, o.p0, o.p1, o.forced_top, o.forced_bot, o.sos_override, o.tracing);
   }
 };
 
@@ -100,6 +101,8 @@ struct hq_ctx {
   ABuf h, att, mlp;
   void* q = nullptr;
   float *x = nullptr, *yd = nullptr, *logits = nullptr;
+  float* splitk_ws = nullptr;   // [3][rows][D] fp32 partial sums of split-K fc2 GEMMs (folded in by the next LayerNorm)
+  int ws_rows = 0;
   void *kc = nullptr, *vc = nullptr, *kd = nullptr, *vd = nullptr;
   int64_t *cond = nullptr, *codes_top = nullptr, *codes_bot = nullptr;
   float* sos_override = nullptr;
@@ -111,6 +114,10 @@ struct hq_ctx {
   int64_t launches = 0;
   int64_t last_launches = 0;
   cudaError_t launch_err = cudaSuccess;
+  bool use_pdl = false;
+  bool tracing = false;
+  int trace_cap = 0;
+  std::vector<const char*> trace_tags;
 };
 
 static void set_err(hq_ctx* ctx, const char* fmt, ...) {
@@ -158,7 +165,10 @@ static int alloc_weight(hq_ctx* ctx, Weight* w, int N, int K) {
   w->K = K;
   int rc = dev_alloc(ctx, &w->ptr, static_cast<size_t>(N) * K * ctx->wsize);
   if (rc) return rc;
-  if (ctx->bf16) return make_map(ctx, &w->map, w->ptr, N, K, 64);
+  if (ctx->bf16) {
+    if ((rc = make_map(ctx, &w->map, w->ptr, N, K, 64))) return rc;
+    return make_map(ctx, &w->map16, w->ptr, N, K, 16);
+  }
   return HQ_OK;
 }
 static int alloc_abuf(hq_ctx* ctx, ABuf* a, int rows, int K) {
@@ -230,6 +240,12 @@ static int set_gemm_attrs(hq_ctx* ctx) {
   HQ_SET(64, EPI_QKV) HQ_SET(64, EPI_RESID) HQ_SET(64, EPI_GELU) HQ_SET(64, EPI_F32)
   HQ_SET(128, EPI_QKV) HQ_SET(128, EPI_RESID) HQ_SET(128, EPI_GELU) HQ_SET(128, EPI_F32)
 #undef HQ_SET
+#define HQ_SET2(BN, EPI) \
+  if ((rc = set_smem(ctx, gemm_tc2_kernel<BN, EPI, bf16>, Tc2Cfg<BN>::SMEM_BYTES))) return rc;
+#define HQ_SET2_ALL(BN) HQ_SET2(BN, EPI_QKV) HQ_SET2(BN, EPI_RESID) HQ_SET2(BN, EPI_GELU) HQ_SET2(BN, EPI_F32)
+  HQ_SET2_ALL(32) HQ_SET2_ALL(64) HQ_SET2_ALL(96) HQ_SET2_ALL(128) HQ_SET2_ALL(192) HQ_SET2_ALL(256)
+#undef HQ_SET2_ALL
+#undef HQ_SET2
   return HQ_OK;
 }
 
@@ -312,6 +328,8 @@ static int reserve_impl(hq_ctx* ctx, int max_batch) {
   if ((rc = alloc_f32(ctx, &ctx->x, static_cast<size_t>(Mx) * D))) return rc;
   if ((rc = alloc_f32(ctx, &ctx->yd, static_cast<size_t>(4) * B * D))) return rc;
   if ((rc = alloc_f32(ctx, &ctx->logits, static_cast<size_t>(4) * B * ctx->Vmax))) return rc;
+  ctx->ws_rows = Mmax;
+  if (ctx->bf16 && (rc = alloc_f32(ctx, &ctx->splitk_ws, static_cast<size_t>(3) * Mmax * D))) return rc;
   const size_t kvn = static_cast<size_t>(ctx->L) * B * ctx->Tc * D * ctx->wsize;
   if ((rc = dev_alloc(ctx, &ctx->kc, kvn))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->vc, kvn))) return rc;
@@ -334,6 +352,7 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
   ctx->device = device;
   ctx->max_batch = max_batch;
   ctx->bf16 = cfg->precision == HQ_PREC_BF16;
+  ctx->use_pdl = cfg->use_pdl != 0;
   ctx->wsize = ctx->bf16 ? 2 : 4;
   const int D = ctx->D = cfg->embed_dim;
   ctx->nh = cfg->n_heads;
@@ -549,37 +568,109 @@ static inline void note_launch(hq_ctx* ctx) {
   if (e != cudaSuccess && ctx->launch_err == cudaSuccess) ctx->launch_err = e;
 }
 
-template <int EPI, typename AT>
-static void gemm(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
-                 const EpiParams<AT>& ep);
+
+// ------------------------------------------------------------------------------------------------
+// launch helper: every kernel of the loop goes through cudaLaunchKernelEx so that the programmatic-dependent-launch
+// attribute can be attached (the kernels call griddepcontrol.launch_dependents / .wait themselves).
+// ------------------------------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+static void launch_k(hq_ctx* ctx, cudaStream_t st, const char* tag, void (*kernel)(int, KArgs...), dim3 grid, dim3 block,
+                     size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+  int trace_id = -1;
+  if (ctx->tracing && static_cast<int>(ctx->trace_tags.size()) < ctx->trace_cap) {
+    trace_id = static_cast<int>(ctx->trace_tags.size());
+    ctx->trace_tags.push_back(tag);
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, trace_id, static_cast<KArgs>(args)...);
+  ++ctx->launches;
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess && ctx->launch_err == cudaSuccess) ctx->launch_err = e;
+}
 
 template <int EPI>
-static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mW, int w_row_off, int M,
-                      int N, int K, const EpiParams<bf16>& ep) {
-  const int mt = (M + 127) / 128;
-  const bool wide = (N % 128 == 0) && (mt * (N / 128) >= 120);
-  if (wide) {
-    dim3 grid(N / 128, mt);
-    gemm_tc_kernel<128, EPI, bf16><<<grid, 192, TcCfg<128>::SMEM_BYTES, st>>>(mA, mW, M, N, K, w_row_off, ep);
-  } else {
-    dim3 grid(N / 64, mt);
-    gemm_tc_kernel<64, EPI, bf16><<<grid, 192, TcCfg<64>::SMEM_BYTES, st>>>(mA, mW, M, N, K, w_row_off, ep);
+static const char* gemm_tag(int M) {
+  (void)M;
+  return EPI == EPI_QKV ? "gemm_qkv" : (EPI == EPI_RESID ? "gemm_resid" : (EPI == EPI_GELU ? "gemm_fc1_gelu" : "gemm_head"));
+}
+
+// Width of the CTA-pair tile (256 x BN) for an [M, N] output: one wave of at most 74 pairs if possible, then the
+// cheapest per-k-block cost of max(L2->SM ingest at ~42.6 B/clk/SM, tensor-pipe time) - see DESIGN.md "GEMM tiles".
+static int pick_pair_bn(int M, int N) {
+  static const int cand[6] = {256, 192, 128, 96, 64, 32};
+  const int mt = (M + 255) / 256;
+  int best = 0;
+  double best_cost = 1e30;
+  for (int bn : cand) {
+    if (N % bn != 0) continue;
+    const int pairs = mt * (N / bn);
+    const double waves = static_cast<double>((pairs + 73) / 74);
+    const double ingest = (16384.0 + 64.0 * bn) / 42.6, mma = 2.0 * bn;
+    const double cost = waves * (ingest > mma ? ingest : mma);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
   }
-  note_launch(ctx);
+  return best;
+}
+
+static int g_force_bn = 0;   // tests: hq_debug_gemm may pin the tile width (0 = heuristic, -64 / -128 = single-CTA kernel)
+
+template <int EPI>
+static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mW64,
+                      const CUtensorMap& mW16, int w_row_off, int M, int N, int K, const EpiParams<bf16>& ep,
+                      int splits = 1, int bn_hint = 0) {
+  int bn = g_force_bn ? g_force_bn : bn_hint;
+  if (bn == 0) bn = (M > 128) ? pick_pair_bn(M, N) : 0;
+  if (bn > 0 && N % bn == 0) {
+    dim3 grid(2 * (N / bn), (M + 255) / 256, splits);
+#define HQ_LAUNCH2(BN)                                                                                             \
+  case BN:                                                                                                         \
+    launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc2_kernel<BN, EPI, bf16>, grid, dim3(192), Tc2Cfg<BN>::SMEM_BYTES, mA, mW16, M, N, K,  \
+             w_row_off, ep);                                                                                       \
+    break;
+    switch (bn) {
+      HQ_LAUNCH2(32) HQ_LAUNCH2(64) HQ_LAUNCH2(96) HQ_LAUNCH2(128) HQ_LAUNCH2(192) HQ_LAUNCH2(256)
+      default: ctx->launch_err = cudaErrorInvalidValue;
+    }
+#undef HQ_LAUNCH2
+    return;
+  }
+  const int mt = (M + 127) / 128;
+  const bool wide = bn == -128 || (bn != -64 && (N % 128 == 0) && (mt * (N / 128) >= 120));
+  if (wide) {
+    dim3 grid(N / 128, mt, splits);
+    launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc_kernel<128, EPI, bf16>, grid, dim3(192), TcCfg<128>::SMEM_BYTES, mA, mW64, M, N, K,
+             w_row_off, ep);
+  } else {
+    dim3 grid(N / 64, mt, splits);
+    launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc_kernel<64, EPI, bf16>, grid, dim3(192), TcCfg<64>::SMEM_BYTES, mA, mW64, M, N, K,
+             w_row_off, ep);
+  }
 }
 
 template <int EPI>
 static void gemm_f32(hq_ctx* ctx, cudaStream_t st, const float* A, const float* W, int M, int N, int K,
                      const EpiParams<float>& ep) {
   dim3 grid((N + 127) / 128, (M + 63) / 64);
-  gemm_simt_kernel<EPI><<<grid, 256, 0, st>>>(A, W, M, N, K, ep);
-  note_launch(ctx);
+  launch_k(ctx, st, gemm_tag<EPI>(M), gemm_simt_kernel<EPI>, grid, dim3(256), 0, A, W, M, N, K, ep);
 }
 
 template <int EPI>
 static void gemm_any(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
                      const EpiParams<bf16>& ep) {
-  gemm_bf16<EPI>(ctx, st, A.map, W.map, w_row_off, M, N, K, ep);
+  gemm_bf16<EPI>(ctx, st, A.map, W.map, W.map16, w_row_off, M, N, K, ep);
 }
 template <int EPI>
 static void gemm_any(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
@@ -588,41 +679,70 @@ static void gemm_any(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& 
                 static_cast<const float*>(W.ptr) + static_cast<size_t>(w_row_off) * K, M, N, K, ep);
 }
 
+// Pending split-K partial sums of the last RESID GEMM: the next LayerNorm on that residual stream folds them in.
+struct Fold {
+  const float* partial = nullptr;
+  int n = 0;
+  size_t stride = 0;
+  const float* bias = nullptr;
+};
+
 template <typename AT>
-static void layernorm_act(hq_ctx* ctx, cudaStream_t st, const float* x, const float* g, const float* b, AT* out,
-                          int rows) {
-  layernorm_kernel<AT><<<(rows + 3) / 4, 128, 0, st>>>(x, g, b, nullptr, out, rows, ctx->D, 1, 0);
-  note_launch(ctx);
+static void layernorm_act(hq_ctx* ctx, cudaStream_t st, float* x, const float* g, const float* b, AT* out, int rows,
+                          Fold* fold = nullptr) {
+  Fold f = fold ? *fold : Fold();
+  launch_k(ctx, st, "layernorm", layernorm_kernel<AT>, dim3(rows), dim3(LN_THREADS), 0, x, g, b, nullptr, out, rows,
+           ctx->D, 1, 0, f.partial, f.n, f.stride, f.bias);
+  if (fold) *fold = Fold();
 }
 
 template <typename AT>
 static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, const AT* V, AT* out, int M, int Tq,
                       int t_stride, int kbase, int causal) {
   const int items = M * ctx->nh;
-  attention_kernel<AT><<<(items + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(q, K, V, out, M, ctx->nh, ctx->D,
-                                                                                       Tq, t_stride, kbase, causal);
-  note_launch(ctx);
+  launch_k(ctx, st, Tq == 1 ? "attention_decode" : "attention_multi", attention_kernel<AT>, dim3((items + ATT_WARPS - 1) / ATT_WARPS), dim3(ATT_WARPS * 32), 0, q, K, V,
+           out, M, ctx->nh, ctx->D, Tq, t_stride, kbase, causal);
 }
 
 static void launch_sample(hq_ctx* ctx, cudaStream_t st, const SampleArgs& a) {
-  if (a.V <= 256 * SMP_IPT) sample_kernel<256><<<a.R, 256, 0, st>>>(a);
-  else sample_kernel<1024><<<a.R, 1024, 0, st>>>(a);
-  note_launch(ctx);
+  if (a.V <= 256 * SMP_IPT) launch_k(ctx, st, "sample", sample_kernel<256>, dim3(a.R), dim3(256), 0, a);
+  else launch_k(ctx, st, "sample", sample_kernel<1024>, dim3(a.R), dim3(1024), 0, a);
 }
 
 // One transformer block (layers.py:324-328 / 371-375) on residual stream `x` [M, D].
 //   mode 0: spatial decode / prefill  - q, k, v; attention over the spatial cache
 //   mode 1: depth pass 0              - k, v only (softmax over one key == identity, a = v)
 //   mode 2: depth pass 1              - q, k, v; 4 queries over the 5 depth keys
+static void gemm_fc2_split(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int M, int N, int K, int splits,
+                           bf16*) {
+  EpiParams<bf16> e;
+  memset(&e, 0, sizeof(e));
+  e.outf = ctx->splitk_ws; e.ldo = N; e.split_stride = static_cast<size_t>(ctx->ws_rows) * N;
+  gemm_bf16<EPI_F32>(ctx, st, A.map, W.map, W.map16, 0, M, N, K, e, splits, 64);
+}
+static void gemm_fc2_split(hq_ctx*, cudaStream_t, const ABuf&, const Weight&, int, int, int, int, float*) {}
+
+// Split-K factor for the fc2 GEMM ([M, D] = [M, 4D] x [D, 4D]^T): its K = 4D main loop is the longest serial chain of a
+// block while its D-wide output fills few CTAs, so when the pair grid leaves SMs idle the K range is cut in up to 3
+// slices (grid.z); the slices write fp32 partial sums that the next LayerNorm adds in a fixed order.
+static int pick_fc2_splits(const hq_ctx* ctx, int M, int N, int K) {
+  if (!ctx->bf16 || M <= 128 || getenv("HQ_NO_SPLITK") != nullptr) return 1;
+  const int pairs = ((M + 255) / 256) * (N / 64);
+  const int kb = K / 64;
+  for (int s = 3; s >= 2; --s)
+    if (pairs * s <= 74 && kb % s == 0) return s;
+  return 1;
+}
+
 template <typename AT>
 static void run_block(hq_ctx* ctx, cudaStream_t st, const BlockW& w, float* x, int M, int mode, AT* kdst, AT* vdst,
-                      int rpb, int t_stride, int t0, int n_keys_base, int causal) {
+                      int rpb, int t_stride, int t0, int n_keys_base, int causal, Fold* fold) {
   const int D = ctx->D;
   AT* h = static_cast<AT*>(ctx->h.ptr);
   AT* att = static_cast<AT*>(ctx->att.ptr);
   AT* mlp = static_cast<AT*>(ctx->mlp.ptr);
   AT* q = static_cast<AT*>(ctx->q);
-  layernorm_act<AT>(ctx, st, x, w.ln1g, w.ln1b, h, M);
+  layernorm_act<AT>(ctx, st, x, w.ln1g, w.ln1b, h, M, fold);
   EpiParams<AT> ep;
   memset(&ep, 0, sizeof(ep));
   ep.q = q; ep.kdst = kdst; ep.vdst = vdst; ep.D = D; ep.rpb = rpb; ep.t_stride = t_stride; ep.t0 = t0;
@@ -643,10 +763,19 @@ static void run_block(hq_ctx* ctx, cudaStream_t st, const BlockW& w, float* x, i
   memset(&eg, 0, sizeof(eg));
   eg.bias = w.b1; eg.out = mlp;
   gemm_any<EPI_GELU>(ctx, st, ctx->h, w.fc1, 0, M, 4 * D, D, eg);
-  EpiParams<AT> e2;
-  memset(&e2, 0, sizeof(e2));
-  e2.bias = w.b2; e2.x = x;
-  gemm_any<EPI_RESID>(ctx, st, ctx->mlp, w.fc2, 0, M, D, 4 * D, e2);
+  const int splits = pick_fc2_splits(ctx, M, D, 4 * D);
+  if (splits > 1 && M <= ctx->ws_rows) {
+    gemm_fc2_split(ctx, st, ctx->mlp, w.fc2, M, D, 4 * D, splits, static_cast<AT*>(nullptr));
+    fold->partial = ctx->splitk_ws;
+    fold->n = splits;
+    fold->stride = static_cast<size_t>(ctx->ws_rows) * D;
+    fold->bias = w.b2;
+  } else {
+    EpiParams<AT> e2;
+    memset(&e2, 0, sizeof(e2));
+    e2.bias = w.b2; e2.x = x;
+    gemm_any<EPI_RESID>(ctx, st, ctx->mlp, w.fc2, 0, M, D, 4 * D, e2);
+  }
 }
 
 struct RunFlags {
@@ -669,35 +798,38 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
   const size_t lstride = static_cast<size_t>(ctx->max_batch) * Tc * D;
   const size_t dstride = static_cast<size_t>(ctx->max_batch) * 5 * D;
 
+  // one float4 per thread: every gather of a row is in flight at once (a single memory round trip after the codes)
+  const int eb = (D / 4 + 31) / 32 * 32 > 1024 ? 1024 : (D / 4 + 31) / 32 * 32;
+  Fold fold_x, fold_y;   // split-K partial sums pending on the spatial / depth residual stream
   // ---- K1: input token(s) ----
   if (prefill) {
-    embed_txt_kernel<<<M, 128, 0, st>>>(ctx->x, f.sos_override ? ctx->sos_override : nullptr, ctx->cond, ctx->E_txt,
-                                        ctx->P_txt, T0, D);
+    launch_k(ctx, st, "embed_txt", embed_txt_kernel, dim3(M), dim3(eb), 0, ctx->x, f.sos_override ? ctx->sos_override : nullptr,
+             ctx->cond, ctx->E_txt, ctx->P_txt, T0, D);
   } else {
     EmbedArgs ea;
     ea.x = ctx->x; ea.sos_table = ctx->sos_table; ea.sos_override = f.sos_override ? ctx->sos_override : nullptr;
     ea.cond = ctx->cond; ea.E_top = ctx->E_top; ea.E_bot = ctx->E_bot; ea.P_top = ctx->P_top; ea.P_emb = ctx->P_emb;
     ea.codes_top = ctx->codes_top; ea.codes_bot = ctx->codes_bot; ea.D = D; ea.S = S; ea.pos = pos;
     ea.cond_kind = ctx->cfg.cond_kind;
-    embed_kernel<<<B, 128, 0, st>>>(ea);
+    launch_k(ctx, st, "embed", embed_kernel, dim3(B), dim3(eb), 0, ea);
   }
-  note_launch(ctx);
 
   // ---- spatial transformer: L blocks over the KV cache ----
   const int tok = (pos == 0) ? 0 : T0 + pos - 1;     // cache slot of this position's (first) token
   for (int l = 0; l < ctx->L; ++l) {
-    if (prefill) run_block<AT>(ctx, st, ctx->blocks[l], ctx->x, M, 0, kc + l * lstride, vc + l * lstride, T0, Tc, 0, 0, 1);
-    else run_block<AT>(ctx, st, ctx->blocks[l], ctx->x, M, 0, kc + l * lstride, vc + l * lstride, 1, Tc, tok, tok + 1, 0);
+    if (prefill) run_block<AT>(ctx, st, ctx->blocks[l], ctx->x, M, 0, kc + l * lstride, vc + l * lstride, T0, Tc, 0, 0, 1, &fold_x);
+    else run_block<AT>(ctx, st, ctx->blocks[l], ctx->x, M, 0, kc + l * lstride, vc + l * lstride, 1, Tc, tok, tok + 1, 0, &fold_x);
   }
   // ---- hs = ln_f(x) (last prefix row for text), depth start token y = hs + sos_depth ----
-  layernorm_kernel<float><<<(B + 3) / 4, 128, 0, st>>>(ctx->x, ctx->lnf_g, ctx->lnf_b, ctx->sos_depth, ctx->yd, B, D,
-                                                        prefill ? T0 : 1, prefill ? T0 - 1 : 0);
-  note_launch(ctx);
+  launch_k(ctx, st, "layernorm_f", layernorm_kernel<float>, dim3(B), dim3(LN_THREADS), 0, ctx->x, ctx->lnf_g, ctx->lnf_b,
+           ctx->sos_depth, ctx->yd, B, D, prefill ? T0 : 1, prefill ? T0 - 1 : 0, fold_x.partial, fold_x.n, fold_x.stride,
+           fold_x.bias);
+  fold_x = Fold();
 
   // ---- depth pass 0 -> top logits ----
   for (int l = 0; l < ctx->Ld; ++l)
-    run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, B, 1, kd + l * dstride, vd + l * dstride, 1, 5, 0, 1, 0);
-  layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnt_g, ctx->lnt_b, h, B);
+    run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, B, 1, kd + l * dstride, vd + l * dstride, 1, 5, 0, 1, 0, &fold_y);
+  layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnt_g, ctx->lnt_b, h, B, &fold_y);
   {
     EpiParams<AT> e;
     memset(&e, 0, sizeof(e));
@@ -712,11 +844,11 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
   if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
 
   // ---- depth pass 1 -> 4 bottom logits ----
-  embed_depth_kernel<<<B, 128, 0, st>>>(ctx->yd, ctx->E_top_depth, ctx->P_depth, ctx->codes_top, S, pos, D);
-  note_launch(ctx);
+  launch_k(ctx, st, "embed_depth", embed_depth_kernel, dim3(B), dim3(eb), 0, ctx->yd, ctx->E_top_depth, ctx->P_depth, ctx->codes_top,
+           S, pos, D);
   for (int l = 0; l < ctx->Ld; ++l)
-    run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, 4 * B, 2, kd + l * dstride, vd + l * dstride, 4, 5, 1, 5, 0);
-  layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnb_g, ctx->lnb_b, h, 4 * B);
+    run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, 4 * B, 2, kd + l * dstride, vd + l * dstride, 4, 5, 1, 5, 0, &fold_y);
+  layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnb_g, ctx->lnb_b, h, 4 * B, &fold_y);
   {
     EpiParams<AT> e;
     memset(&e, 0, sizeof(e));
@@ -805,7 +937,7 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
   ctx->launch_err = cudaSuccess;
   const bool use_graph = ctx->cfg.use_cuda_graph && f.logits_out == nullptr;
   if (use_graph) {
-    GraphKey key{B, S, a->pos_begin, a->pos_end, f.forced_top, f.forced_bot, f.sos_override};
+    GraphKey key{B, S, a->pos_begin, a->pos_end, f.forced_top, f.forced_bot, f.sos_override, ctx->tracing ? 1 : 0};
     auto it = ctx->graphs.find(key);
     if (it == ctx->graphs.end()) {
       cudaGraph_t graph = nullptr;
@@ -863,7 +995,8 @@ extern "C" int hq_run_host(hq_ctx* ctx, const hq_run_args* args) {
 // ------------------------------------------------------------------------------------------------
 // test / measurement hooks
 // ------------------------------------------------------------------------------------------------
-extern "C" int hq_debug_gemm(int prec, const void* A, const void* W, float* C, int M, int N, int K, void* stream) {
+extern "C" int hq_debug_gemm(int prec, const void* A, const void* W, float* C, int M, int N, int K, int tile,
+                             void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   hq_ctx tmp;   // only used for error text + launch bookkeeping
   if (M < 1 || N < 8 || K < 16) {
@@ -897,14 +1030,17 @@ extern "C" int hq_debug_gemm(int prec, const void* A, const void* W, float* C, i
       cudaMemsetAsync(Ap, 0, static_cast<size_t>(Mp) * K * 2, st);
       cudaMemcpyAsync(Ap, A, static_cast<size_t>(M) * K * 2, cudaMemcpyDeviceToDevice, st);
     }
-    CUtensorMap mA, mW;
+    CUtensorMap mA, mW, mW16;
     if (rc == HQ_OK) rc = make_map(&tmp, &mA, Ap, Mp, K, 128);
     if (rc == HQ_OK) rc = make_map(&tmp, &mW, const_cast<void*>(W), N, K, 64);
+    if (rc == HQ_OK) rc = make_map(&tmp, &mW16, const_cast<void*>(W), N, K, 16);
     if (rc == HQ_OK) {
       EpiParams<bf16> e;
       memset(&e, 0, sizeof(e));
       e.outf = C; e.ldo = N;
-      gemm_bf16<EPI_F32>(&tmp, st, mA, mW, 0, M, N, K, e);
+      g_force_bn = tile;
+      gemm_bf16<EPI_F32>(&tmp, st, mA, mW, mW16, 0, M, N, K, e);
+      g_force_bn = 0;
     }
     cudaError_t se = cudaStreamSynchronize(st);
     if (Ap) cudaFree(Ap);
@@ -965,6 +1101,7 @@ extern "C" int hq_bench_attention(hq_ctx* ctx, int B, int n_keys, int iters, flo
   HQ_CUDA(ctx, cudaEventCreate(&e1));
   const size_t lstride = static_cast<size_t>(ctx->max_batch) * ctx->Tc * ctx->D;
   ctx->launch_err = cudaSuccess;
+  struct PdlOff { hq_ctx* c; bool saved; PdlOff(hq_ctx* x) : c(x), saved(x->use_pdl) { x->use_pdl = false; } ~PdlOff() { c->use_pdl = saved; } } pdl_off(ctx);
   auto launch = [&](int l) {
     if (ctx->bf16) {
       bf16* kc = static_cast<bf16*>(ctx->kc) + l * lstride;
@@ -1010,6 +1147,7 @@ extern "C" int hq_bench_gemm(hq_ctx* ctx, int kind, int M, int iters, float* use
   std::vector<cudaEvent_t> ev(2 * iters);
   for (auto& e : ev) cudaEventCreate(&e);
   ctx->launch_err = cudaSuccess;
+  struct PdlOff { hq_ctx* c; bool saved; PdlOff(hq_ctx* x) : c(x), saved(x->use_pdl) { x->use_pdl = false; } ~PdlOff() { c->use_pdl = saved; } } pdl_off(ctx);
   auto launch = [&](int i) {
     const BlockW& w = ctx->blocks[i % ctx->L];
     if (ctx->bf16) {
@@ -1078,4 +1216,170 @@ extern "C" int hq_bench_gemm(hq_ctx* ctx, int kind, int M, int iters, float* use
   }
   *usec = static_cast<float>(tot * 1000.0 / iters);
   return HQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone GEMM timing on synthetic operands (own allocations): per-launch CUDA-event times of the bf16 kernels
+// for an arbitrary shape / tile.  flush: 0 = none (the W copies are cycled: `copies` distinct weight buffers),
+// 1 = 256 MB memset before every launch (leaves L2 full of dirty lines), 2 = 256 MB read sweep (clean eviction).
+// ------------------------------------------------------------------------------------------------
+__global__ void read_sweep_kernel(const uint4* __restrict__ p, size_t n, unsigned* sink) {
+  unsigned acc = 0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 v = p[i];
+    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (acc == 0x12345678u) *sink = acc;
+}
+
+extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int flush, int copies, float* usec_mean,
+                                   float* usec_min, void* stream) {
+  if (M < 1 || N % 64 != 0 || K % 64 != 0 || iters < 1 || copies < 1 || !usec_mean || !usec_min) {
+    set_err(nullptr, "hq_bench_gemm_shape: bad argument");
+    return HQ_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  hq_ctx tmp;
+  int dev = 0;
+  HQ_CUDA(nullptr, cudaGetDevice(&dev));
+  int rc = check_device(&tmp, dev);
+  if (rc == HQ_OK) rc = get_encode_fn(&tmp, &tmp.encode);
+  if (rc == HQ_OK) rc = set_gemm_attrs(&tmp);
+  if (rc != HQ_OK) {
+    g_last_error = tmp.err;
+    return rc;
+  }
+  const int Mp = (M + 127) / 128 * 128;
+  void *A = nullptr, *W = nullptr, *flushbuf = nullptr;
+  float* C = nullptr;
+  unsigned* sink = nullptr;
+  const size_t wbytes = static_cast<size_t>(N) * K * 2;
+  const size_t flush_bytes = static_cast<size_t>(256) << 20;
+  HQ_CUDA(nullptr, cudaMalloc(&A, static_cast<size_t>(Mp) * K * 2));
+  HQ_CUDA(nullptr, cudaMalloc(&W, wbytes * copies));
+  HQ_CUDA(nullptr, cudaMalloc(reinterpret_cast<void**>(&C), static_cast<size_t>(M) * N * 4));
+  HQ_CUDA(nullptr, cudaMalloc(&flushbuf, flush_bytes));
+  HQ_CUDA(nullptr, cudaMalloc(reinterpret_cast<void**>(&sink), 4));
+  cudaMemsetAsync(A, 0, static_cast<size_t>(Mp) * K * 2, st);
+  cudaMemsetAsync(W, 0, wbytes * copies, st);
+  cudaMemsetAsync(flushbuf, 1, flush_bytes, st);
+  CUtensorMap mA;
+  std::vector<CUtensorMap> mW(copies), mW16(copies);
+  rc = make_map(&tmp, &mA, A, Mp, K, 128);
+  for (int c = 0; rc == HQ_OK && c < copies; ++c) {
+    rc = make_map(&tmp, &mW[c], static_cast<char*>(W) + wbytes * c, N, K, 64);
+    if (rc == HQ_OK) rc = make_map(&tmp, &mW16[c], static_cast<char*>(W) + wbytes * c, N, K, 16);
+  }
+  std::vector<cudaEvent_t> ev(2 * iters);
+  for (auto& e : ev) cudaEventCreate(&e);
+  unsigned long long* d_trace = nullptr;
+  const int max_ctas = 8192;
+  const bool want_trace = getenv("HQ_GEMM_TRACE") != nullptr;
+  if (want_trace) {
+    cudaMalloc(reinterpret_cast<void**>(&d_trace), sizeof(unsigned long long) * 8 * max_ctas);
+    cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * 8 * max_ctas, st);
+  }
+  if (rc == HQ_OK) {
+    EpiParams<bf16> e;
+    memset(&e, 0, sizeof(e));
+    e.outf = C; e.ldo = N;
+    g_force_bn = tile;
+    for (int i = -3; i < iters; ++i) {
+      e.trace = (i == iters - 1) ? d_trace : nullptr;
+      const int c = ((i % copies) + copies) % copies;
+      if (flush == 1) cudaMemsetAsync(flushbuf, i & 0xff, flush_bytes, st);
+      if (flush == 2) read_sweep_kernel<<<1184, 256, 0, st>>>(static_cast<const uint4*>(flushbuf), flush_bytes / 16, sink);
+      if (i >= 0) cudaEventRecord(ev[2 * i], st);
+      gemm_bf16<EPI_F32>(&tmp, st, mA, mW[c], mW16[c], 0, M, N, K, e);
+      if (i >= 0) cudaEventRecord(ev[2 * i + 1], st);
+    }
+    g_force_bn = 0;
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  double tot = 0.0, mn = 1e30;
+  for (int i = 0; i < iters; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
+    tot += ms;
+    if (ms < mn) mn = ms;
+  }
+  if (want_trace && se == cudaSuccess) {
+    std::vector<unsigned long long> h(8 * max_ctas);
+    cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    int n = 0;
+    for (int c = 0; c < max_ctas; ++c)
+      if (h[c * 8] != 0) { ++n; if (h[c * 8] < t0) t0 = h[c * 8]; }
+    static const char* names[8] = {"cta_start", "prologue_done", "tma_ring_issued", "first_stage_landed", "last_mma_issued",
+                                   "accum_complete", "epilogue_done", "cta_end"};
+    fprintf(stderr, "[trace] M=%d N=%d K=%d tile=%d ctas=%d (ns since first CTA start; min / mean / max over CTAs)\n", M, N, K, tile, n);
+    for (int sl = 0; sl < 8; ++sl) {
+      double mn2 = 1e30, mx2 = 0, sum = 0; int cnt = 0;
+      for (int c = 0; c < max_ctas; ++c) {
+        if (h[c * 8] == 0 || h[c * 8 + sl] == 0) continue;
+        const double v = static_cast<double>(h[c * 8 + sl] - t0);
+        mn2 = v < mn2 ? v : mn2; mx2 = v > mx2 ? v : mx2; sum += v; ++cnt;
+      }
+      if (cnt) fprintf(stderr, "[trace]   %-20s %8.0f %8.0f %8.0f  (n=%d)\n", names[sl], mn2, sum / cnt, mx2, cnt);
+    }
+  }
+  if (d_trace) cudaFree(d_trace);
+  for (auto& e : ev) cudaEventDestroy(e);
+  cudaFree(A); cudaFree(W); cudaFree(C); cudaFree(flushbuf); cudaFree(sink);
+  if (rc != HQ_OK) {
+    g_last_error = tmp.err;
+    return rc;
+  }
+  if (se != cudaSuccess || tmp.launch_err != cudaSuccess) {
+    set_err(nullptr, "hq_bench_gemm_shape: %s / %s", cudaGetErrorString(se), cudaGetErrorString(tmp.launch_err));
+    return HQ_ERR_CUDA;
+  }
+  *usec_mean = static_cast<float>(tot * 1000.0 / iters);
+  *usec_min = static_cast<float>(mn * 1000.0);
+  return HQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hq_trace_run: one hq_run with the per-kernel timeline recorded on the device (%globaltimer, ns).
+// out_ns[2*i], out_ns[2*i+1] = first-CTA start / last-CTA end of launch i (in launch order); tags[i*24..] = kernel tag.
+// ------------------------------------------------------------------------------------------------
+extern "C" int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, unsigned long long* out_ns, char* tags,
+                            int max_entries, int* n_entries) {
+  if (!ctx || !args || !out_ns || !tags || !n_entries || max_entries < 1) return HQ_ERR_INVALID;
+  HQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* dbuf = nullptr;
+  HQ_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&dbuf), sizeof(unsigned long long) * 2 * max_entries));
+  std::vector<unsigned long long> init(2 * static_cast<size_t>(max_entries));
+  for (int i = 0; i < max_entries; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+  HQ_CUDA(ctx, cudaMemcpy(dbuf, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+  HQ_CUDA(ctx, cudaMemcpyToSymbol(g_hq_trace, &dbuf, sizeof(dbuf)));
+  // drop a previously captured traced graph of this shape: its launch ids are baked in, the tags vector is rebuilt now
+  for (auto it = ctx->graphs.begin(); it != ctx->graphs.end();) {
+    if (it->first.tracing) { cudaGraphExecDestroy(it->second.exec); it = ctx->graphs.erase(it); } else ++it;
+  }
+  ctx->tracing = true;
+  ctx->trace_cap = max_entries;
+  ctx->trace_tags.clear();
+  int rc = run_impl(ctx, args, st, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);
+  ctx->tracing = false;
+  cudaError_t se = cudaStreamSynchronize(st);
+  if (rc == HQ_OK && se != cudaSuccess) {
+    set_err(ctx, "hq_trace_run: %s", cudaGetErrorString(se));
+    rc = HQ_ERR_CUDA;
+  }
+  if (rc == HQ_OK) {
+    const int n = static_cast<int>(ctx->trace_tags.size());
+    cudaMemcpy(out_ns, dbuf, sizeof(unsigned long long) * 2 * n, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < n; ++i) {
+      strncpy(tags + static_cast<size_t>(i) * 24, ctx->trace_tags[i], 23);
+      tags[static_cast<size_t>(i) * 24 + 23] = 0;
+    }
+    *n_entries = n;
+  }
+  unsigned long long* nullp = nullptr;
+  cudaMemcpyToSymbol(g_hq_trace, &nullp, sizeof(nullp));
+  cudaFree(dbuf);
+  return rc;
 }

@@ -33,9 +33,19 @@ struct EpiParams {
   // EPI_GELU
   AT* out;            // [M, N]
   // EPI_F32
-  float* outf;        // [M, ldo]
+  float* outf;        // [M, ldo]; split-K: slice blockIdx.z of the K range writes outf + blockIdx.z * split_stride
   int ldo;
+  size_t split_stride;
+  unsigned long long* trace;   // optional (profiling builds of the microbenchmark): 8 %globaltimer stamps per CTA
 };
+
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int slot) {
+  if (trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = t;
+  }
+}
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
@@ -76,6 +86,125 @@ __device__ __forceinline__ void epi_store8(const EpiParams<AT>& ep, int m, int n
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue of the tcgen05 kernels.  tcgen05.ld hands every thread one ROW of the accumulator, which would make each
+// global store touch 32 different lines (half-written sectors: measured 1.6 us for a 128 x 64 tile and 6.7 us for
+// 128 x 256, profiles/r1_gemm_trace.txt).  Instead each warp parks its 32 x 32 fp32 chunk in a private 4 KB slab of
+// shared memory (the finished pipeline's stage-0 buffer; 16-byte pieces XOR-swizzled by row so both phases are
+// bank-conflict free) and writes it out with 8 lanes per row: every store instruction covers 4 complete 128-byte row
+// pieces (64-byte pieces for bf16 outputs).  Bias / GELU / residual are applied at write-out.
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+// `sbias` points at BN floats of shared memory outside the pipeline stages (filled here, before the accumulator is
+// complete, so the cold bias loads overlap the main loop).  The chunk loop is NOT unrolled and all index arithmetic
+// (section of the fused q/k/v columns, KV-cache row of each output row) is hoisted: the epilogue is straight-line code
+// that every warp fetches once per launch, and a decode step launches ~80 GEMMs with a cold instruction cache.
+template <int BN, int EPI, typename AT>
+__device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, uint8_t* slab_base, float* sbias, int warp, int lane,
+                                              int m0, int n0, int M, int N, const EpiParams<AT>& ep,
+                                              uint64_t* tmem_full_bar) {
+  const int quarter = warp & 3;
+  const int etid = quarter * 32 + lane;                        // 0..127 over the four epilogue warps
+  const bool has_bias = (EPI != EPI_F32) && ep.bias != nullptr;
+  if (has_bias) {
+    for (int i = etid; i < BN; i += 128) sbias[i] = (n0 + i < N) ? ep.bias[n0 + i] : 0.f;
+  }
+  // rows this lane writes: it*4 + (lane >> 3) of the warp's 32; destination row offsets (elements) per row
+  const int piece = lane & 7;
+  size_t row_a[8], row_b[8];
+  bool row_ok[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int m = m0 + quarter * 32 + it * 4 + (lane >> 3);
+    row_ok[it] = m < M;
+    if (EPI == EPI_QKV) {
+      row_a[it] = static_cast<size_t>(m) * ep.D;                                                        // q / vdup row
+      row_b[it] = (static_cast<size_t>(m / ep.rpb) * ep.t_stride + ep.t0 + (m % ep.rpb)) * ep.D;       // k / v row
+    } else if (EPI == EPI_F32) {
+      row_a[it] = static_cast<size_t>(m) * ep.ldo;
+      row_b[it] = 0;
+    } else {
+      row_a[it] = static_cast<size_t>(m) * N;
+      row_b[it] = 0;
+    }
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");               // sbias visible to the four epilogue warps
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+
+  uint8_t* slab = slab_base + quarter * 4096;                  // this warp's 32 rows x 128 B
+  const uint32_t slab_u32 = smem_u32(slab);
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c * 32), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                              // row = lane; piece j -> slot j ^ (lane & 7)
+      const uint32_t addr = slab_u32 + lane * 128 + ((j ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                   "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                   : "memory");
+    }
+    __syncwarp();
+    const int nb = n0 + c * 32;                                // chunk base column (a chunk never straddles q/k/v)
+    const int n = nb + piece * 4;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_bias) b4 = *reinterpret_cast<const float4*>(sbias + c * 32 + piece * 4);
+    // chunk-uniform destination selection
+    int sec = 0, col = n;
+    if (EPI == EPI_QKV) {
+      sec = ep.sec0 + nb / ep.D;
+      col = nb % ep.D + piece * 4;
+    }
+    if (n < N) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + (lane >> 3);
+        float4 v;
+        const uint32_t addr = slab_u32 + row * 128 + ((piece ^ (row & 7)) << 4);
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+        if (!row_ok[it]) continue;
+        if (EPI == EPI_F32) {
+          *reinterpret_cast<float4*>(ep.outf + row_a[it] + col) = v;
+        } else if (EPI == EPI_RESID) {
+          float4* p = reinterpret_cast<float4*>(ep.x + row_a[it] + col);
+          float4 a = *p;
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+          *p = a;
+        } else {
+          AT* dst;
+          AT* dup = nullptr;
+          if (EPI == EPI_GELU) {
+            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+            dst = ep.out + row_a[it] + col;
+          } else if (sec == 0) {
+            dst = ep.q + row_a[it] + col;
+          } else {
+            dst = (sec == 1 ? ep.kdst : ep.vdst) + row_b[it] + col;
+            if (sec == 2 && ep.vdup != nullptr) dup = ep.vdup + row_a[it] + col;
+          }
+          if (sizeof(AT) == 4) {
+            *reinterpret_cast<float4*>(dst) = v;
+            if (dup != nullptr) *reinterpret_cast<float4*>(dup) = v;
+          } else {
+            uint2 u;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(dst) = u;
+            if (dup != nullptr) *reinterpret_cast<uint2*>(dup) = u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // tcgen05 / TMA GEMM.  One CTA computes a 128 x BN tile; grid = (ceil(N/BN), ceil(M/128)).
 //   warp 0: TMA producer (one lane)      warp 1: tcgen05.mma issuer (one lane)
@@ -87,16 +216,17 @@ struct TcCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 128) ? 3 : 4;   // <= ~98 KB: two CTAs (of consecutive kernels) fit per SM
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
 };
 
 template <int BN, int EPI, typename AT>
 __global__ void __launch_bounds__(192, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
+gemm_tc_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
                int w_row_off, EpiParams<AT> ep) {
 #if defined(__CUDA_ARCH__)
+  TraceScope trace_scope(trace_id);
   using C = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -106,12 +236,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * C::BM;
   const int n0 = blockIdx.x * BN;
-  const int num_kb = K / C::BK;
+  const int num_kb = (K / C::BK) / static_cast<int>(gridDim.z);        // split-K: this CTA's share of the k-blocks
+  const int kb0 = static_cast<int>(blockIdx.z) * num_kb;
+  if (EPI == EPI_F32) ep.outf += static_cast<size_t>(blockIdx.z) * ep.split_stride;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -134,18 +267,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  pdl_launch_dependents();
   if (warp == 0) {
     if (lane == 0) {
-      // ---- TMA producer ----
-      for (int kb = 0; kb < num_kb; ++kb) {
+      // ---- TMA producer.  Weights do not depend on the previous kernel: the first ring of W tiles is requested
+      //      before griddepcontrol.wait, the activation tiles after it. ----
+      const int pre = num_kb < C::STAGES ? num_kb : C::STAGES;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_arrive_expect_tx(&full_bar[kb], C::A_BYTES + C::B_BYTES);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_2d(sB + kb * C::B_BYTES + j * (64 * 128), &tmW, &full_bar[kb], (kb0 + kb) * C::BK, w_row_off + n0 + j * 64);
+      }
+      pdl_wait();
+      for (int kb = 0; kb < pre; ++kb) tma_load_2d(sA + kb * C::A_BYTES, &tmA, &full_bar[kb], (kb0 + kb) * C::BK, m0);
+      for (int kb = pre; kb < num_kb; ++kb) {
         const int s = kb % C::STAGES;
         const uint32_t ph = (kb / C::STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], C::A_BYTES + C::B_BYTES);
-        tma_load_2d(sA + s * C::A_BYTES, &tmA, &full_bar[s], kb * C::BK, m0);
+        tma_load_2d(sA + s * C::A_BYTES, &tmA, &full_bar[s], (kb0 + kb) * C::BK, m0);
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
-          tma_load_2d(sB + s * C::B_BYTES + j * (64 * 128), &tmW, &full_bar[s], kb * C::BK, w_row_off + n0 + j * 64);
+          tma_load_2d(sB + s * C::B_BYTES + j * (64 * 128), &tmW, &full_bar[s], (kb0 + kb) * C::BK, w_row_off + n0 + j * 64);
       }
     }
   } else if (warp == 1) {
@@ -170,29 +314,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(tmem_full_bar);    // accumulator complete
     }
   } else {
-    // ---- epilogue: TMEM -> registers -> global ----
-    const int quarter = warp & 3;
-    const int m = m0 + quarter * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c * 32), r);
-      tmem_ld_wait();
-      if (m < M) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n0 + c * 32 + g * 8;
-          if (n < N) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-            epi_store8<EPI, AT>(ep, m, n, N, v);
-          }
-        }
-      }
-    }
+    // ---- epilogue: TMEM -> registers -> warp-private smem slab -> coalesced global ----
+    pdl_wait();
+    epilogue_tile<BN, EPI, AT>(tmem_base, sA, sbias, warp, lane, m0, n0, M, N, ep, tmem_full_bar);
     tc_fence_before();
   }
   __syncthreads();
@@ -203,14 +327,157 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 / TMA GEMM on CTA pairs (cta_group::2).  A cluster of two CTAs computes a 256 x BN tile: CTA r stages
+// rows [r*128, r*128+128) of A and rows [r*BN/2, (r+1)*BN/2) of the W tile; the leader's single MMA thread issues
+// tcgen05.mma.cta_group::2 (M = 256, N = BN) which reads both CTAs' shared memory and accumulates rows r*128.. in CTA
+// r's TMEM.  Per SM this halves the weight bytes staged per output row, which is what bounds these GEMMs: measured
+// L2->SM ingest is ~84 GB/s per SM (profiles/r1_*), not the tensor pipe.
+//   grid = (2 * N/BN, ceil(M/256)), cluster (2,1,1); warp roles as in gemm_tc_kernel.
+// tmA: [rows_pad, K] box {64,128}; tmW: [N, K] box {64,16} (BN/32 loads per stage per CTA); both SWIZZLE_128B.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct Tc2Cfg {
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = 128 * BK * 2;          // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;     // this CTA's half of the W tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 102400 / STAGE_BYTES;   // <= 100 KB: two CTAs (of consecutive kernels) fit per SM
+  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
+};
+
+template <int BN, int EPI, typename AT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
+                int w_row_off, EpiParams<AT> ep) {
+#if defined(__CUDA_ARCH__)
+  TraceScope trace_scope(trace_id);
+  using C = Tc2Cfg<BN>;
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "pair tile width");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::STAGES * C::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + C::STAGES * C::B_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m0 = blockIdx.y * 256 + static_cast<int>(rank) * 128;      // this CTA's rows
+  const int n0 = (blockIdx.x >> 1) * BN;                               // the pair's columns
+  const int num_kb = (K / C::BK) / static_cast<int>(gridDim.z);        // split-K: this pair's share of the k-blocks
+  const int kb0 = static_cast<int>(blockIdx.z) * num_kb;
+  if (EPI == EPI_F32) ep.outf += static_cast<size_t>(blockIdx.z) * ep.split_stride;
+  if (threadIdx.x == 0) trace_stamp(ep.trace, 0);            // CTA start
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);     // leader: one arrive.expect_tx covering both CTAs' bytes
+      mbar_init(&empty_bar[s], 1);    // one multicast tcgen05.commit per use
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();                 // peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_stamp(ep.trace, 1);            // prologue done
+
+  pdl_launch_dependents();
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer (both CTAs): own A rows + own half of the W tile, credited to the leader's full barrier.
+      //      The first ring of W tiles is requested before griddepcontrol.wait (weights never depend on the
+      //      previous kernel), the activation tiles after it. ----
+      const int wrow = w_row_off + n0 + static_cast<int>(rank) * (BN / 2);
+      const int pre = num_kb < C::STAGES ? num_kb : C::STAGES;
+      for (int kb = 0; kb < pre; ++kb) {
+        if (leader) mbar_arrive_expect_tx(&full_bar[kb], 2 * C::STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j)
+          tma_load_2d_2sm(sB + kb * C::B_BYTES + j * (16 * 128), &tmW, &full_bar[kb], (kb0 + kb) * C::BK, wrow + j * 16);
+      }
+      pdl_wait();
+      for (int kb = 0; kb < pre; ++kb) tma_load_2d_2sm(sA + kb * C::A_BYTES, &tmA, &full_bar[kb], (kb0 + kb) * C::BK, m0);
+      trace_stamp(ep.trace, 2);                                // first ring of TMA requests issued
+      for (int kb = pre; kb < num_kb; ++kb) {
+        const int s = kb % C::STAGES;
+        const uint32_t ph = (kb / C::STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+        tma_load_2d_2sm(sA + s * C::A_BYTES, &tmA, &full_bar[s], (kb0 + kb) * C::BK, m0);
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j)
+          tma_load_2d_2sm(sB + s * C::B_BYTES + j * (16 * 128), &tmW, &full_bar[s], (kb0 + kb) * C::BK, wrow + j * 16);
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // ---- MMA issuer (leader CTA only) ----
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % C::STAGES;
+        const uint32_t ph = (kb / C::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (kb == 0) trace_stamp(ep.trace, 3);                 // first stage landed
+        const uint64_t da = umma_smem_desc_sw128(smem_u32(sA + s * C::A_BYTES));
+        const uint64_t db = umma_smem_desc_sw128(smem_u32(sB + s * C::B_BYTES));
+#pragma unroll
+        for (int k = 0; k < C::BK / 16; ++k)
+          umma_bf16_2sm(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit_2sm(&empty_bar[s], 0x3);   // both CTAs may refill this slot
+      }
+      umma_commit_2sm(tmem_full_bar, 0x3);     // both CTAs' accumulators are complete
+      trace_stamp(ep.trace, 4);                // last MMA issued
+    }
+  } else {
+    // ---- epilogue: this CTA's 128 rows (TMEM -> registers -> warp-private smem slab -> coalesced global) ----
+    pdl_wait();
+    if (warp == 2 && lane == 0) trace_stamp(ep.trace, 5);      // epilogue warps ready
+    epilogue_tile<BN, EPI, AT>(tmem_base, sA, sbias, warp, lane, m0, n0, M, N, ep, tmem_full_bar);
+    tc_fence_before();
+    if (warp == 2 && lane == 0) trace_stamp(ep.trace, 6);      // epilogue stores issued
+  }
+  __syncwarp();
+  cluster_sync_all();                 // the peer may still be reading this CTA's smem / signalling its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+  }
+  if (threadIdx.x == 0) trace_stamp(ep.trace, 7);            // CTA end
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // fp32 CUDA-core GEMM: 64 x 128 tile, BK = 16, 256 threads, 4 x 8 outputs per thread.
 // A [M, K] and W [N, K] row-major fp32 (K % 16 == 0, N % 8 == 0).
 // ------------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(256)
-gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ W, int M, int N, int K, EpiParams<float> ep) {
+gemm_simt_kernel(int trace_id, const float* __restrict__ A, const float* __restrict__ W, int M, int N, int K, EpiParams<float> ep) {
   constexpr int BM = 64, BN = 128, BK = 16;
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Ws[BK][BN + 4];
   const int tid = threadIdx.x;

@@ -24,7 +24,10 @@ struct EmbedArgs {
   int D, S, pos, cond_kind;
 };
 
-__global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a) {
+__global__ void __launch_bounds__(1024) embed_kernel(int trace_id, EmbedArgs a) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();   // programmatic dependent launch: let the next kernel get resident ...
+  pdl_wait();                // ... and wait for the previous kernel's results (no-ops without the launch attribute)
   const int b = blockIdx.x;
   float4* xo = reinterpret_cast<float4*>(a.x + static_cast<size_t>(b) * a.D);
   const int n4 = a.D / 4;
@@ -61,9 +64,12 @@ __global__ void __launch_bounds__(128) embed_kernel(EmbedArgs a) {
 }
 
 // text prefix embedding (sampling.py:187-190): x[b*T + t] = E_txt[ids[b, t]] + P_txt[t]
-__global__ void __launch_bounds__(128)
-embed_txt_kernel(float* x, const float* sos_override, const int64_t* ids, const float* E_txt, const float* P_txt,
+__global__ void __launch_bounds__(1024)
+embed_txt_kernel(int trace_id, float* x, const float* sos_override, const int64_t* ids, const float* E_txt, const float* P_txt,
                  int T, int D) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();   // programmatic dependent launch: let the next kernel get resident ...
+  pdl_wait();                // ... and wait for the previous kernel's results (no-ops without the launch attribute)
   const int row = blockIdx.x;  // b*T + t
   const int t = row % T;
   float4* xo = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * D);
@@ -82,9 +88,12 @@ embed_txt_kernel(float* x, const float* sos_override, const int64_t* ids, const 
 }
 
 // K11: depth pass-1 inputs (hierarchical_ar.py:701-703): y[b*4 + j] = E_top_depth[c_top[b]] + P_depth[j]
-__global__ void __launch_bounds__(128)
-embed_depth_kernel(float* y, const float* E_top_depth, const float* P_depth, const int64_t* codes_top, int S, int pos,
+__global__ void __launch_bounds__(1024)
+embed_depth_kernel(int trace_id, float* y, const float* E_top_depth, const float* P_depth, const int64_t* codes_top, int S, int pos,
                    int D) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();   // programmatic dependent launch: let the next kernel get resident ...
+  pdl_wait();                // ... and wait for the previous kernel's results (no-ops without the launch attribute)
   const int b = blockIdx.x;
   const int64_t ct = codes_top[static_cast<size_t>(b) * S + pos];
   const float4* e = reinterpret_cast<const float4*>(E_top_depth + static_cast<size_t>(ct) * D);
@@ -106,47 +115,146 @@ embed_depth_kernel(float* y, const float* E_top_depth, const float* P_depth, con
 //   out[r] = LN(x[r * in_mul + in_off]) * gamma + beta (+ add)        OutT = float | bf16
 // The (+ add) form produces the depth transformer's start token hs + sos_depth (hierarchical_ar.py:561, 685).
 // ------------------------------------------------------------------------------------------------
+constexpr int LN_THREADS = 128;
+constexpr int LN_MAXV = 3;    // float4 per thread held in registers: rows up to 3 * 512 = 1536 columns
+
 template <typename OutT>
-__global__ void __launch_bounds__(128)
-layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 const float* __restrict__ add, OutT* __restrict__ out, int rows, int D, int in_mul, int in_off) {
-  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  const float* xr = x + (static_cast<size_t>(r) * in_mul + in_off) * D;
+__device__ __forceinline__ void ln_store4(OutT* o, int i, float y0, float y1, float y2, float y3) {
+  if (sizeof(OutT) == 4) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(o) + i) = make_float4(y0, y1, y2, y3);
+  } else {
+    uint2 u;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(o) + i) = u;
+  }
+}
+
+__device__ __forceinline__ float block_sum_128(float v, float* red /*[4]*/) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// One row per CTA (128 threads).  A decode step is a chain of ~150 dependent kernels, so what matters here is the
+// number of serialized memory round trips, not bandwidth: x, gamma, beta (and the optional partial sums / addend)
+// are ALL requested before the first use - one round trip - then two block reductions and the stores.
+//   fold != nullptr: x[r] += fold_bias + sum_s fold[s][r]  first (split-K partial sums of the preceding GEMM, summed
+//   in a fixed order, so the result is deterministic), and the updated x row is written back.
+template <typename OutT>
+__global__ void __launch_bounds__(LN_THREADS)
+layernorm_kernel(int trace_id, float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const float* __restrict__ add, OutT* __restrict__ out, int rows, int D, int in_mul, int in_off,
+                 const float* __restrict__ fold, int n_fold, size_t fold_stride, const float* __restrict__ fold_bias) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[4];
+  const int r = blockIdx.x;
+  float* xr = x + (static_cast<size_t>(r) * in_mul + in_off) * D;
+  OutT* o = out + static_cast<size_t>(r) * D;
+  const int tid = threadIdx.x;
+  if (D <= LN_MAXV * LN_THREADS * 4) {
+    float4 v[LN_MAXV], g[LN_MAXV], bt[LN_MAXV], ad[LN_MAXV], fb[LN_MAXV], f0[LN_MAXV], f1[LN_MAXV], f2[LN_MAXV];
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j) {
+      const int i = (j * LN_THREADS + tid) * 4;
+      const int ic = i < D ? i : 0;                       // clamped: the load is unconditional, the value masked
+      v[j] = *reinterpret_cast<const float4*>(xr + ic);
+      g[j] = *reinterpret_cast<const float4*>(gamma + ic);
+      bt[j] = *reinterpret_cast<const float4*>(beta + ic);
+      ad[j] = add != nullptr ? *reinterpret_cast<const float4*>(add + ic) : z4;
+      fb[j] = z4; f0[j] = z4; f1[j] = z4; f2[j] = z4;
+      if (fold != nullptr) {
+        const float* fr = fold + (static_cast<size_t>(r) * in_mul + in_off) * D + ic;
+        fb[j] = fold_bias != nullptr ? *reinterpret_cast<const float4*>(fold_bias + ic) : z4;
+        f0[j] = *reinterpret_cast<const float4*>(fr);
+        if (n_fold > 1) f1[j] = *reinterpret_cast<const float4*>(fr + fold_stride);
+        if (n_fold > 2) f2[j] = *reinterpret_cast<const float4*>(fr + 2 * fold_stride);
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j) {
+      const int i = (j * LN_THREADS + tid) * 4;
+      if (fold != nullptr) {
+        v[j].x += fb[j].x + ((f0[j].x + f1[j].x) + f2[j].x);
+        v[j].y += fb[j].y + ((f0[j].y + f1[j].y) + f2[j].y);
+        v[j].z += fb[j].z + ((f0[j].z + f1[j].z) + f2[j].z);
+        v[j].w += fb[j].w + ((f0[j].w + f1[j].w) + f2[j].w);
+        if (i < D) *reinterpret_cast<float4*>(xr + i) = v[j];
+      }
+      if (i < D) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = block_sum_128(s, red) / static_cast<float>(D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j) {
+      if ((j * LN_THREADS + tid) * 4 < D) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(block_sum_128(q, red) / static_cast<float>(D) + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < LN_MAXV; ++j) {
+      const int i = (j * LN_THREADS + tid) * 4;
+      if (i < D) {
+        ln_store4<OutT>(o, i, (v[j].x - mean) * rstd * g[j].x + bt[j].x + ad[j].x,
+                        (v[j].y - mean) * rstd * g[j].y + bt[j].y + ad[j].y,
+                        (v[j].z - mean) * rstd * g[j].z + bt[j].z + ad[j].z,
+                        (v[j].w - mean) * rstd * g[j].w + bt[j].w + ad[j].w);
+      }
+    }
+    return;
+  }
+  // wide rows (D > 1536): strided passes
+  if (fold != nullptr) {
+    for (int i = tid * 4; i < D; i += LN_THREADS * 4) {
+      float4 v = *reinterpret_cast<const float4*>(xr + i);
+      const float* fr = fold + (static_cast<size_t>(r) * in_mul + in_off) * D + i;
+      float4 acc = *reinterpret_cast<const float4*>(fr);
+      for (int sidx = 1; sidx < n_fold; ++sidx) {
+        const float4 f = *reinterpret_cast<const float4*>(fr + sidx * fold_stride);
+        acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+      }
+      if (fold_bias != nullptr) {
+        const float4 b = *reinterpret_cast<const float4*>(fold_bias + i);
+        acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+      }
+      v.x += acc.x; v.y += acc.y; v.z += acc.z; v.w += acc.w;
+      *reinterpret_cast<float4*>(xr + i) = v;
+    }
+    __syncthreads();
+  }
   float s = 0.f;
-  for (int i = lane * 4; i < D; i += 128) {
+  for (int i = tid * 4; i < D; i += LN_THREADS * 4) {
     const float4 v = *reinterpret_cast<const float4*>(xr + i);
     s += (v.x + v.y) + (v.z + v.w);
   }
-  const float mean = warp_sum(s) / static_cast<float>(D);
+  const float mean = block_sum_128(s, red) / static_cast<float>(D);
   float q = 0.f;
-  for (int i = lane * 4; i < D; i += 128) {
+  for (int i = tid * 4; i < D; i += LN_THREADS * 4) {
     const float4 v = *reinterpret_cast<const float4*>(xr + i);
     const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
     q += (a * a + b * b) + (c * c + d * d);
   }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(D) + 1e-5f);
-  OutT* o = out + static_cast<size_t>(r) * D;
-  for (int i = lane * 4; i < D; i += 128) {
+  const float rstd = 1.0f / sqrtf(block_sum_128(q, red) / static_cast<float>(D) + 1e-5f);
+  for (int i = tid * 4; i < D; i += LN_THREADS * 4) {
     const float4 v = *reinterpret_cast<const float4*>(xr + i);
     const float4 g = *reinterpret_cast<const float4*>(gamma + i);
     const float4 bt = *reinterpret_cast<const float4*>(beta + i);
     float y0 = (v.x - mean) * rstd * g.x + bt.x, y1 = (v.y - mean) * rstd * g.y + bt.y;
     float y2 = (v.z - mean) * rstd * g.z + bt.z, y3 = (v.w - mean) * rstd * g.w + bt.w;
     if (add != nullptr) {
-      const float4 ad = *reinterpret_cast<const float4*>(add + i);
-      y0 += ad.x; y1 += ad.y; y2 += ad.z; y3 += ad.w;
+      const float4 a4 = *reinterpret_cast<const float4*>(add + i);
+      y0 += a4.x; y1 += a4.y; y2 += a4.z; y3 += a4.w;
     }
-    if (sizeof(OutT) == 4) {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(o) + i) = make_float4(y0, y1, y2, y3);
-    } else {
-      uint2 u;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(y2, y3);
-      u.x = *reinterpret_cast<uint32_t*>(&h0);
-      u.y = *reinterpret_cast<uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(o) + i) = u;
-    }
+    ln_store4<OutT>(o, i, y0, y1, y2, y3);
   }
 }
 
@@ -163,8 +271,11 @@ constexpr int ATT_WARPS = 8;
 
 template <typename AT>
 __global__ void __launch_bounds__(ATT_WARPS * 32)
-attention_kernel(const AT* __restrict__ q, const AT* __restrict__ K, const AT* __restrict__ V, AT* __restrict__ out,
+attention_kernel(int trace_id, const AT* __restrict__ q, const AT* __restrict__ K, const AT* __restrict__ V, AT* __restrict__ out,
                  int M, int n_heads, int D, int Tq, int t_stride, int kbase, int causal) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();   // programmatic dependent launch: let the next kernel get resident ...
+  pdl_wait();                // ... and wait for the previous kernel's results (no-ops without the launch attribute)
   __shared__ float sc[ATT_WARPS][ATT_MAX_KEYS];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * ATT_WARPS + w;
@@ -288,7 +399,10 @@ struct OpMaxI { __device__ int operator()(int a, int b) const { return a > b ? a
 struct OpMinI { __device__ int operator()(int a, int b) const { return a < b ? a : b; } };
 
 template <int NTHR>
-__global__ void __launch_bounds__(NTHR) sample_kernel(SampleArgs a) {
+__global__ void __launch_bounds__(NTHR) sample_kernel(int trace_id, SampleArgs a) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();   // programmatic dependent launch: let the next kernel get resident ...
+  pdl_wait();                // ... and wait for the previous kernel's results (no-ops without the launch attribute)
   __shared__ float fscratch[33];
   __shared__ int iscratch[33];
   __shared__ float wsum[33];

@@ -45,7 +45,8 @@ class Engine:
     def __init__(self, *, embed_dim: int, n_heads: int, n_layers: int, n_layers_depth: int, vocab_top: int,
                  vocab_bot: int, vocab_txt: int = 16384, n_classes: int = 1000, ctx_len_img: int = 256,
                  ctx_len_txt: int = 64, cond: str = "cls", precision: str = "bf16", max_seq_len: int = 64,
-                 max_batch: int = 16, device: Union[int, str, torch.device] = 0, use_cuda_graph: bool = True):
+                 max_batch: int = 16, device: Union[int, str, torch.device] = 0, use_cuda_graph: bool = True,
+                 use_pdl: bool = True):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
@@ -61,7 +62,8 @@ class Engine:
                        ctx_len_img=ctx_len_img, ctx_len_txt=ctx_len_txt,
                        cond_kind={"cls": _lib.HQ_COND_CLS, "txt": _lib.HQ_COND_TXT, "uncond": _lib.HQ_COND_UNCOND}[cond],
                        precision={"bf16": _lib.HQ_PREC_BF16, "fp32": _lib.HQ_PREC_FP32}[precision],
-                       max_seq_len=max_seq_len, use_cuda_graph=1 if use_cuda_graph else 0)
+                       max_seq_len=max_seq_len, use_cuda_graph=1 if use_cuda_graph else 0,
+                       use_pdl=1 if use_pdl else 0)
         check(self._lib.hq_create(C.byref(cfg), self.device.index, int(max_batch), C.byref(self._ctx)), None, "hq_create")
 
     # ---- lifetime ----
@@ -143,6 +145,23 @@ class Engine:
                 stream = torch.cuda.current_stream(self.device).cuda_stream
             check(self._lib.hq_run(self._ctx, C.byref(args), C.c_void_p(stream)), self._ctx, "hq_run")
 
+    def trace_run(self, *, batch: int, seq_len: int, pos_begin: int, pos_end: int, sampling: SamplingParams,
+                  cond: Optional[torch.Tensor], codes_top: torch.Tensor, codes_bot: torch.Tensor,
+                  max_entries: int = 16384):
+        """hq_trace_run: returns [(tag, start_ns, end_ns), ...] per kernel launch of one run (device timeline)."""
+        args = HQRunArgs(batch=batch, seq_len=seq_len, pos_begin=pos_begin, pos_end=pos_end, cond=_ptr(cond), sos=None,
+                         given_top=None, given_bot=None, codes_top=_ptr(codes_top), codes_bot=_ptr(codes_bot),
+                         logits=None, sampling=sampling.to_c())
+        out = (C.c_uint64 * (2 * max_entries))()
+        tags = C.create_string_buffer(24 * max_entries)
+        n = C.c_int()
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._lib.hq_trace_run(self._ctx, C.byref(args), C.c_void_p(st), out, tags, max_entries, C.byref(n)),
+              self._ctx, "hq_trace_run")
+        raw = tags.raw
+        return [(raw[24 * i:24 * i + 24].split(b"\0")[0].decode(), int(out[2 * i]), int(out[2 * i + 1]))
+                for i in range(n.value)]
+
     def bench_attention(self, batch: int, n_keys: int, iters: int = 50) -> float:
         """Mean microseconds of one single-query KV-cache attention launch (CUDA events on the current stream)."""
         us = C.c_float()
@@ -162,8 +181,9 @@ class Engine:
 
 
 # ---- stand-alone hooks used by tests / bench ----
-def debug_gemm(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
-    """C = A @ W^T through the engine's GEMM kernel (bf16 -> tcgen05 path, fp32 -> CUDA-core path)."""
+def debug_gemm(A: torch.Tensor, W: torch.Tensor, tile: int = 0) -> torch.Tensor:
+    """C = A @ W^T through the engine's GEMM kernels (bf16 -> tcgen05 path, fp32 -> CUDA-core path).
+    tile: 0 = engine heuristic, 32..256 = CTA-pair kernel of that width, -64/-128 = single-CTA kernel."""
     lib = _lib.load()
     assert A.is_cuda and W.is_cuda and A.dtype == W.dtype and A.is_contiguous() and W.is_contiguous()
     M, K = A.shape
@@ -172,7 +192,7 @@ def debug_gemm(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
     prec = _lib.HQ_PREC_BF16 if A.dtype == torch.bfloat16 else _lib.HQ_PREC_FP32
     with torch.cuda.device(A.device):
         st = torch.cuda.current_stream(A.device).cuda_stream
-        check(lib.hq_debug_gemm(prec, A.data_ptr(), W.data_ptr(), out.data_ptr(), M, N, K, C.c_void_p(st)), None,
+        check(lib.hq_debug_gemm(prec, A.data_ptr(), W.data_ptr(), out.data_ptr(), M, N, K, tile, C.c_void_p(st)), None,
               "hq_debug_gemm")
     return out
 
@@ -200,3 +220,13 @@ def debug_sample(logits: torch.Tensor, temperature: float = 1.0, top_k: Optional
                                   float(top_p) if top_p is not None else 0.0, seed, row_offset, position, slot,
                                   codes.data_ptr(), _ptr(probs), C.c_void_p(st)), None, "hq_debug_sample")
     return (codes, probs) if return_probs else codes
+
+
+def bench_gemm_shape(M: int, N: int, K: int, tile: int = 0, iters: int = 20, flush: int = 2, copies: int = 1):
+    """(mean, min) microseconds per launch of the bf16 GEMM kernel on synthetic operands (hq_bench_gemm_shape)."""
+    lib = _lib.load()
+    mean, mn = C.c_float(), C.c_float()
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.hq_bench_gemm_shape(M, N, K, tile, iters, flush, copies, C.byref(mean), C.byref(mn), C.c_void_p(st)), None,
+          "hq_bench_gemm_shape")
+    return mean.value, mn.value

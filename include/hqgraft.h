@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HQ_ABI_VERSION 1
+#define HQ_ABI_VERSION 2
 
 enum hq_status {
   HQ_OK = 0,
@@ -65,6 +65,8 @@ typedef struct hq_config {
   int32_t precision;       /* hq_precision */
   int32_t max_seq_len;     /* number of top positions a run may cover (64 for 8x8) */
   int32_t use_cuda_graph;  /* 1: capture each run shape once and replay it; 0: plain stream launches */
+  int32_t use_pdl;         /* 1: chain the kernels with programmatic dependent launch (prologue of kernel n+1 and
+                              its first weight tiles overlap the tail of kernel n); 0: plain stream order */
 } hq_config;
 
 /* Arguments of Sample(z; T, k, p) - hierarchical_ar.py:762-785 with utils/sampling.py:12-37.
@@ -158,9 +160,11 @@ size_t hq_device_bytes(const hq_ctx* ctx);
 
 /* ---- test / measurement hooks (used by tests/ and bench.py, not by the sampling entry points) ---- */
 
-/* C[M,N] = A[M,K] * W[N,K]^T through the same tcgen05/TMA kernel the sampler uses (prec == HQ_PREC_BF16,
- * A and W bf16) or the fp32 CUDA-core kernel (HQ_PREC_FP32, A and W fp32); C fp32; device pointers. */
-int hq_debug_gemm(int prec, const void* A, const void* W, float* C, int M, int N, int K, void* stream);
+/* C[M,N] = A[M,K] * W[N,K]^T through the same tcgen05/TMA kernels the sampler uses (prec == HQ_PREC_BF16,
+ * A and W bf16) or the fp32 CUDA-core kernel (HQ_PREC_FP32, A and W fp32); C fp32; device pointers.
+ * tile: 0 = the engine's own choice; 32/64/96/128/192/256 = CTA-pair kernel with that tile width;
+ * -64 / -128 = single-CTA kernel. */
+int hq_debug_gemm(int prec, const void* A, const void* W, float* C, int M, int N, int K, int tile, void* stream);
 
 /* Philox4x32-10 block for (seed, counter) - known-answer test of the RNG; host pointers. */
 int hq_debug_philox(uint64_t seed, const uint32_t counter[4], uint32_t out[4]);
@@ -179,6 +183,17 @@ int hq_bench_attention(hq_ctx* ctx, int B, int n_keys, int iters, float* usec, v
  * 1 = attention proj [D, D], 2 = mlp fc1 [4D, D], 3 = mlp fc2 [D, 4D], 4 = head_top [V, D]; M rows.  L2 is evicted
  * between launches (256 MB write) and layers are cycled, so weights stream from HBM as in the real loop. */
 int hq_bench_gemm(hq_ctx* ctx, int kind, int M, int iters, float* usec, void* stream);
+
+/* One hq_run (device pointers) with the kernel timeline recorded on the device: out_ns[2i] / out_ns[2i+1] = first-CTA
+ * start / last-CTA end (%globaltimer, ns) of the i-th kernel launch, tags[24*i] = its NUL-terminated tag. */
+int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, unsigned long long* out_ns, char* tags,
+                 int max_entries, int* n_entries);
+
+/* Stand-alone timing of the bf16 GEMM kernels on synthetic operands of any shape / tile (see hq_debug_gemm for
+ * `tile`).  flush: 0 none (cycles `copies` weight buffers), 1 = 256 MB memset before each launch, 2 = 256 MB read
+ * sweep before each launch.  Per-launch CUDA-event times; mean and min in microseconds. */
+int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int flush, int copies, float* usec_mean,
+                        float* usec_min, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,22 @@ def test_gemm_tcgen05_matches_fp32_matmul(M, N, K):
     assert err <= 2e-5 * max(scale, 1.0) * (K / 64) ** 0.5 + 1e-5, (err, scale)
 
 
+@pytest.mark.parametrize("tile", [32, 64, 96, 128, 192, 256, -64, -128])
+@pytest.mark.parametrize("M,N,K", [(256, 1536, 1536), (1024, 4608, 512), (300, 768, 128), (129, 3072, 6144)])
+def test_gemm_tcgen05_every_tile_variant(M, N, K, tile):
+    """CTA-pair kernel (cta_group::2, 256 x tile) for every tile width, and the single-CTA kernel, incl. ragged M."""
+    from hqtransformer_b200.engine import debug_gemm
+    if tile > 0 and N % tile != 0:
+        pytest.skip("N not a multiple of the tile width")
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + tile)
+    A = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    C = debug_gemm(A, W, tile=tile)
+    ref = A.double() @ W.double().t()
+    err = (C.double() - ref).abs().max().item()
+    assert err <= 2e-5 * max(ref.abs().max().item(), 1.0) * (K / 64) ** 0.5 + 1e-5, err
+
+
 @pytest.mark.parametrize("M,N,K", [(64, 128, 16), (5, 256, 128), (100, 1032, 256), (257, 384, 1536)])
 def test_gemm_fp32_matches_matmul(M, N, K):
     from hqtransformer_b200.engine import debug_gemm

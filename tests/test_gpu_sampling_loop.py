@@ -12,15 +12,15 @@ GREEDY = dict(top_k_top=1, top_p_top=1.0, top_k_bot=1, top_p_bot=1.0, softmax_te
 
 
 @pytest.mark.parametrize("name", ["tiny_cls_greedy.npz", "small_cls_greedy.npz"])
-@pytest.mark.parametrize("graph", [False, True])
-def test_greedy_codes_bit_exact_vs_reference_fp32(name, graph):
+@pytest.mark.parametrize("graph,pdl", [(False, False), (True, False), (False, True), (True, True)])
+def test_greedy_codes_bit_exact_vs_reference_fp32(name, graph, pdl):
     """Config 1 of BASELINE.json: greedy code grids from the reference's own sampler (CPU, fp32) must be reproduced
     bit for bit by the fp32 engine (use_fp16=False).  Golden margins are >= 1e-4, fp32 GEMM error ~1e-6."""
     import hqtransformer_b200 as H
     g, meta = load_golden(name)
     cfg = cfg_from_meta(meta)
     P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
-    model = build_model(cfg, P, precision="fp32", use_cuda_graph=graph)
+    model = build_model(cfg, P, precision="fp32", use_cuda_graph=graph, use_pdl=pdl)
     labels = torch.from_numpy(g["labels"])
     ct, cb = H.sampling_ihqgpt(model, len(labels), labels, use_fp16=False, max_seq_len=64, is_tqdm=False, **GREEDY)
     assert ct.dtype == torch.int64 and tuple(ct.shape) == (len(labels), 64) and tuple(cb.shape) == (len(labels), 64, 4)
@@ -72,6 +72,51 @@ def test_step_logits_bf16_vs_oracle_and_reference(name):
     rel = d2.max() / want.abs().max()
     print(f"{name}: bf16 vs reference fp32 max-abs {d2.max():.3e} mean-abs {d2.mean():.3e} max-rel {rel:.3e}")
     assert d2.max() <= 0.15 and d2.mean() <= 0.02, (d2.max(), d2.mean())
+
+
+@pytest.mark.parametrize("graph,pdl", [(False, False), (True, True)])
+def test_bf16_sampling_is_deterministic_and_launch_mode_invariant(graph, pdl):
+    """Same seed -> same grids, whether the loop is replayed as a CUDA graph with programmatic dependent launch or
+    issued as plain stream launches (a race in the PDL chain would show up here)."""
+    import hqtransformer_b200 as H
+    g, meta = load_golden("small_cls_greedy.npz")
+    cfg = cfg_from_meta(meta)
+    P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
+    labels = torch.arange(300) % cfg.n_classes
+    kw = dict(top_k_top=50, top_p_top=0.9, top_k_bot=50, top_p_bot=0.9, softmax_temperature=[0.9, 0.9], use_fp16=True,
+              max_seq_len=16, is_tqdm=False, seed=7)
+    base = build_model(cfg, P, precision="bf16", max_batch=300, use_cuda_graph=False, use_pdl=False)
+    ct0, cb0 = H.sampling_ihqgpt(base, 300, labels, **kw)
+    model = build_model(cfg, P, precision="bf16", max_batch=300, use_cuda_graph=graph, use_pdl=pdl)
+    for _ in range(3):
+        ct, cb = H.sampling_ihqgpt(model, 300, labels, **kw)
+        assert torch.equal(ct, ct0) and torch.equal(cb, cb0)
+
+
+@pytest.mark.parametrize("B", [40, 150])
+def test_step_logits_bf16_wide_batch_vs_oracle(B):
+    """Batches wide enough to take the CTA-pair GEMM kernel (M > 128) and the split-K fc2 + LayerNorm fold path;
+    same tolerance as the narrow-batch logits test."""
+    import hqtransformer_b200 as H
+    g, meta = load_golden("small_cls_greedy.npz")
+    cfg = cfg_from_meta(meta)
+    P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
+    S = 3
+    gen = torch.Generator().manual_seed(B)
+    labels = torch.randint(0, cfg.n_classes, (B,), generator=gen)
+    ct = torch.randint(0, cfg.vocab_top, (B, S), generator=gen)
+    cb = torch.randint(0, cfg.vocab_bot, (B, S, 4), generator=gen)
+    model = build_model(cfg, P, precision="bf16", max_batch=B, max_seq_len=S)
+    lg = H.step_logits(model, labels, ct, cb, use_fp16=True).cpu()
+    emu = O.step_logits(P, cfg, labels, ct, cb, emulate="bf16")
+    d = (lg - emu).abs()
+    print(f"B={B}: bf16 vs emulated oracle max-abs {d.max():.3e} mean-abs {d.mean():.3e}")
+    assert d.max() <= 2e-2 and d.mean() <= 2e-3, (d.max(), d.mean())
+    # fp32 engine on the same inputs: plain fp32 tolerance
+    m32 = build_model(cfg, P, precision="fp32", max_batch=B, max_seq_len=S)
+    lg32 = H.step_logits(m32, labels, ct, cb, use_fp16=False).cpu()
+    ref = O.step_logits(P, cfg, labels, ct, cb)
+    assert (lg32 - ref).abs().max() < 2e-5
 
 
 def test_bf16_greedy_margin_aware():
