@@ -117,7 +117,8 @@ struct hq_ctx {
   bool use_pdl = false;
   bool tracing = false;
   int trace_cap = 0;
-  std::vector<const char*> trace_tags;
+  std::vector<std::string> trace_tags;
+  std::string tag_suffix;   // shape annotation appended to the next launch tag (tracing only)
 };
 
 static void set_err(hq_ctx* ctx, const char* fmt, ...) {
@@ -386,6 +387,8 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
     if ((rc = get_encode_fn(ctx, &ctx->encode))) return rc;
     if ((rc = set_gemm_attrs(ctx))) return rc;
   }
+  if ((rc = set_smem(ctx, attention_decode_kernel<bf16>, 113 * 1024))) return rc;
+  if ((rc = set_smem(ctx, attention_decode_kernel<float>, 113 * 1024))) return rc;
   HQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
 
   // ---- parameters ----
@@ -590,8 +593,9 @@ static void launch_k(hq_ctx* ctx, cudaStream_t st, const char* tag, void (*kerne
   int trace_id = -1;
   if (ctx->tracing && static_cast<int>(ctx->trace_tags.size()) < ctx->trace_cap) {
     trace_id = static_cast<int>(ctx->trace_tags.size());
-    ctx->trace_tags.push_back(tag);
+    ctx->trace_tags.push_back(std::string(tag) + ctx->tag_suffix);
   }
+  ctx->tag_suffix.clear();
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, trace_id, static_cast<KArgs>(args)...);
   ++ctx->launches;
   if (e == cudaSuccess) e = cudaGetLastError();
@@ -633,6 +637,11 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
                       int splits = 1, int bn_hint = 0) {
   int bn = g_force_bn ? g_force_bn : bn_hint;
   if (bn == 0) bn = (M > 128) ? pick_pair_bn(M, N) : 0;
+  if (ctx->tracing) {
+    char buf[48];
+    snprintf(buf, sizeof(buf), ":%dx%dx%d:s%d", M, N, K, splits);
+    ctx->tag_suffix = buf;
+  }
   if (bn > 0 && N % bn == 0) {
     dim3 grid(2 * (N / bn), (M + 255) / 256, splits);
 #define HQ_LAUNCH2(BN)                                                                                             \
@@ -696,12 +705,40 @@ static void layernorm_act(hq_ctx* ctx, cudaStream_t st, float* x, const float* g
   if (fold) *fold = Fold();
 }
 
+// Shared-memory plan of attention_decode_kernel for this model: keys per ring stage and dynamic smem bytes.
+template <typename AT>
+static void attn_decode_plan(const hq_ctx* ctx, int* CH, int* ncw, size_t* smem) {
+  const int row_bytes = ctx->D * static_cast<int>(sizeof(AT));
+  int ch = (24576 / row_bytes) / 4 * 4;
+  if (ch < 4) ch = 4;
+  if (ch > 32) ch = 32;
+  *CH = ch;
+  *ncw = ctx->nh < ATTD_MAXW ? ctx->nh : ATTD_MAXW;
+  *smem = static_cast<size_t>(ATTD_STAGES) * ch * row_bytes + static_cast<size_t>(ctx->nh) * ATT_MAX_KEYS * 4 +
+          2 * ATTD_STAGES * 8 + 128;
+}
+
 template <typename AT>
 static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, const AT* V, AT* out, int M, int Tq,
                       int t_stride, int kbase, int causal) {
+  int CH, ncw;
+  size_t smem;
+  attn_decode_plan<AT>(ctx, &CH, &ncw, &smem);
+  if (Tq == 1 && !causal && ctx->nh <= ATTD_MAXW * ATTD_HPW && smem <= 113 * 1024 && getenv("HQ_ATTN_GENERIC") == nullptr) {
+    // spatial decode: one CTA per batch row, K/V streamed through shared memory by bulk async copies
+    if (ctx->tracing) ctx->tag_suffix = ":t" + std::to_string(kbase) + ":B" + std::to_string(M);
+    launch_k(ctx, st, "attention_decode", attention_decode_kernel<AT>, dim3(M), dim3((ncw + 1) * 32), smem, q, K, V, out,
+             ctx->nh, ctx->D, t_stride, kbase, CH, ncw);
+    return;
+  }
   const int items = M * ctx->nh;
-  launch_k(ctx, st, Tq == 1 ? "attention_decode" : "attention_multi", attention_kernel<AT>, dim3((items + ATT_WARPS - 1) / ATT_WARPS), dim3(ATT_WARPS * 32), 0, q, K, V,
-           out, M, ctx->nh, ctx->D, Tq, t_stride, kbase, causal);
+  if (!causal && kbase <= 8) {
+    launch_k(ctx, st, "attention_fewkeys", attention_fewkeys_kernel<AT>, dim3((items + ATT_WARPS - 1) / ATT_WARPS),
+             dim3(ATT_WARPS * 32), 0, q, K, V, out, M, ctx->nh, ctx->D, Tq, t_stride, kbase);
+    return;
+  }
+  launch_k(ctx, st, "attention_generic", attention_kernel<AT>, dim3((items + ATT_WARPS - 1) / ATT_WARPS),
+           dim3(ATT_WARPS * 32), 0, q, K, V, out, M, ctx->nh, ctx->D, Tq, t_stride, kbase, causal);
 }
 
 static void launch_sample(hq_ctx* ctx, cudaStream_t st, const SampleArgs& a) {
@@ -714,24 +751,45 @@ static void launch_sample(hq_ctx* ctx, cudaStream_t st, const SampleArgs& a) {
 //   mode 1: depth pass 0              - k, v only (softmax over one key == identity, a = v)
 //   mode 2: depth pass 1              - q, k, v; 4 queries over the 5 depth keys
 static void gemm_fc2_split(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int M, int N, int K, int splits,
-                           bf16*) {
+                           int bn, bf16*) {
   EpiParams<bf16> e;
   memset(&e, 0, sizeof(e));
   e.outf = ctx->splitk_ws; e.ldo = N; e.split_stride = static_cast<size_t>(ctx->ws_rows) * N;
-  gemm_bf16<EPI_F32>(ctx, st, A.map, W.map, W.map16, 0, M, N, K, e, splits, 64);
+  gemm_bf16<EPI_F32>(ctx, st, A.map, W.map, W.map16, 0, M, N, K, e, splits, bn);
 }
-static void gemm_fc2_split(hq_ctx*, cudaStream_t, const ABuf&, const Weight&, int, int, int, int, float*) {}
+static void gemm_fc2_split(hq_ctx*, cudaStream_t, const ABuf&, const Weight&, int, int, int, int, int, float*) {}
 
-// Split-K factor for the fc2 GEMM ([M, D] = [M, 4D] x [D, 4D]^T): its K = 4D main loop is the longest serial chain of a
-// block while its D-wide output fills few CTAs, so when the pair grid leaves SMs idle the K range is cut in up to 3
-// slices (grid.z); the slices write fp32 partial sums that the next LayerNorm adds in a fixed order.
-static int pick_fc2_splits(const hq_ctx* ctx, int M, int N, int K) {
-  if (!ctx->bf16 || M <= 128 || getenv("HQ_NO_SPLITK") != nullptr) return 1;
-  const int pairs = ((M + 255) / 256) * (N / 64);
-  const int kb = K / 64;
-  for (int s = 3; s >= 2; --s)
-    if (pairs * s <= 74 && kb % s == 0) return s;
-  return 1;
+// Tile width and split-K factor for the fc2 GEMM ([M, D] = [M, 4D] x [D, 4D]^T).  Its K = 4D main loop is the longest
+// serial chain of a block while its D-wide output fills few CTA pairs, so when the pair grid leaves SMs idle the K
+// range is cut in up to 3 slices (grid.z); the slices write fp32 partial sums that the next LayerNorm adds in a fixed
+// order (deterministic).  Same per-k-block cost model as pick_pair_bn; a split pays ~2000 cycles for the extra
+// partial-sum traffic.
+struct Fc2Plan { int bn, splits; };
+static Fc2Plan pick_fc2_plan(const hq_ctx* ctx, int M, int N, int K) {
+  Fc2Plan best{0, 1};
+  if (!ctx->bf16 || M <= 128 || getenv("HQ_NO_SPLITK") != nullptr) return best;
+  static const int cand[5] = {256, 192, 128, 96, 64};
+  const int mt = (M + 255) / 256, kb = K / 64;
+  if (const char* f = getenv("HQ_FORCE_SPLITK")) {       // tests: pin the split factor (tile width 64)
+    const int s = atoi(f);
+    if (s >= 1 && s <= 3 && kb % s == 0 && N % 64 == 0) return Fc2Plan{64, s};
+  }
+  double best_cost = 1e30;
+  for (int bn : cand) {
+    if (N % bn != 0) continue;
+    for (int s = 1; s <= 3; ++s) {
+      if (kb % s != 0) continue;
+      const int pairs = mt * (N / bn) * s;
+      const double waves = static_cast<double>((pairs + 73) / 74);
+      const double ingest = (16384.0 + 64.0 * bn) / 42.6, mma = 2.0 * bn;
+      const double cost = waves * (kb / s) * (ingest > mma ? ingest : mma) + (s > 1 ? 2000.0 * s : 0.0) + 40.0 * bn;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = Fc2Plan{bn, s};
+      }
+    }
+  }
+  return best;
 }
 
 template <typename AT>
@@ -763,11 +821,11 @@ static void run_block(hq_ctx* ctx, cudaStream_t st, const BlockW& w, float* x, i
   memset(&eg, 0, sizeof(eg));
   eg.bias = w.b1; eg.out = mlp;
   gemm_any<EPI_GELU>(ctx, st, ctx->h, w.fc1, 0, M, 4 * D, D, eg);
-  const int splits = pick_fc2_splits(ctx, M, D, 4 * D);
-  if (splits > 1 && M <= ctx->ws_rows) {
-    gemm_fc2_split(ctx, st, ctx->mlp, w.fc2, M, D, 4 * D, splits, static_cast<AT*>(nullptr));
+  const Fc2Plan plan = pick_fc2_plan(ctx, M, D, 4 * D);
+  if (plan.splits > 1 && M <= ctx->ws_rows) {
+    gemm_fc2_split(ctx, st, ctx->mlp, w.fc2, M, D, 4 * D, plan.splits, plan.bn, static_cast<AT*>(nullptr));
     fold->partial = ctx->splitk_ws;
-    fold->n = splits;
+    fold->n = plan.splits;
     fold->stride = static_cast<size_t>(ctx->ws_rows) * D;
     fold->bias = w.b2;
   } else {
@@ -1373,8 +1431,8 @@ extern "C" int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, 
     const int n = static_cast<int>(ctx->trace_tags.size());
     cudaMemcpy(out_ns, dbuf, sizeof(unsigned long long) * 2 * n, cudaMemcpyDeviceToHost);
     for (int i = 0; i < n; ++i) {
-      strncpy(tags + static_cast<size_t>(i) * 24, ctx->trace_tags[i], 23);
-      tags[static_cast<size_t>(i) * 24 + 23] = 0;
+      strncpy(tags + static_cast<size_t>(i) * 48, ctx->trace_tags[i].c_str(), 47);
+      tags[static_cast<size_t>(i) * 48 + 47] = 0;
     }
     *n_entries = n;
   }

@@ -341,6 +341,232 @@ attention_kernel(int trace_id, const AT* __restrict__ q, const AT* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5b: depth-transformer attention (hierarchical_ar.py:696-710 via layers.py:93-187): a handful of keys (<= 8; the
+// parallel depth pass has 4 queries over 5 keys, no mask).  One warp per (query row, head); lane = (key slot g, 16-byte
+// piece c).  q, both key rows and both value rows of a lane are requested before anything is used: one memory round
+// trip, then shuffles.
+// ------------------------------------------------------------------------------------------------
+template <typename AT>
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_fewkeys_kernel(int trace_id, const AT* __restrict__ q, const AT* __restrict__ K, const AT* __restrict__ V,
+                         AT* __restrict__ out, int M, int n_heads, int D, int Tq, int t_stride, int n_keys) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * ATT_WARPS + w;
+  if (item >= M * n_heads) return;
+  const int m = item / n_heads, h = item % n_heads;
+  const int b = m / Tq;
+  const int g = lane >> 3, c = lane & 7;
+  const size_t base = static_cast<size_t>(b) * t_stride * D + h * 64 + c * 8;
+  const int t0 = g, t1 = g + 4;
+  const int t0c = t0 < n_keys ? t0 : 0, t1c = t1 < n_keys ? t1 : 0;   // clamped: loads are unconditional
+  float qv[8], k0[8], k1[8], v0[8], v1[8];
+  load8(q + static_cast<size_t>(m) * D + h * 64 + c * 8, qv);
+  load8(K + base + static_cast<size_t>(t0c) * D, k0);
+  load8(K + base + static_cast<size_t>(t1c) * D, k1);
+  load8(V + base + static_cast<size_t>(t0c) * D, v0);
+  load8(V + base + static_cast<size_t>(t1c) * D, v1);
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    s0 = fmaf(qv[e], k0[e] * 0.125f, s0);
+    s1 = fmaf(qv[e], k1[e] * 0.125f, s1);
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if (t0 >= n_keys) s0 = -INFINITY;
+  if (t1 >= n_keys) s1 = -INFINITY;
+  float mx = fmaxf(s0, s1);
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  const float e0 = (t0 < n_keys) ? expf(s0 - mx) : 0.f;
+  const float e1 = (t1 < n_keys) ? expf(s1 - mx) : 0.f;
+  float sum = e0 + e1;                       // identical on the 8 lanes of a key slot
+  sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+  const float inv = 1.0f / sum;
+  const float p0 = e0 * inv, p1 = e1 * inv;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    acc[e] = fmaf(p0, v0[e], p1 * v1[e]);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+  }
+  if (g == 0) store8(out + static_cast<size_t>(m) * D + h * 64 + c * 8, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5a: single-query attention over the spatial KV cache - the bandwidth-bound kernel of the loop.
+// One CTA per batch row.  The keys of a row are contiguous in the cache ([B][Tc][D]), so a producer warp streams
+// them through a ring of shared-memory stages with cp.async.bulk (one bulk copy of CH keys x D elements per stage,
+// completion on an mbarrier): first every K chunk, then every V chunk.  That keeps ~4 x 24 KB per CTA in flight with no
+// register staging, which is what a latency-bound chain of 12 such launches per position needs.  Consumer warps own
+// heads (ATTD_HPW per warp); lane = (key slot 0..3, 16-byte piece 0..7) inside a chunk.  Scores go to shared memory,
+// a full (not online) softmax is taken once all keys are seen - the same arithmetic as the reference's
+// bmm / softmax / bmm (layers.py:102, 183-186).
+// ------------------------------------------------------------------------------------------------
+constexpr int ATTD_MAXW = 12;     // consumer warps
+constexpr int ATTD_HPW = 3;       // heads per consumer warp (n_heads <= 36)
+constexpr int ATTD_STAGES = 4;
+
+template <typename AT>
+__global__ void __launch_bounds__((ATTD_MAXW + 1) * 32, 2)
+attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __restrict__ K, const AT* __restrict__ V,
+                        AT* __restrict__ out, int n_heads, int D, int t_stride, int n_keys, int CH, int ncw) {
+#if defined(__CUDA_ARCH__)
+  TraceScope trace_scope(trace_id);
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  const int stage_bytes = CH * D * static_cast<int>(sizeof(AT));
+  uint8_t* ring = att_smem;
+  float* sc = reinterpret_cast<float*>(att_smem + ATTD_STAGES * stage_bytes);              // [n_heads][ATT_MAX_KEYS]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sc + n_heads * ATT_MAX_KEYS);
+  uint64_t* empty_bar = full_bar + ATTD_STAGES;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int nck = (n_keys + CH - 1) / CH;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ATTD_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], ncw);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (w == ncw) {
+    // ---- producer: K chunks then V chunks through the ring ----
+    if (lane == 0) {
+      const AT* Kb = K + static_cast<size_t>(b) * t_stride * D;
+      const AT* Vb = V + static_cast<size_t>(b) * t_stride * D;
+      for (int i = 0; i < 2 * nck; ++i) {
+        const int s = i % ATTD_STAGES;
+        const uint32_t ph = (i / ATTD_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int ck = i < nck ? i : i - nck;
+        const int rows = (n_keys - ck * CH) < CH ? (n_keys - ck * CH) : CH;
+        const uint32_t bytes = static_cast<uint32_t>(rows) * D * sizeof(AT);
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        bulk_load_1d(ring + s * stage_bytes, (i < nck ? Kb : Vb) + static_cast<size_t>(ck) * CH * D, bytes, &full_bar[s]);
+      }
+    }
+    return;
+  }
+  if (w > ncw) return;
+
+  // ---- consumers ----
+  const int g = lane >> 3, c = lane & 7;
+  float qv[ATTD_HPW][8];
+#pragma unroll
+  for (int j = 0; j < ATTD_HPW; ++j) {
+    const int h = w + j * ncw;
+    if (h < n_heads) load8(q + static_cast<size_t>(b) * D + h * 64 + c * 8, qv[j]);
+  }
+  int i = 0;
+  for (; i < nck; ++i) {
+    const int s = i % ATTD_STAGES;
+    mbar_wait(&full_bar[s], (i / ATTD_STAGES) & 1);
+    const AT* st = reinterpret_cast<const AT*>(ring + s * stage_bytes);
+    for (int kk = 0; kk < CH; kk += 4) {
+      const int t = i * CH + kk + g;
+#pragma unroll
+      for (int j = 0; j < ATTD_HPW; ++j) {
+        const int h = w + j * ncw;
+        if (h < n_heads) {                                   // warp-uniform
+          float kv[8];
+          if (t < n_keys) {
+            load8(st + static_cast<size_t>(kk + g) * D + h * 64 + c * 8, kv);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) kv[e] = 0.f;
+          }
+          float sdot = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sdot = fmaf(qv[j][e], kv[e] * 0.125f, sdot);
+          sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+          sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+          sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+          if (c == 0 && t < n_keys) sc[h * ATT_MAX_KEYS + t] = sdot;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+  // ---- softmax per head (this warp's heads only; scores were written by this warp) ----
+  float inv[ATTD_HPW];
+#pragma unroll
+  for (int j = 0; j < ATTD_HPW; ++j) {
+    const int h = w + j * ncw;
+    inv[j] = 0.f;
+    if (h < n_heads) {
+      float* row = sc + h * ATT_MAX_KEYS;
+      float mx = -INFINITY;
+      for (int t = lane; t < n_keys; t += 32) mx = fmaxf(mx, row[t]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int t = lane; t < n_keys; t += 32) {
+        const float e = expf(row[t] - mx);
+        row[t] = e;
+        sum += e;
+      }
+      inv[j] = 1.0f / warp_sum(sum);
+    }
+  }
+  __syncwarp();
+  float acc[ATTD_HPW][8];
+#pragma unroll
+  for (int j = 0; j < ATTD_HPW; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  for (; i < 2 * nck; ++i) {
+    const int s = i % ATTD_STAGES;
+    mbar_wait(&full_bar[s], (i / ATTD_STAGES) & 1);
+    const AT* st = reinterpret_cast<const AT*>(ring + s * stage_bytes);
+    const int ck = i - nck;
+    for (int kk = 0; kk < CH; kk += 4) {
+      const int t = ck * CH + kk + g;
+      if (t < n_keys) {
+#pragma unroll
+        for (int j = 0; j < ATTD_HPW; ++j) {
+          const int h = w + j * ncw;
+          if (h < n_heads) {
+            float vv[8];
+            load8(st + static_cast<size_t>(kk + g) * D + h * 64 + c * 8, vv);
+            const float p = sc[h * ATT_MAX_KEYS + t] * inv[j];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(p, vv[e], acc[j][e]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+#pragma unroll
+  for (int j = 0; j < ATTD_HPW; ++j) {
+    const int h = w + j * ncw;
+    if (h < n_heads) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        acc[j][e] += __shfl_xor_sync(0xffffffffu, acc[j][e], 8);
+        acc[j][e] += __shfl_xor_sync(0xffffffffu, acc[j][e], 16);
+      }
+      if (g == 0) store8(out + static_cast<size_t>(b) * D + h * 64 + c * 8, acc[j]);
+    }
+  }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
 // K10: Sample(z; T, k, p) fused into one kernel per logits row (hierarchical_ar.py:762-785,
 // utils/sampling.py:12-37): z /= T; keep z >= k-th largest (ties kept); softmax; nucleus cut on the
 // *preceding* cumulative mass; renormalise; one categorical draw.

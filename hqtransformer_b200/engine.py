@@ -153,13 +153,13 @@ class Engine:
                          given_top=None, given_bot=None, codes_top=_ptr(codes_top), codes_bot=_ptr(codes_bot),
                          logits=None, sampling=sampling.to_c())
         out = (C.c_uint64 * (2 * max_entries))()
-        tags = C.create_string_buffer(24 * max_entries)
+        tags = C.create_string_buffer(48 * max_entries)
         n = C.c_int()
         st = torch.cuda.current_stream(self.device).cuda_stream
         check(self._lib.hq_trace_run(self._ctx, C.byref(args), C.c_void_p(st), out, tags, max_entries, C.byref(n)),
               self._ctx, "hq_trace_run")
         raw = tags.raw
-        return [(raw[24 * i:24 * i + 24].split(b"\0")[0].decode(), int(out[2 * i]), int(out[2 * i + 1]))
+        return [(raw[48 * i:48 * i + 48].split(b"\0")[0].decode(), int(out[2 * i]), int(out[2 * i + 1]))
                 for i in range(n.value)]
 
     def bench_attention(self, batch: int, n_keys: int, iters: int = 50) -> float:

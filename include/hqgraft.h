@@ -185,7 +185,8 @@ int hq_bench_attention(hq_ctx* ctx, int B, int n_keys, int iters, float* usec, v
 int hq_bench_gemm(hq_ctx* ctx, int kind, int M, int iters, float* usec, void* stream);
 
 /* One hq_run (device pointers) with the kernel timeline recorded on the device: out_ns[2i] / out_ns[2i+1] = first-CTA
- * start / last-CTA end (%globaltimer, ns) of the i-th kernel launch, tags[24*i] = its NUL-terminated tag. */
+ * start / last-CTA end (%globaltimer, ns) of the i-th kernel launch, tags[48*i] = its NUL-terminated tag
+ * (GEMMs carry their shape as ":MxNxK:s<splits>", the decode attention its cache length as ":t<keys>:B<rows>"). */
 int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, unsigned long long* out_ns, char* tags,
                  int max_entries, int* n_entries);
 

@@ -93,11 +93,13 @@ def test_bf16_sampling_is_deterministic_and_launch_mode_invariant(graph, pdl):
         assert torch.equal(ct, ct0) and torch.equal(cb, cb0)
 
 
-@pytest.mark.parametrize("B", [40, 150])
-def test_step_logits_bf16_wide_batch_vs_oracle(B):
+@pytest.mark.parametrize("B,force_split", [(40, None), (150, None), (40, "2"), (150, "2")])
+def test_step_logits_bf16_wide_batch_vs_oracle(B, force_split, monkeypatch):
     """Batches wide enough to take the CTA-pair GEMM kernel (M > 128) and the split-K fc2 + LayerNorm fold path;
     same tolerance as the narrow-batch logits test."""
     import hqtransformer_b200 as H
+    if force_split is not None:
+        monkeypatch.setenv("HQ_FORCE_SPLITK", force_split)      # pin the split-K factor of the fc2 GEMMs
     g, meta = load_golden("small_cls_greedy.npz")
     cfg = cfg_from_meta(meta)
     P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
