@@ -308,27 +308,42 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
         local_ct, local_cb = local["ct"], local["cb"]
         if not args.no_kernel_table:
             rows, span_us = kernel_table(eng, sp, B, cond_dev, local_ct, local_cb, D, peaks)
-            gemm_us = sum(r["us_per_position"] for r in rows if r["kernel"].startswith("gemm"))
-            gemm_flops = sum(r["flops"] * r["launches_per_position"] for r in rows if "flops" in r)
-            gemm_bytes = sum(r["bytes"] * r["launches_per_position"] for r in rows if r["kernel"].startswith("gemm"))
-            att = [r for r in rows if r["kernel"].startswith("attention_decode")]
-            att_us = sum(r["us_per_position"] for r in att)
-            # dominant kernel = the tcgen05 GEMM family (one kernel template; shapes differ): aggregate over its launches
+            traffic = {}
+            tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+            if os.path.isfile(tp):
+                traffic = json.load(open(tp))
+            gemm_rows = [r for r in rows if r["kernel"].startswith("gemm")]
+            gemm_us = sum(r["us_per_position"] for r in gemm_rows)
+            gemm_flops = sum(r["flops"] * r["launches_per_position"] for r in gemm_rows)
+            gemm_bytes = sum(r["bytes"] * r["launches_per_position"] for r in gemm_rows)
+            # dominant kernel = the GEMM launch type with the largest share of a top position
+            dom = max(gemm_rows, key=lambda r: r["us_per_position"])
             line["roofline"] = {
-                "bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (all GEMM launches of a top position)",
-                "achieved": gemm_flops / gemm_us * 1e-6, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": gemm_flops / gemm_us * 1e-6 / peaks["bf16_tflops_sustained"], "traffic": None,
-                "share_of_step": gemm_us / span_us,
-                "hbm_view": {"achieved_gbs": gemm_bytes / gemm_us * 1e-3, "peak_gbs": peaks["hbm_gbs"],
-                             "frac": gemm_bytes / gemm_us * 1e-3 / peaks["hbm_gbs"]},
-                "peak_source": peaks["source"] + ", sustained figure (kernels timed inside a long step)",
-                "how": "device %globaltimer per launch inside the replayed loop (hq_trace_run), positions 30-33"}
+                "bound": "tensor", "kernel": dom["kernel"], "achieved": dom["tflops"], "peak": peaks["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": dom["frac_tensor"],
+                "traffic": traffic.get(dom["kernel"], {}).get("dram_bytes"),
+                "algorithmic_bytes_per_launch": dom["bytes"], "algorithmic_flops_per_launch": dom["flops"],
+                "us_per_launch": dom["us"], "share_of_step": dom["share"],
+                "hbm_view": {"achieved_gbs": dom["weight_gbs"], "peak_gbs": peaks["hbm_gbs"], "frac": dom["frac_hbm"]},
+                "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                "how": "device %globaltimer per launch inside the replayed loop (hq_trace_run), top positions 30-33; "
+                       "traffic from profiles/r1_ncu_traffic.json (ncu --set full of the same command)"}
+            line["roofline_gemm_all"] = {
+                "bound": "tensor", "kernel": "all tcgen05 GEMM launches of a top position", "achieved": gemm_flops / gemm_us * 1e-6,
+                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": gemm_flops / gemm_us * 1e-6 / peaks["bf16_tflops_sustained"], "share_of_step": gemm_us / span_us,
+                "weight_stream_gbs": gemm_bytes / gemm_us * 1e-3}
+            att = [r for r in rows if r["kernel"].startswith("attention_decode")]
             if att:
+                att_us = sum(r["us_per_position"] for r in att)
                 a_bytes = sum(r["bytes"] * r["launches_per_position"] for r in att)
                 line["roofline_attention"] = {
                     "bound": "hbm", "kernel": "attention_decode_kernel", "achieved": a_bytes / att_us * 1e-3,
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a_bytes / att_us * 1e-3 / peaks["hbm_gbs"],
-                    "traffic": None, "share_of_step": att_us / span_us, "keys": [r["keys"] for r in att]}
+                    "traffic": traffic.get("attention_decode:t64:B256", {}).get("dram_bytes"),
+                    "traffic_note": "ncu capture at 64 keys (100.3 MB DRAM vs 100.7 MB algorithmic); timed launches here have "
+                                    + str(sorted(set(r["keys"] for r in att))) + " keys",
+                    "share_of_step": att_us / span_us}
             line["kernels"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()
                                 if k not in ("flops", "bytes")} for r in sorted(rows, key=lambda r: -r["us_per_position"])]
             line["trace_us_per_position"] = span_us

@@ -1417,11 +1417,14 @@ extern "C" int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, 
   for (auto it = ctx->graphs.begin(); it != ctx->graphs.end();) {
     if (it->first.tracing) { cudaGraphExecDestroy(it->second.exec); it = ctx->graphs.erase(it); } else ++it;
   }
+  const bool saved_pdl = ctx->use_pdl;
+  ctx->use_pdl = false;   // with PDL a kernel is resident (waiting) long before it can run: lifetimes would overlap
   ctx->tracing = true;
   ctx->trace_cap = max_entries;
   ctx->trace_tags.clear();
   int rc = run_impl(ctx, args, st, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);
   ctx->tracing = false;
+  ctx->use_pdl = saved_pdl;
   cudaError_t se = cudaStreamSynchronize(st);
   if (rc == HQ_OK && se != cudaSuccess) {
     set_err(ctx, "hq_trace_run: %s", cudaGetErrorString(se));
