@@ -387,8 +387,8 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
     if ((rc = get_encode_fn(ctx, &ctx->encode))) return rc;
     if ((rc = set_gemm_attrs(ctx))) return rc;
   }
-  if ((rc = set_smem(ctx, attention_decode_kernel<bf16>, 113 * 1024))) return rc;
-  if ((rc = set_smem(ctx, attention_decode_kernel<float>, 113 * 1024))) return rc;
+  if ((rc = set_smem(ctx, attention_decode_kernel<bf16>, 64 * 1024))) return rc;
+  if ((rc = set_smem(ctx, attention_decode_kernel<float>, 64 * 1024))) return rc;
   HQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
 
   // ---- parameters ----
@@ -644,6 +644,7 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
   }
   if (bn > 0 && N % bn == 0) {
     dim3 grid(2 * (N / bn), (M + 255) / 256, splits);
+
 #define HQ_LAUNCH2(BN)                                                                                             \
   case BN:                                                                                                         \
     launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc2_kernel<BN, EPI, bf16>, grid, dim3(192), Tc2Cfg<BN>::SMEM_BYTES, mA, mW16, M, N, K,  \
@@ -705,30 +706,39 @@ static void layernorm_act(hq_ctx* ctx, cudaStream_t st, float* x, const float* g
   if (fold) *fold = Fold();
 }
 
-// Shared-memory plan of attention_decode_kernel for this model: keys per ring stage and dynamic smem bytes.
+// Launch plan of attention_decode_kernel for this model: head groups per image, keys per ring stage, dynamic smem.
 template <typename AT>
-static void attn_decode_plan(const hq_ctx* ctx, int* CH, int* ncw, size_t* smem) {
-  const int row_bytes = ctx->D * static_cast<int>(sizeof(AT));
-  int ch = (24576 / row_bytes) / 4 * 4;
+static bool attn_decode_plan(const hq_ctx* ctx, int* CH, int* hpc, int* groups, size_t* smem) {
+  int g = 1;
+  for (int cand : {4, 3, 2, 1})
+    if (ctx->nh % cand == 0 && ctx->nh / cand <= ATTD_MAXHPC) { g = cand; break; }
+  if (const char* f = getenv("HQ_ATTN_GROUPS")) {          // experiments: pin the number of head groups per image
+    const int v = atoi(f);
+    if (v >= 1 && ctx->nh % v == 0) g = v;
+  }
+  if (ctx->nh / g > ATTD_MAXHPC) return false;
+  *groups = g;
+  *hpc = ctx->nh / g;
+  const int row_bytes = *hpc * 64 * static_cast<int>(sizeof(AT));
+  int ch = (6144 / row_bytes) / 4 * 4;          // ~6 KB per stage
   if (ch < 4) ch = 4;
-  if (ch > 32) ch = 32;
+  if (ch > 16) ch = 16;
   *CH = ch;
-  *ncw = ctx->nh < ATTD_MAXW ? ctx->nh : ATTD_MAXW;
-  *smem = static_cast<size_t>(ATTD_STAGES) * ch * row_bytes + static_cast<size_t>(ctx->nh) * ATT_MAX_KEYS * 4 +
+  *smem = static_cast<size_t>(ATTD_STAGES) * ch * row_bytes + static_cast<size_t>(*hpc) * ATT_MAX_KEYS * 4 +
           2 * ATTD_STAGES * 8 + 128;
+  return *smem <= 64 * 1024;
 }
 
 template <typename AT>
 static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, const AT* V, AT* out, int M, int Tq,
                       int t_stride, int kbase, int causal) {
-  int CH, ncw;
-  size_t smem;
-  attn_decode_plan<AT>(ctx, &CH, &ncw, &smem);
-  if (Tq == 1 && !causal && ctx->nh <= ATTD_MAXW * ATTD_HPW && smem <= 113 * 1024 && getenv("HQ_ATTN_GENERIC") == nullptr) {
-    // spatial decode: one CTA per batch row, K/V streamed through shared memory by bulk async copies
+  int CH = 0, hpc = 0, groups = 0;
+  size_t smem = 0;
+  if (Tq == 1 && !causal && getenv("HQ_ATTN_GENERIC") == nullptr && attn_decode_plan<AT>(ctx, &CH, &hpc, &groups, &smem)) {
+    // spatial decode: (image, head group) CTAs, K/V streamed through shared memory by bulk async copies
     if (ctx->tracing) ctx->tag_suffix = ":t" + std::to_string(kbase) + ":B" + std::to_string(M);
-    launch_k(ctx, st, "attention_decode", attention_decode_kernel<AT>, dim3(M), dim3((ncw + 1) * 32), smem, q, K, V, out,
-             ctx->nh, ctx->D, t_stride, kbase, CH, ncw);
+    launch_k(ctx, st, "attention_decode", attention_decode_kernel<AT>, dim3(M * groups), dim3((hpc + 1) * 32), smem, q, K, V,
+             out, ctx->D, t_stride, kbase, CH, hpc, groups);
     return;
   }
   const int items = M * ctx->nh;
@@ -765,10 +775,10 @@ static void gemm_fc2_split(hq_ctx*, cudaStream_t, const ABuf&, const Weight&, in
 // order (deterministic).  Same per-k-block cost model as pick_pair_bn; a split pays ~2000 cycles for the extra
 // partial-sum traffic.
 struct Fc2Plan { int bn, splits; };
-static Fc2Plan pick_fc2_plan(const hq_ctx* ctx, int M, int N, int K) {
+static Fc2Plan pick_resid_plan(const hq_ctx* ctx, int M, int N, int K) {
   Fc2Plan best{0, 1};
   if (!ctx->bf16 || M <= 128 || getenv("HQ_NO_SPLITK") != nullptr) return best;
-  static const int cand[5] = {256, 192, 128, 96, 64};
+  static const int cand[6] = {256, 192, 128, 96, 64, 32};
   const int mt = (M + 255) / 256, kb = K / 64;
   if (const char* f = getenv("HQ_FORCE_SPLITK")) {       // tests: pin the split factor (tile width 64)
     const int s = atoi(f);
@@ -782,7 +792,7 @@ static Fc2Plan pick_fc2_plan(const hq_ctx* ctx, int M, int N, int K) {
       const int pairs = mt * (N / bn) * s;
       const double waves = static_cast<double>((pairs + 73) / 74);
       const double ingest = (16384.0 + 64.0 * bn) / 42.6, mma = 2.0 * bn;
-      const double cost = waves * (kb / s) * (ingest > mma ? ingest : mma) + (s > 1 ? 2000.0 * s : 0.0) + 40.0 * bn;
+      const double cost = waves * (kb / s) * (ingest > mma ? ingest : mma) + (s > 1 ? 400.0 * s : 0.0) + 40.0 * bn;
       if (cost < best_cost) {
         best_cost = cost;
         best = Fc2Plan{bn, s};
@@ -790,6 +800,26 @@ static Fc2Plan pick_fc2_plan(const hq_ctx* ctx, int M, int N, int K) {
     }
   }
   return best;
+}
+
+// x += A W^T + bias.  Either in the GEMM epilogue, or (split-K) as fp32 partial sums that the next LayerNorm on this
+// residual stream folds in; `fold` carries that pending state to the LayerNorm launch.
+template <typename AT>
+static void gemm_resid(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, const float* bias, float* x, int M,
+                       int N, int K, Fold* fold) {
+  const Fc2Plan plan = pick_resid_plan(ctx, M, N, K);
+  if (plan.splits > 1 && M <= ctx->ws_rows) {
+    gemm_fc2_split(ctx, st, A, W, M, N, K, plan.splits, plan.bn, static_cast<AT*>(nullptr));
+    fold->partial = ctx->splitk_ws;
+    fold->n = plan.splits;
+    fold->stride = static_cast<size_t>(ctx->ws_rows) * N;
+    fold->bias = bias;
+    return;
+  }
+  EpiParams<AT> e;
+  memset(&e, 0, sizeof(e));
+  e.bias = bias; e.x = x;
+  gemm_any<EPI_RESID>(ctx, st, A, W, 0, M, N, K, e);
 }
 
 template <typename AT>
@@ -812,28 +842,13 @@ static void run_block(hq_ctx* ctx, cudaStream_t st, const BlockW& w, float* x, i
     gemm_any<EPI_QKV>(ctx, st, ctx->h, w.qkv, 0, M, 3 * D, D, ep);
     attention<AT>(ctx, st, q, kdst, vdst, att, M, rpb, t_stride, n_keys_base, causal);
   }
-  EpiParams<AT> er;
-  memset(&er, 0, sizeof(er));
-  er.bias = w.bproj; er.x = x;
-  gemm_any<EPI_RESID>(ctx, st, ctx->att, w.proj, 0, M, D, D, er);
-  layernorm_act<AT>(ctx, st, x, w.ln2g, w.ln2b, h, M);
+  gemm_resid<AT>(ctx, st, ctx->att, w.proj, w.bproj, x, M, D, D, fold);
+  layernorm_act<AT>(ctx, st, x, w.ln2g, w.ln2b, h, M, fold);
   EpiParams<AT> eg;
   memset(&eg, 0, sizeof(eg));
   eg.bias = w.b1; eg.out = mlp;
   gemm_any<EPI_GELU>(ctx, st, ctx->h, w.fc1, 0, M, 4 * D, D, eg);
-  const Fc2Plan plan = pick_fc2_plan(ctx, M, D, 4 * D);
-  if (plan.splits > 1 && M <= ctx->ws_rows) {
-    gemm_fc2_split(ctx, st, ctx->mlp, w.fc2, M, D, 4 * D, plan.splits, plan.bn, static_cast<AT*>(nullptr));
-    fold->partial = ctx->splitk_ws;
-    fold->n = plan.splits;
-    fold->stride = static_cast<size_t>(ctx->ws_rows) * D;
-    fold->bias = w.b2;
-  } else {
-    EpiParams<AT> e2;
-    memset(&e2, 0, sizeof(e2));
-    e2.bias = w.b2; e2.x = x;
-    gemm_any<EPI_RESID>(ctx, st, ctx->mlp, w.fc2, 0, M, D, 4 * D, e2);
-  }
+  gemm_resid<AT>(ctx, st, ctx->mlp, w.fc2, w.b2, x, M, D, 4 * D, fold);
 }
 
 struct RunFlags {
@@ -1418,7 +1433,8 @@ extern "C" int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, 
     if (it->first.tracing) { cudaGraphExecDestroy(it->second.exec); it = ctx->graphs.erase(it); } else ++it;
   }
   const bool saved_pdl = ctx->use_pdl;
-  ctx->use_pdl = false;   // with PDL a kernel is resident (waiting) long before it can run: lifetimes would overlap
+  // with PDL a kernel is resident (waiting) long before it can run, so lifetimes overlap: off unless asked for
+  if (getenv("HQ_TRACE_PDL") == nullptr) ctx->use_pdl = false;
   ctx->tracing = true;
   ctx->trace_cap = max_entries;
   ctx->trace_tags.clear();

@@ -374,6 +374,7 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
   const int n0 = (blockIdx.x >> 1) * BN;                               // the pair's columns
   const int num_kb = (K / C::BK) / static_cast<int>(gridDim.z);        // split-K: this pair's share of the k-blocks
   const int kb0 = static_cast<int>(blockIdx.z) * num_kb;
+
   if (EPI == EPI_F32) ep.outf += static_cast<size_t>(blockIdx.z) * ep.split_stride;
   if (threadIdx.x == 0) trace_stamp(ep.trace, 0);            // CTA start
 

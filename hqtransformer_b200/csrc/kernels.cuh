@@ -403,166 +403,147 @@ attention_fewkeys_kernel(int trace_id, const AT* __restrict__ q, const AT* __res
 
 // ------------------------------------------------------------------------------------------------
 // K5a: single-query attention over the spatial KV cache - the bandwidth-bound kernel of the loop.
-// One CTA per batch row.  The keys of a row are contiguous in the cache ([B][Tc][D]), so a producer warp streams
-// them through a ring of shared-memory stages with cp.async.bulk (one bulk copy of CH keys x D elements per stage,
-// completion on an mbarrier): first every K chunk, then every V chunk.  That keeps ~4 x 24 KB per CTA in flight with no
-// register staging, which is what a latency-bound chain of 12 such launches per position needs.  Consumer warps own
-// heads (ATTD_HPW per warp); lane = (key slot 0..3, 16-byte piece 0..7) inside a chunk.  Scores go to shared memory,
-// a full (not online) softmax is taken once all keys are seen - the same arithmetic as the reference's
-// bmm / softmax / bmm (layers.py:102, 183-186).
+// One CTA per (batch row, head group): grid = B * G CTAs, HPC = n_heads / G heads (= consumer warps) each, so that
+// the ~1000 small CTAs balance over the 148 SMs (one CTA per image left 40 SMs with half the work of the others).
+// A producer warp streams the group's slice of the row's keys and then values - HPC*64 contiguous elements per key -
+// through a ring of shared-memory stages with cp.async.bulk (CH keys per stage, completion on mbarriers): no register
+// staging, ~4 stages in flight per CTA and 8 CTAs per SM.  All cached keys except the newest one were written by
+// earlier launches, so with programmatic dependent launch the producer fills the ring BEFORE griddepcontrol.wait and
+// only the chunk holding the newest key (and everything after it) waits for the QKV GEMM.
+// Consumer warp = one head; lane = (key slot 0..3, 16-byte piece 0..7).  Scores go to shared memory, a full (not
+// online) softmax is taken once all keys are seen - the arithmetic of the reference's bmm / softmax / bmm
+// (layers.py:102, 183-186).
 // ------------------------------------------------------------------------------------------------
-constexpr int ATTD_MAXW = 12;     // consumer warps
-constexpr int ATTD_HPW = 3;       // heads per consumer warp (n_heads <= 36)
+constexpr int ATTD_MAXHPC = 24;   // heads (consumer warps) per CTA
 constexpr int ATTD_STAGES = 4;
 
 template <typename AT>
-__global__ void __launch_bounds__((ATTD_MAXW + 1) * 32, 2)
+__global__ void __launch_bounds__((ATTD_MAXHPC + 1) * 32)
 attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __restrict__ K, const AT* __restrict__ V,
-                        AT* __restrict__ out, int n_heads, int D, int t_stride, int n_keys, int CH, int ncw) {
+                        AT* __restrict__ out, int D, int t_stride, int n_keys, int CH, int hpc, int groups) {
 #if defined(__CUDA_ARCH__)
   TraceScope trace_scope(trace_id);
   extern __shared__ __align__(128) uint8_t att_smem[];
-  const int stage_bytes = CH * D * static_cast<int>(sizeof(AT));
+  const int slice = hpc * 64;                                       // elements of one key owned by this CTA
+  const int row_bytes = slice * static_cast<int>(sizeof(AT));
+  const int stage_bytes = CH * row_bytes;
   uint8_t* ring = att_smem;
-  float* sc = reinterpret_cast<float*>(att_smem + ATTD_STAGES * stage_bytes);              // [n_heads][ATT_MAX_KEYS]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sc + n_heads * ATT_MAX_KEYS);
+  float* sc = reinterpret_cast<float*>(att_smem + ATTD_STAGES * stage_bytes);              // [hpc][ATT_MAX_KEYS]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sc + hpc * ATT_MAX_KEYS);
   uint64_t* empty_bar = full_bar + ATTD_STAGES;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / groups, grp = blockIdx.x % groups;
+  const int h0 = grp * hpc;
   const int nck = (n_keys + CH - 1) / CH;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < ATTD_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], ncw);
+      mbar_init(&empty_bar[s], hpc);
     }
     fence_barrier_init();
   }
   __syncthreads();
   pdl_launch_dependents();
-  pdl_wait();
 
-  if (w == ncw) {
-    // ---- producer: K chunks then V chunks through the ring ----
+  if (w == hpc) {
+    // ---- producer: K chunks then V chunks through the ring; one bulk copy per key (slice bytes, contiguous) ----
     if (lane == 0) {
-      const AT* Kb = K + static_cast<size_t>(b) * t_stride * D;
-      const AT* Vb = V + static_cast<size_t>(b) * t_stride * D;
+      const AT* Kb = K + static_cast<size_t>(b) * t_stride * D + h0 * 64;
+      const AT* Vb = V + static_cast<size_t>(b) * t_stride * D + h0 * 64;
+      bool waited = false;
       for (int i = 0; i < 2 * nck; ++i) {
         const int s = i % ATTD_STAGES;
         const uint32_t ph = (i / ATTD_STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
         const int ck = i < nck ? i : i - nck;
         const int rows = (n_keys - ck * CH) < CH ? (n_keys - ck * CH) : CH;
-        const uint32_t bytes = static_cast<uint32_t>(rows) * D * sizeof(AT);
-        mbar_arrive_expect_tx(&full_bar[s], bytes);
-        bulk_load_1d(ring + s * stage_bytes, (i < nck ? Kb : Vb) + static_cast<size_t>(ck) * CH * D, bytes, &full_bar[s]);
+        // chunks made of keys older than the newest one do not depend on the previous kernel
+        if (!waited && (i >= nck || ck * CH + rows >= n_keys)) {
+          pdl_wait();
+          waited = true;
+        }
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(rows) * row_bytes);
+        const AT* src = (i < nck ? Kb : Vb) + static_cast<size_t>(ck) * CH * D;
+        for (int r = 0; r < rows; ++r)
+          bulk_load_1d(ring + s * stage_bytes + r * row_bytes, src + static_cast<size_t>(r) * D, row_bytes, &full_bar[s]);
       }
     }
     return;
   }
-  if (w > ncw) return;
+  if (w > hpc) return;
 
-  // ---- consumers ----
+  // ---- consumers: warp w owns head h0 + w ----
+  pdl_wait();
   const int g = lane >> 3, c = lane & 7;
-  float qv[ATTD_HPW][8];
-#pragma unroll
-  for (int j = 0; j < ATTD_HPW; ++j) {
-    const int h = w + j * ncw;
-    if (h < n_heads) load8(q + static_cast<size_t>(b) * D + h * 64 + c * 8, qv[j]);
-  }
+  const int h = h0 + w;
+  float qv[8];
+  load8(q + static_cast<size_t>(b) * D + h * 64 + c * 8, qv);
+  float* row = sc + w * ATT_MAX_KEYS;
   int i = 0;
   for (; i < nck; ++i) {
     const int s = i % ATTD_STAGES;
     mbar_wait(&full_bar[s], (i / ATTD_STAGES) & 1);
-    const AT* st = reinterpret_cast<const AT*>(ring + s * stage_bytes);
+    const AT* st = reinterpret_cast<const AT*>(ring + s * stage_bytes) + w * 64 + c * 8;
     for (int kk = 0; kk < CH; kk += 4) {
       const int t = i * CH + kk + g;
+      float kv[8];
+      if (t < n_keys) {
+        load8(st + static_cast<size_t>(kk + g) * slice, kv);
+      } else {
 #pragma unroll
-      for (int j = 0; j < ATTD_HPW; ++j) {
-        const int h = w + j * ncw;
-        if (h < n_heads) {                                   // warp-uniform
-          float kv[8];
-          if (t < n_keys) {
-            load8(st + static_cast<size_t>(kk + g) * D + h * 64 + c * 8, kv);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) kv[e] = 0.f;
-          }
-          float sdot = 0.f;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) sdot = fmaf(qv[j][e], kv[e] * 0.125f, sdot);
-          sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-          sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-          sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
-          if (c == 0 && t < n_keys) sc[h * ATT_MAX_KEYS + t] = sdot;
-        }
+        for (int e = 0; e < 8; ++e) kv[e] = 0.f;
       }
+      float sdot = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sdot = fmaf(qv[e], kv[e] * 0.125f, sdot);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+      if (c == 0 && t < n_keys) row[t] = sdot;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
-  // ---- softmax per head (this warp's heads only; scores were written by this warp) ----
-  float inv[ATTD_HPW];
-#pragma unroll
-  for (int j = 0; j < ATTD_HPW; ++j) {
-    const int h = w + j * ncw;
-    inv[j] = 0.f;
-    if (h < n_heads) {
-      float* row = sc + h * ATT_MAX_KEYS;
-      float mx = -INFINITY;
-      for (int t = lane; t < n_keys; t += 32) mx = fmaxf(mx, row[t]);
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int t = lane; t < n_keys; t += 32) {
-        const float e = expf(row[t] - mx);
-        row[t] = e;
-        sum += e;
-      }
-      inv[j] = 1.0f / warp_sum(sum);
-    }
+  // ---- softmax over this head's scores ----
+  float mx = -INFINITY;
+  for (int t = lane; t < n_keys; t += 32) mx = fmaxf(mx, row[t]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int t = lane; t < n_keys; t += 32) {
+    const float e = expf(row[t] - mx);
+    row[t] = e;
+    sum += e;
   }
+  const float inv = 1.0f / warp_sum(sum);
   __syncwarp();
-  float acc[ATTD_HPW][8];
+  float acc[8];
 #pragma unroll
-  for (int j = 0; j < ATTD_HPW; ++j)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   for (; i < 2 * nck; ++i) {
     const int s = i % ATTD_STAGES;
     mbar_wait(&full_bar[s], (i / ATTD_STAGES) & 1);
-    const AT* st = reinterpret_cast<const AT*>(ring + s * stage_bytes);
+    const AT* st = reinterpret_cast<const AT*>(ring + s * stage_bytes) + w * 64 + c * 8;
     const int ck = i - nck;
     for (int kk = 0; kk < CH; kk += 4) {
       const int t = ck * CH + kk + g;
       if (t < n_keys) {
+        float vv[8];
+        load8(st + static_cast<size_t>(kk + g) * slice, vv);
+        const float p = row[t] * inv;
 #pragma unroll
-        for (int j = 0; j < ATTD_HPW; ++j) {
-          const int h = w + j * ncw;
-          if (h < n_heads) {
-            float vv[8];
-            load8(st + static_cast<size_t>(kk + g) * D + h * 64 + c * 8, vv);
-            const float p = sc[h * ATT_MAX_KEYS + t] * inv[j];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(p, vv[e], acc[j][e]);
-          }
-        }
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vv[e], acc[e]);
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
 #pragma unroll
-  for (int j = 0; j < ATTD_HPW; ++j) {
-    const int h = w + j * ncw;
-    if (h < n_heads) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        acc[j][e] += __shfl_xor_sync(0xffffffffu, acc[j][e], 8);
-        acc[j][e] += __shfl_xor_sync(0xffffffffu, acc[j][e], 16);
-      }
-      if (g == 0) store8(out + static_cast<size_t>(b) * D + h * 64 + c * 8, acc[j]);
-    }
+  for (int e = 0; e < 8; ++e) {
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
   }
+  if (g == 0) store8(out + static_cast<size_t>(b) * D + h * 64 + c * 8, acc);
 #endif
 }
 

@@ -7,6 +7,9 @@ from hqtransformer_b200.engine import SamplingParams
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 P0, P1 = 30, 34
+for a in sys.argv:
+    if a.startswith("--pos="):
+        P0 = int(a.split("=")[1]); P1 = P0 + 4
 graph = "--no-graph" not in sys.argv
 pdl = "--no-pdl" not in sys.argv
 cfg = os.path.join(os.path.dirname(H.__file__), "configs", "imagenet_l12.yaml")
@@ -41,7 +44,16 @@ for tag, s, e in tl:
 span = max(e for _, _, e in tl) - t0
 print(f"B={B} graph={graph} pdl={pdl}: {len(tl)} launches over {n_pos} positions, span {span/1e3/n_pos:.1f} us/position, "
       f"sum of kernel lifetimes {sum(v[1] for v in agg.values())/1e3/n_pos:.1f} us/position, sum of gaps {total_gap/1e3/n_pos:.1f} us/position")
-print(f"{'kernel':22s} {'n/pos':>6s} {'avg_us':>8s} {'avg_gap_before_us':>18s} {'us/pos':>9s}")
+e2e = collections.OrderedDict()
+prev = None
+for tag, s, e in tl:
+    if prev is not None:
+        d = e2e.setdefault(tag, [0, 0.0])
+        d[0] += 1
+        d[1] += e - prev
+    prev = e
+print(f"{'kernel':34s} {'n/pos':>6s} {'avg_us':>8s} {'gap_before':>10s} {'us/pos':>8s} {'end-to-end delta us':>20s}")
 for tag, (n, dur, gap) in agg.items():
-    print(f"{tag:22s} {n/n_pos:6.1f} {dur/n/1e3:8.2f} {gap/n/1e3:18.2f} {dur/1e3/n_pos:9.1f}")
+    dd = e2e.get(tag, [1, 0.0])
+    print(f"{tag:34s} {n/n_pos:6.1f} {dur/n/1e3:8.2f} {gap/n/1e3:10.2f} {dur/1e3/n_pos:8.1f} {dd[1]/dd[0]/1e3:20.2f}")
 json.dump([(t, s - t0, e - t0) for t, s, e in tl], open(f"gpurun_out/timeline_B{B}_g{int(graph)}_p{int(pdl)}_L{conf.stage2.hparams.n_layers}.json", "w"))
