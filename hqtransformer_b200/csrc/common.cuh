@@ -200,15 +200,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++polls > (1u << 24)) __trap();
   }
 }
-// Whole-warp wait: one lane polls, the others park at the warp barrier (no issue slots), then every lane observes
-// the completed phase itself (its own acquire of the data the async proxy wrote).
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
-  if (lane == 0) mbar_wait(bar, parity);
-  __syncwarp();
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) - 2D tile load global -> shared, completion on an mbarrier
 // ------------------------------------------------------------------------------------------------

@@ -565,11 +565,6 @@ extern "C" size_t hq_device_bytes(const hq_ctx* ctx) { return ctx ? ctx->device_
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-static inline void note_launch(hq_ctx* ctx) {
-  ++ctx->launches;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess && ctx->launch_err == cudaSuccess) ctx->launch_err = e;
-}
 
 
 // ------------------------------------------------------------------------------------------------

@@ -479,6 +479,8 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
   const int h = h0 + w;
   float qv[8];
   load8(q + static_cast<size_t>(b) * D + h * 64 + c * 8, qv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) qv[e] *= 0.125f;     // hs^-1/2 = 2^-3 is exact: same products as scaling K (layers.py:102)
   float* row = sc + w * ATT_MAX_KEYS;
   int i = 0;
   for (; i < nck; ++i) {
@@ -496,7 +498,7 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
       }
       float sdot = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sdot = fmaf(qv[e], kv[e] * 0.125f, sdot);
+      for (int e = 0; e < 8; ++e) sdot = fmaf(qv[e], kv[e], sdot);
       sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
       sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
       sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
