@@ -608,7 +608,7 @@ struct OpMaxI { __device__ int operator()(int a, int b) const { return a > b ? a
 struct OpMinI { __device__ int operator()(int a, int b) const { return a < b ? a : b; } };
 
 template <int NTHR>
-__global__ void __launch_bounds__(NTHR) sample_kernel(int trace_id, SampleArgs a) {
+__global__ void __launch_bounds__(NTHR, NTHR == 256 ? 3 : 1) sample_kernel(int trace_id, SampleArgs a) {
   TraceScope trace_scope(trace_id);
   pdl_launch_dependents();   // programmatic dependent launch: let the next kernel get resident ...
   pdl_wait();                // ... and wait for the previous kernel's results (no-ops without the launch attribute)
@@ -695,18 +695,18 @@ __global__ void __launch_bounds__(NTHR) sample_kernel(int trace_id, SampleArgs a
       if (float_order_key(z[i]) < thr) z[i] = -INFINITY;
   }
 
-  // ---- softmax numerators (F.softmax, hierarchical_ar.py:765) ----
-  float wgt[SMP_IPT];
+  // ---- softmax (F.softmax, hierarchical_ar.py:765), in place: z[] becomes the probabilities ----
   float lsum = 0.f;
 #pragma unroll
   for (int i = 0; i < SMP_IPT; ++i) {
-    wgt[i] = (z[i] == -INFINITY) ? 0.f : expf(z[i] - mx);
-    lsum += wgt[i];
+    z[i] = (z[i] == -INFINITY) ? 0.f : expf(z[i] - mx);
+    lsum += z[i];
   }
   const float Z = block_reduce(lsum, OpSumF(), 0.f, fscratch);
   const float invZ = 1.0f / Z;
 #pragma unroll
-  for (int i = 0; i < SMP_IPT; ++i) wgt[i] *= invZ;   // probabilities
+  for (int i = 0; i < SMP_IPT; ++i) z[i] *= invZ;
+  float (&wgt)[SMP_IPT] = z;
 
   // ---- top-p (sampling.py:22-37): keep the smallest upper set {p_i >= c*} whose mass reaches p; among
   //      entries equal to c* keep, in index order, those whose preceding cumulative mass is still < p ----

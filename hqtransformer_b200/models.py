@@ -241,11 +241,20 @@ class iHQGPT:
         """Conditioning tensor for the engine: int64 [B] class ids, int64 [B, ctx_len_txt] text ids, or None."""
         if self.use_cls_cond:
             if isinstance(cond, int):
+                if not 0 <= cond < self.n_classes:       # nn.Embedding would raise IndexError (sampling.py:186)
+                    raise IndexError(f"class id {cond} out of range [0, {self.n_classes})")
                 return torch.full((num_candidates,), cond, dtype=torch.int64, device=self.device)
             c = torch.as_tensor(cond, dtype=torch.int64).reshape(-1).to(self.device)
+            if c.numel() and (int(c.min()) < 0 or int(c.max()) >= self.n_classes):
+                raise IndexError(f"class ids out of range [0, {self.n_classes})")
             return c.repeat(num_candidates) if c.numel() == 1 else c
         if self.use_txt_cond:
-            return torch.as_tensor(cond, dtype=torch.int64).to(self.device).contiguous()
+            c = torch.as_tensor(cond, dtype=torch.int64).to(self.device).contiguous()
+            if c.dim() != 2 or c.shape[1] != self.ctx_len_txt:
+                raise ValueError(f"text condition must be int64 [B, {self.ctx_len_txt}], got {tuple(c.shape)}")
+            if c.numel() and (int(c.min()) < 0 or int(c.max()) >= self.vocab_size_txt):
+                raise IndexError(f"text token ids out of range [0, {self.vocab_size_txt})")
+            return c
         return None
 
 

@@ -44,6 +44,10 @@ def sampling_ihqgpt(model, num_candidates: int, cond, top_k_top: Optional[float]
     given = None
     if given_top_code is not None:
         given = given_top_code[:, :max_seq_len].to(device=dev, dtype=torch.int64).contiguous()
+        if tuple(given.shape) != (B, max_seq_len):
+            raise ValueError(f"given_top_code must be [B, >= {max_seq_len}], got {tuple(given_top_code.shape)}")
+        if int(given.min()) < 0 or int(given.max()) >= model.vocab_size_top:
+            raise IndexError(f"given_top_code out of range [0, {model.vocab_size_top})")
     eng.run(batch=B, seq_len=max_seq_len, pos_begin=0, pos_end=max_seq_len, sampling=sp, cond=cond_t,
             given_top=given, codes_top=codes_top, codes_bot=codes_bot)
     return codes_top, codes_bot
@@ -59,6 +63,8 @@ def step_logits(model, cond, codes_top: torch.Tensor, codes_bot: torch.Tensor, u
     dev = model.device
     ct = codes_top.to(device=dev, dtype=torch.int64).contiguous()
     cb = codes_bot.to(device=dev, dtype=torch.int64).contiguous()
+    if int(ct.min()) < 0 or int(ct.max()) >= model.vocab_size_top or int(cb.min()) < 0 or int(cb.max()) >= model.vocab_size_bot:
+        raise IndexError("code indices out of the vocabulary range")
     out_t, out_b = ct.clone(), cb.clone()
     logits = torch.zeros(B, S, 5, eng.vocab_max, dtype=torch.float32, device=dev)
     eng.run(batch=B, seq_len=S, pos_begin=0, pos_end=S, sampling=SamplingParams(), cond=cond_t, given_top=ct,

@@ -266,3 +266,10 @@ def test_errors_are_loud():
         H.sampling_ihqgpt(model, 2, 0, max_seq_len=256, use_fp16=False)
     with pytest.raises(H.HQError, match="temperature"):
         H.sampling_ihqgpt(model, 2, 0, max_seq_len=64, use_fp16=False, softmax_temperature=[0.0, 1.0])
+    with pytest.raises(IndexError):                       # nn.Embedding raises IndexError in the reference
+        H.sampling_ihqgpt(model, 2, cfg.n_classes, max_seq_len=64, use_fp16=False)
+    with pytest.raises(IndexError):
+        H.sampling_ihqgpt(model, 2, 0, max_seq_len=64, use_fp16=False,
+                          given_top_code=torch.full((2, 64), cfg.vocab_top, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="no bf16 engine"):   # fp32-only model asked for the bf16 path
+        H.sampling_ihqgpt(model, 2, 0, max_seq_len=64, use_fp16=True)
