@@ -200,6 +200,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++polls > (1u << 24)) __trap();
   }
 }
+// Polling with back-off for waits whose wake-up latency is not critical (consumers of a deep ring that many warps
+// of many resident CTAs poll at once): the sleeping warp frees issue slots for the warps that have data.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++polls > (1u << 24)) __trap();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) - 2D tile load global -> shared, completion on an mbarrier
 // ------------------------------------------------------------------------------------------------

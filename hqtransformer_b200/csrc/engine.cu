@@ -701,6 +701,11 @@ static void layernorm_act(hq_ctx* ctx, cudaStream_t st, float* x, const float* g
   if (fold) *fold = Fold();
 }
 
+static int attn_sleep_ns() {
+  static const int v = getenv("HQ_ATTN_SLEEP") ? atoi(getenv("HQ_ATTN_SLEEP")) : 0;
+  return v;
+}
+
 // Launch plan of attention_decode_kernel for this model: head groups per image, keys per ring stage, dynamic smem.
 template <typename AT>
 static bool attn_decode_plan(const hq_ctx* ctx, int* CH, int* hpc, int* groups, size_t* smem) {
@@ -733,7 +738,7 @@ static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, co
     // spatial decode: (image, head group) CTAs, K/V streamed through shared memory by bulk async copies
     if (ctx->tracing) ctx->tag_suffix = ":t" + std::to_string(kbase) + ":B" + std::to_string(M);
     launch_k(ctx, st, "attention_decode", attention_decode_kernel<AT>, dim3(M * groups), dim3((hpc + 1) * 32), smem, q, K, V,
-             out, ctx->D, t_stride, kbase, CH, hpc, groups);
+             out, ctx->D, t_stride, kbase, CH, hpc, groups, attn_sleep_ns());
     return;
   }
   const int items = M * ctx->nh;

@@ -216,7 +216,7 @@ struct TcCfg {
   static constexpr int BM = 128, BK = 64;
   static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGES = (BN == 128) ? 3 : 4;   // <= ~98 KB: two CTAs (of consecutive kernels) fit per SM
+  static constexpr int STAGES = (BN == 128) ? 5 : 6;   // 144-160 KB: ONE GEMM CTA per SM (see Tc2Cfg)
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
 };
@@ -343,7 +343,10 @@ struct Tc2Cfg {
   static constexpr int A_BYTES = 128 * BK * 2;          // this CTA's 128 rows of A
   static constexpr int B_BYTES = (BN / 2) * BK * 2;     // this CTA's half of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 102400 / STAGE_BYTES;   // <= 100 KB: two CTAs (of consecutive kernels) fit per SM
+  // >= 120 KB of shared memory per CTA on purpose: at most ONE GEMM CTA is resident per SM.  With two (the next
+  // kernel's CTA launched early by PDL next to the current one) tcgen05.alloc/dealloc of different CTA pairs interleave
+  // on the same SM pair, and the sampling loop was seen to hang in that state (round-1 notes).
+  static constexpr int STAGES = (163840 / STAGE_BYTES) > 8 ? 8 : (163840 / STAGE_BYTES);
   static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
 };

@@ -420,7 +420,8 @@ constexpr int ATTD_STAGES = 4;
 template <typename AT>
 __global__ void __launch_bounds__((ATTD_MAXHPC + 1) * 32)
 attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __restrict__ K, const AT* __restrict__ V,
-                        AT* __restrict__ out, int D, int t_stride, int n_keys, int CH, int hpc, int groups) {
+                        AT* __restrict__ out, int D, int t_stride, int n_keys, int CH, int hpc, int groups,
+                        int sleep_ns) {
 #if defined(__CUDA_ARCH__)
   TraceScope trace_scope(trace_id);
   extern __shared__ __align__(128) uint8_t att_smem[];
@@ -462,7 +463,8 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
           pdl_wait();
           waited = true;
         }
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (sleep_ns) mbar_wait_sleep(&empty_bar[s], ph ^ 1, sleep_ns);
+        else mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(rows) * row_bytes);
         const AT* src = (i < nck ? Kb : Vb) + static_cast<size_t>(ck) * CH * D;
         for (int r = 0; r < rows; ++r)
@@ -485,7 +487,8 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
   int i = 0;
   for (; i < nck; ++i) {
     const int s = i % ATTD_STAGES;
-    mbar_wait(&full_bar[s], (i / ATTD_STAGES) & 1);
+    if (sleep_ns) mbar_wait_sleep(&full_bar[s], (i / ATTD_STAGES) & 1, sleep_ns);
+    else mbar_wait(&full_bar[s], (i / ATTD_STAGES) & 1);
     const AT* st = reinterpret_cast<const AT*>(ring + s * stage_bytes) + w * 64 + c * 8;
     for (int kk = 0; kk < CH; kk += 4) {
       const int t = i * CH + kk + g;
@@ -524,7 +527,8 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   for (; i < 2 * nck; ++i) {
     const int s = i % ATTD_STAGES;
-    mbar_wait(&full_bar[s], (i / ATTD_STAGES) & 1);
+    if (sleep_ns) mbar_wait_sleep(&full_bar[s], (i / ATTD_STAGES) & 1, sleep_ns);
+    else mbar_wait(&full_bar[s], (i / ATTD_STAGES) & 1);
     const AT* st = reinterpret_cast<const AT*>(ring + s * stage_bytes) + w * 64 + c * 8;
     const int ck = i - nck;
     for (int kk = 0; kk < CH; kk += 4) {
