@@ -603,19 +603,26 @@ static const char* gemm_tag(int M) {
   return EPI == EPI_QKV ? "gemm_qkv" : (EPI == EPI_RESID ? "gemm_resid" : (EPI == EPI_GELU ? "gemm_fc1_gelu" : "gemm_head"));
 }
 
-// Width of the CTA-pair tile (256 x BN) for an [M, N] output: one wave of at most 74 pairs if possible, then the
-// cheapest per-k-block cost of max(L2->SM ingest at ~42.6 B/clk/SM, tensor-pipe time) - see DESIGN.md "GEMM tiles".
-static int pick_pair_bn(int M, int N) {
+// Cost model behind the tile / split-K choices (cycles; constants fitted to profiles/r1_gemm_plan_sweep.txt, measured
+// with ONE GEMM CTA per SM): a wave of <= 74 CTA pairs costs a fixed ~11k cycles (launch ramp, prologue, first TMA round
+// trip, epilogue, teardown) plus, per 64-wide k-block, the larger of the operand ingest at ~42.6 B/clk/SM and the tensor
+// pipe time; wide tiles pay for their extra epilogue chunks.
+static double pair_gemm_cost(int M, int N, int K, int bn, int splits) {
+  const int pairs = ((M + 255) / 256) * (N / bn) * splits;
+  const double waves = static_cast<double>((pairs + 73) / 74);
+  const double ingest = (16384.0 + 64.0 * bn) / 42.6, mma = 2.0 * bn;
+  return waves * ((K / 64 / splits) * (ingest > mma ? ingest : mma) + 11000.0) + (splits > 1 ? 400.0 * splits : 0.0) +
+         16.0 * bn;
+}
+
+// Width of the CTA-pair tile (256 x BN) for an [M, N] output
+static int pick_pair_bn(int M, int N, int K) {
   static const int cand[6] = {256, 192, 128, 96, 64, 32};
-  const int mt = (M + 255) / 256;
   int best = 0;
   double best_cost = 1e30;
   for (int bn : cand) {
     if (N % bn != 0) continue;
-    const int pairs = mt * (N / bn);
-    const double waves = static_cast<double>((pairs + 73) / 74);
-    const double ingest = (16384.0 + 64.0 * bn) / 42.6, mma = 2.0 * bn;
-    const double cost = waves * (ingest > mma ? ingest : mma);
+    const double cost = pair_gemm_cost(M, N, K, bn, 1);
     if (cost < best_cost) {
       best_cost = cost;
       best = bn;
@@ -631,7 +638,7 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
                       const CUtensorMap& mW16, int w_row_off, int M, int N, int K, const EpiParams<bf16>& ep,
                       int splits = 1, int bn_hint = 0) {
   int bn = g_force_bn ? g_force_bn : bn_hint;
-  if (bn == 0) bn = (M > 128) ? pick_pair_bn(M, N) : 0;
+  if (bn == 0) bn = (M > 128) ? pick_pair_bn(M, N, K) : 0;
   if (ctx->tracing) {
     char buf[48];
     snprintf(buf, sizeof(buf), ":%dx%dx%d:s%d", M, N, K, splits);
@@ -772,14 +779,13 @@ static void gemm_fc2_split(hq_ctx*, cudaStream_t, const ABuf&, const Weight&, in
 // Tile width and split-K factor for the fc2 GEMM ([M, D] = [M, 4D] x [D, 4D]^T).  Its K = 4D main loop is the longest
 // serial chain of a block while its D-wide output fills few CTA pairs, so when the pair grid leaves SMs idle the K
 // range is cut in up to 3 slices (grid.z); the slices write fp32 partial sums that the next LayerNorm adds in a fixed
-// order (deterministic).  Same per-k-block cost model as pick_pair_bn; a split pays ~2000 cycles for the extra
-// partial-sum traffic.
+// order (deterministic).  Same cost model as pick_pair_bn.
 struct Fc2Plan { int bn, splits; };
 static Fc2Plan pick_resid_plan(const hq_ctx* ctx, int M, int N, int K) {
   Fc2Plan best{0, 1};
   if (!ctx->bf16 || M <= 128 || getenv("HQ_NO_SPLITK") != nullptr) return best;
   static const int cand[6] = {256, 192, 128, 96, 64, 32};
-  const int mt = (M + 255) / 256, kb = K / 64;
+  const int kb = K / 64;
   if (const char* f = getenv("HQ_FORCE_SPLITK")) {       // tests: pin the split factor (tile width 64)
     const int s = atoi(f);
     if (s >= 1 && s <= 3 && kb % s == 0 && N % 64 == 0) return Fc2Plan{64, s};
@@ -789,10 +795,7 @@ static Fc2Plan pick_resid_plan(const hq_ctx* ctx, int M, int N, int K) {
     if (N % bn != 0) continue;
     for (int s = 1; s <= 3; ++s) {
       if (kb % s != 0) continue;
-      const int pairs = mt * (N / bn) * s;
-      const double waves = static_cast<double>((pairs + 73) / 74);
-      const double ingest = (16384.0 + 64.0 * bn) / 42.6, mma = 2.0 * bn;
-      const double cost = waves * (kb / s) * (ingest > mma ? ingest : mma) + (s > 1 ? 400.0 * s : 0.0) + 40.0 * bn;
+      const double cost = pair_gemm_cost(M, N, K, bn, s);
       if (cost < best_cost) {
         best_cost = cost;
         best = Fc2Plan{bn, s};
@@ -1308,6 +1311,7 @@ __global__ void read_sweep_kernel(const uint4* __restrict__ p, size_t n, unsigne
 
 extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int flush, int copies, float* usec_mean,
                                    float* usec_min, void* stream) {
+  const int splits = getenv("HQ_BENCH_SPLITS") ? atoi(getenv("HQ_BENCH_SPLITS")) : 1;
   if (M < 1 || N % 64 != 0 || K % 64 != 0 || iters < 1 || copies < 1 || !usec_mean || !usec_min) {
     set_err(nullptr, "hq_bench_gemm_shape: bad argument");
     return HQ_ERR_INVALID;
@@ -1331,7 +1335,7 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
   const size_t flush_bytes = static_cast<size_t>(256) << 20;
   HQ_CUDA(nullptr, cudaMalloc(&A, static_cast<size_t>(Mp) * K * 2));
   HQ_CUDA(nullptr, cudaMalloc(&W, wbytes * copies));
-  HQ_CUDA(nullptr, cudaMalloc(reinterpret_cast<void**>(&C), static_cast<size_t>(M) * N * 4));
+  HQ_CUDA(nullptr, cudaMalloc(reinterpret_cast<void**>(&C), static_cast<size_t>(M) * N * 4 * splits));
   HQ_CUDA(nullptr, cudaMalloc(&flushbuf, flush_bytes));
   HQ_CUDA(nullptr, cudaMalloc(reinterpret_cast<void**>(&sink), 4));
   cudaMemsetAsync(A, 0, static_cast<size_t>(Mp) * K * 2, st);
@@ -1356,7 +1360,7 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
   if (rc == HQ_OK) {
     EpiParams<bf16> e;
     memset(&e, 0, sizeof(e));
-    e.outf = C; e.ldo = N;
+    e.outf = C; e.ldo = N; e.split_stride = static_cast<size_t>(M) * N;
     g_force_bn = tile;
     for (int i = -3; i < iters; ++i) {
       e.trace = (i == iters - 1) ? d_trace : nullptr;
@@ -1364,7 +1368,7 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
       if (flush == 1) cudaMemsetAsync(flushbuf, i & 0xff, flush_bytes, st);
       if (flush == 2) read_sweep_kernel<<<1184, 256, 0, st>>>(static_cast<const uint4*>(flushbuf), flush_bytes / 16, sink);
       if (i >= 0) cudaEventRecord(ev[2 * i], st);
-      gemm_bf16<EPI_F32>(&tmp, st, mA, mW[c], mW16[c], 0, M, N, K, e);
+      gemm_bf16<EPI_F32>(&tmp, st, mA, mW[c], mW16[c], 0, M, N, K, e, splits);
       if (i >= 0) cudaEventRecord(ev[2 * i + 1], st);
     }
     g_force_bn = 0;
