@@ -645,12 +645,12 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
     ctx->tag_suffix = buf;
   }
   if (bn > 0 && N % bn == 0) {
-    dim3 grid(2 * (N / bn), (M + 255) / 256, splits);
-
+    const int tiles = (N / bn) * ((M + 255) / 256) * splits;
+    dim3 grid(2 * (tiles < 74 ? tiles : 74));               // persistent: at most one CTA pair per SM pair
 #define HQ_LAUNCH2(BN)                                                                                             \
   case BN:                                                                                                         \
     launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc2_kernel<BN, EPI, bf16>, grid, dim3(192), Tc2Cfg<BN>::SMEM_BYTES, mA, mW16, M, N, K,  \
-             w_row_off, ep);                                                                                       \
+             w_row_off, splits, ep);                                                                               \
     break;
     switch (bn) {
       HQ_LAUNCH2(32) HQ_LAUNCH2(64) HQ_LAUNCH2(96) HQ_LAUNCH2(128) HQ_LAUNCH2(192) HQ_LAUNCH2(256)
@@ -1350,20 +1350,12 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
   }
   std::vector<cudaEvent_t> ev(2 * iters);
   for (auto& e : ev) cudaEventCreate(&e);
-  unsigned long long* d_trace = nullptr;
-  const int max_ctas = 8192;
-  const bool want_trace = getenv("HQ_GEMM_TRACE") != nullptr;
-  if (want_trace) {
-    cudaMalloc(reinterpret_cast<void**>(&d_trace), sizeof(unsigned long long) * 8 * max_ctas);
-    cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * 8 * max_ctas, st);
-  }
   if (rc == HQ_OK) {
     EpiParams<bf16> e;
     memset(&e, 0, sizeof(e));
     e.outf = C; e.ldo = N; e.split_stride = static_cast<size_t>(M) * N;
     g_force_bn = tile;
     for (int i = -3; i < iters; ++i) {
-      e.trace = (i == iters - 1) ? d_trace : nullptr;
       const int c = ((i % copies) + copies) % copies;
       if (flush == 1) cudaMemsetAsync(flushbuf, i & 0xff, flush_bytes, st);
       if (flush == 2) read_sweep_kernel<<<1184, 256, 0, st>>>(static_cast<const uint4*>(flushbuf), flush_bytes / 16, sink);
@@ -1381,27 +1373,6 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
     tot += ms;
     if (ms < mn) mn = ms;
   }
-  if (want_trace && se == cudaSuccess) {
-    std::vector<unsigned long long> h(8 * max_ctas);
-    cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
-    unsigned long long t0 = ~0ull;
-    int n = 0;
-    for (int c = 0; c < max_ctas; ++c)
-      if (h[c * 8] != 0) { ++n; if (h[c * 8] < t0) t0 = h[c * 8]; }
-    static const char* names[8] = {"cta_start", "prologue_done", "tma_ring_issued", "first_stage_landed", "last_mma_issued",
-                                   "accum_complete", "epilogue_done", "cta_end"};
-    fprintf(stderr, "[trace] M=%d N=%d K=%d tile=%d ctas=%d (ns since first CTA start; min / mean / max over CTAs)\n", M, N, K, tile, n);
-    for (int sl = 0; sl < 8; ++sl) {
-      double mn2 = 1e30, mx2 = 0, sum = 0; int cnt = 0;
-      for (int c = 0; c < max_ctas; ++c) {
-        if (h[c * 8] == 0 || h[c * 8 + sl] == 0) continue;
-        const double v = static_cast<double>(h[c * 8 + sl] - t0);
-        mn2 = v < mn2 ? v : mn2; mx2 = v > mx2 ? v : mx2; sum += v; ++cnt;
-      }
-      if (cnt) fprintf(stderr, "[trace]   %-20s %8.0f %8.0f %8.0f  (n=%d)\n", names[sl], mn2, sum / cnt, mx2, cnt);
-    }
-  }
-  if (d_trace) cudaFree(d_trace);
   for (auto& e : ev) cudaEventDestroy(e);
   cudaFree(A); cudaFree(W); cudaFree(C); cudaFree(flushbuf); cudaFree(sink);
   if (rc != HQ_OK) {

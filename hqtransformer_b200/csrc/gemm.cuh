@@ -36,16 +36,8 @@ struct EpiParams {
   float* outf;        // [M, ldo]; split-K: slice blockIdx.z of the K range writes outf + blockIdx.z * split_stride
   int ldo;
   size_t split_stride;
-  unsigned long long* trace;   // optional (profiling builds of the microbenchmark): 8 %globaltimer stamps per CTA
 };
 
-__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int slot) {
-  if (trace != nullptr) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    trace[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = t;
-  }
-}
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
@@ -103,11 +95,12 @@ __device__ __forceinline__ void epi_store8(const EpiParams<AT>& ep, int m, int n
 template <int BN, int EPI, typename AT>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, uint8_t* slab_base, float* sbias, int warp, int lane,
                                               int m0, int n0, int M, int N, const EpiParams<AT>& ep,
-                                              uint64_t* tmem_full_bar) {
+                                              uint64_t* tmem_full_bar, uint32_t full_parity = 0) {
   const int quarter = warp & 3;
   const int etid = quarter * 32 + lane;                        // 0..127 over the four epilogue warps
   const bool has_bias = (EPI != EPI_F32) && ep.bias != nullptr;
   if (has_bias) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");             // persistent kernel: previous tile's bias fully consumed
     for (int i = etid; i < BN; i += 128) sbias[i] = (n0 + i < N) ? ep.bias[n0 + i] : 0.f;
   }
   // rows this lane writes: it*4 + (lane >> 3) of the warp's 32; destination row offsets (elements) per row
@@ -130,7 +123,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, uint8_t* slab_
     }
   }
   asm volatile("bar.sync 1, 128;" ::: "memory");               // sbias visible to the four epilogue warps
-  mbar_wait(tmem_full_bar, 0);
+  mbar_wait(tmem_full_bar, full_parity);
   tc_fence_after();
 
   uint8_t* slab = slab_base + quarter * 4096;                  // this warp's 32 rows x 128 B
@@ -345,16 +338,31 @@ struct Tc2Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // >= 120 KB of shared memory per CTA on purpose: at most ONE GEMM CTA is resident per SM.  With two (the next
   // kernel's CTA launched early by PDL next to the current one) tcgen05.alloc/dealloc of different CTA pairs interleave
-  // on the same SM pair, and the sampling loop was seen to hang in that state (round-1 notes, DESIGN.md 3.4).
-  static constexpr int STAGES = (163840 / STAGE_BYTES) > 8 ? 8 : (163840 / STAGE_BYTES);
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
+  // on the same SM pair, and the sampling loop was seen to hang in that state (round-1 notes, DESIGN.md 3.1).
+  static constexpr int STAGES = (184320 / STAGE_BYTES) > 8 ? 8 : (184320 / STAGE_BYTES);
+  static constexpr int ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // one accumulator
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;                                               // double buffered
+  static constexpr int SLAB_BYTES = 16384;              // epilogue staging: 4 warps x (32 rows x 128 B)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
 };
 
+// arrive on the mbarrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+#if defined(__CUDA_ARCH__)
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+#endif
+}
+
+// Persistent over output tiles: grid.x = 2 * min(tiles, 74) CTAs; pair p computes tiles p, p + pairs, ...  The smem ring
+// and its mbarrier phases run on across tiles, the accumulator is double buffered in TMEM (tile i+1's MMAs start while
+// tile i is drained), so a GEMM with more tiles than pairs pays the fixed per-wave cost once.
+// tile index -> (split z, row block, column block), column block fastest.
 template <int BN, int EPI, typename AT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
-gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
-                int w_row_off, EpiParams<AT> ep) {
+gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M,
+                int N, int K, int w_row_off, int splits, EpiParams<AT> ep) {
 #if defined(__CUDA_ARCH__)
   TraceScope trace_scope(trace_id);
   using C = Tc2Cfg<BN>;
@@ -363,23 +371,22 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + C::STAGES * C::B_BYTES);
+  uint8_t* slab = sB + C::STAGES * C::B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slab + C::SLAB_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;       // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2], used in the leader CTA only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int m0 = blockIdx.y * 256 + static_cast<int>(rank) * 128;      // this CTA's rows
-  const int n0 = (blockIdx.x >> 1) * BN;                               // the pair's columns
-  const int num_kb = (K / C::BK) / static_cast<int>(gridDim.z);        // split-K: this pair's share of the k-blocks
-  const int kb0 = static_cast<int>(blockIdx.z) * num_kb;
-
-  if (EPI == EPI_F32) ep.outf += static_cast<size_t>(blockIdx.z) * ep.split_stride;
-  if (threadIdx.x == 0) trace_stamp(ep.trace, 0);            // CTA start
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nt = N / BN, mt = (M + 255) / 256;
+  const int total_tiles = nt * mt * splits;
+  const int num_kb = (K / C::BK) / splits;               // k-blocks per tile
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -390,7 +397,10 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
       mbar_init(&full_bar[s], 1);     // leader: one arrive.expect_tx covering both CTAs' bytes
       mbar_init(&empty_bar[s], 1);    // one multicast tcgen05.commit per use
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);    // one multicast tcgen05.commit per tile
+      mbar_init(&tmem_empty_bar[b], 8);   // 4 epilogue warps of each CTA
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -402,7 +412,6 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
   cluster_sync_all();                 // peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) trace_stamp(ep.trace, 1);            // prologue done
 
   pdl_launch_dependents();
   if (warp == 0) {
@@ -410,56 +419,83 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
       // ---- TMA producer (both CTAs): own A rows + own half of the W tile, credited to the leader's full barrier.
       //      The first ring of W tiles is requested before griddepcontrol.wait (weights never depend on the
       //      previous kernel), the activation tiles after it. ----
-      const int wrow = w_row_off + n0 + static_cast<int>(rank) * (BN / 2);
-      const int pre = num_kb < C::STAGES ? num_kb : C::STAGES;
-      for (int kb = 0; kb < pre; ++kb) {
-        if (leader) mbar_arrive_expect_tx(&full_bar[kb], 2 * C::STAGE_BYTES);
+      int g = 0;                                          // k-blocks issued so far (all tiles)
+      bool first = true;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const int z = tile / (nt * mt), rem = tile % (nt * mt);
+        const int m0 = (rem / nt) * 256 + static_cast<int>(rank) * 128;
+        const int wrow = w_row_off + (rem % nt) * BN + static_cast<int>(rank) * (BN / 2);
+        const int kb0 = z * num_kb;
+        int kb = 0;
+        if (first) {
+          first = false;
+          const int pre = num_kb < C::STAGES ? num_kb : C::STAGES;
+          for (; kb < pre; ++kb) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[kb], 2 * C::STAGE_BYTES);
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j)
-          tma_load_2d_2sm(sB + kb * C::B_BYTES + j * (16 * 128), &tmW, &full_bar[kb], (kb0 + kb) * C::BK, wrow + j * 16);
-      }
-      pdl_wait();
-      for (int kb = 0; kb < pre; ++kb) tma_load_2d_2sm(sA + kb * C::A_BYTES, &tmA, &full_bar[kb], (kb0 + kb) * C::BK, m0);
-      trace_stamp(ep.trace, 2);                                // first ring of TMA requests issued
-      for (int kb = pre; kb < num_kb; ++kb) {
-        const int s = kb % C::STAGES;
-        const uint32_t ph = (kb / C::STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
-        tma_load_2d_2sm(sA + s * C::A_BYTES, &tmA, &full_bar[s], (kb0 + kb) * C::BK, m0);
+            for (int j = 0; j < BN / 32; ++j)
+              tma_load_2d_2sm(sB + kb * C::B_BYTES + j * (16 * 128), &tmW, &full_bar[kb], (kb0 + kb) * C::BK, wrow + j * 16);
+          }
+          pdl_wait();
+          for (int k2 = 0; k2 < pre; ++k2)
+            tma_load_2d_2sm(sA + k2 * C::A_BYTES, &tmA, &full_bar[k2], (kb0 + k2) * C::BK, m0);
+          g = pre;
+        }
+        for (; kb < num_kb; ++kb, ++g) {
+          const int s = g % C::STAGES;
+          const uint32_t ph = (g / C::STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+          tma_load_2d_2sm(sA + s * C::A_BYTES, &tmA, &full_bar[s], (kb0 + kb) * C::BK, m0);
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j)
-          tma_load_2d_2sm(sB + s * C::B_BYTES + j * (16 * 128), &tmW, &full_bar[s], (kb0 + kb) * C::BK, wrow + j * 16);
+          for (int j = 0; j < BN / 32; ++j)
+            tma_load_2d_2sm(sB + s * C::B_BYTES + j * (16 * 128), &tmW, &full_bar[s], (kb0 + kb) * C::BK, wrow + j * 16);
+        }
       }
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
       // ---- MMA issuer (leader CTA only) ----
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % C::STAGES;
-        const uint32_t ph = (kb / C::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int g = 0, it = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);     // both CTAs drained this accumulator
         tc_fence_after();
-        if (kb == 0) trace_stamp(ep.trace, 3);                 // first stage landed
-        const uint64_t da = umma_smem_desc_sw128(smem_u32(sA + s * C::A_BYTES));
-        const uint64_t db = umma_smem_desc_sw128(smem_u32(sB + s * C::B_BYTES));
+        const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS);
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % C::STAGES;
+          const uint32_t ph = (g / C::STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t da = umma_smem_desc_sw128(smem_u32(sA + s * C::A_BYTES));
+          const uint64_t db = umma_smem_desc_sw128(smem_u32(sB + s * C::B_BYTES));
 #pragma unroll
-        for (int k = 0; k < C::BK / 16; ++k)
-          umma_bf16_2sm(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
-        umma_commit_2sm(&empty_bar[s], 0x3);   // both CTAs may refill this slot
+          for (int k = 0; k < C::BK / 16; ++k)
+            umma_bf16_2sm(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[s], 0x3);   // both CTAs may refill this slot
+        }
+        umma_commit_2sm(&tmem_full_bar[buf], 0x3);   // both CTAs' accumulators of this tile are complete
       }
-      umma_commit_2sm(tmem_full_bar, 0x3);     // both CTAs' accumulators are complete
-      trace_stamp(ep.trace, 4);                // last MMA issued
     }
   } else {
-    // ---- epilogue: this CTA's 128 rows (TMEM -> registers -> warp-private smem slab -> coalesced global) ----
+    // ---- epilogue: this CTA's 128 rows of every tile (TMEM -> registers -> smem slab -> coalesced global) ----
     pdl_wait();
-    if (warp == 2 && lane == 0) trace_stamp(ep.trace, 5);      // epilogue warps ready
-    epilogue_tile<BN, EPI, AT>(tmem_base, sA, sbias, warp, lane, m0, n0, M, N, ep, tmem_full_bar);
-    tc_fence_before();
-    if (warp == 2 && lane == 0) trace_stamp(ep.trace, 6);      // epilogue stores issued
+    int it = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+      const int buf = it & 1;
+      const int z = tile / (nt * mt), rem = tile % (nt * mt);
+      const int m0 = (rem / nt) * 256 + static_cast<int>(rank) * 128;
+      const int n0 = (rem % nt) * BN;
+      EpiParams<AT> ept = ep;
+      if (EPI == EPI_F32) ept.outf = ep.outf + static_cast<size_t>(z) * ep.split_stride;
+      epilogue_tile<BN, EPI, AT>(tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS), slab, sbias, warp, lane, m0, n0, M, N,
+                                 ept, &tmem_full_bar[buf], (it >> 1) & 1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[buf], 0);   // this warp is done with the accumulator
+    }
   }
   __syncwarp();
   cluster_sync_all();                 // the peer may still be reading this CTA's smem / signalling its barriers
@@ -467,7 +503,6 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
   }
-  if (threadIdx.x == 0) trace_stamp(ep.trace, 7);            // CTA end
 #endif
 }
 
