@@ -53,6 +53,10 @@ PROTOTYPES = {
     "hq_debug_philox": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "hq_debug_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_uint64, C.c_uint64,
                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hq_debug_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_void_p]),
+    "hq_debug_attention_phases": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int,
+                                            C.POINTER(C.c_int), C.c_void_p]),
     "hq_bench_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "hq_trace_run": (C.c_int, [C.c_void_p, C.POINTER(HQRunArgs), C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p, C.c_int,
                                C.POINTER(C.c_int)]),

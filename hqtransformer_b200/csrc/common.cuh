@@ -145,6 +145,19 @@ struct TraceScope {
   }
 };
 
+// Phase timestamps inside a kernel (hq_debug_attention_phases): when the buffer is set, one thread per CTA stores
+// %globaltimer at up to 8 named points of the CTA's life; the host reduces them to min / mean / max per phase.
+__device__ unsigned long long* g_hq_phase = nullptr;
+__device__ __forceinline__ void phase_mark(int p) {
+#if defined(__CUDA_ARCH__)
+  if (g_hq_phase != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_hq_phase[blockIdx.x * 8 + p] = t;
+  }
+#endif
+}
+
 // Programmatic dependent launch: wait for the producer grid's memory / let the dependent grid start its prologue
 __device__ __forceinline__ void pdl_wait() {
 #if defined(__CUDA_ARCH__)

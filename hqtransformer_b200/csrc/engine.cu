@@ -101,7 +101,9 @@ struct hq_ctx {
   ABuf h, att, mlp;
   void* q = nullptr;
   float *x = nullptr, *yd = nullptr, *logits = nullptr;
-  float* splitk_ws = nullptr;   // [3][rows][D] fp32 partial sums of split-K fc2 GEMMs (folded in by the next LayerNorm)
+  float* splitk_ws = nullptr;   // [LN_MAXFOLD][rows][D] fp32 partial sums of split-K fc2 GEMMs (folded in by the next LayerNorm)
+  unsigned int* att_sched = nullptr;   // [2] work-ticket / finished-CTA counters of attention_decode_mma_kernel (rest at 0)
+  int num_sms = 0;
   int ws_rows = 0;
   void *kc = nullptr, *vc = nullptr, *kd = nullptr, *vd = nullptr;
   int64_t *cond = nullptr, *codes_top = nullptr, *codes_bot = nullptr;
@@ -330,7 +332,7 @@ static int reserve_impl(hq_ctx* ctx, int max_batch) {
   if ((rc = alloc_f32(ctx, &ctx->yd, static_cast<size_t>(4) * B * D))) return rc;
   if ((rc = alloc_f32(ctx, &ctx->logits, static_cast<size_t>(4) * B * ctx->Vmax))) return rc;
   ctx->ws_rows = Mmax;
-  if (ctx->bf16 && (rc = alloc_f32(ctx, &ctx->splitk_ws, static_cast<size_t>(3) * Mmax * D))) return rc;
+  if (ctx->bf16 && (rc = alloc_f32(ctx, &ctx->splitk_ws, static_cast<size_t>(LN_MAXFOLD) * Mmax * D))) return rc;
   const size_t kvn = static_cast<size_t>(ctx->L) * B * ctx->Tc * D * ctx->wsize;
   if ((rc = dev_alloc(ctx, &ctx->kc, kvn))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->vc, kvn))) return rc;
@@ -389,6 +391,10 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
   }
   if ((rc = set_smem(ctx, attention_decode_kernel<bf16>, 64 * 1024))) return rc;
   if ((rc = set_smem(ctx, attention_decode_kernel<float>, 64 * 1024))) return rc;
+  if ((rc = set_smem(ctx, attention_decode_mma_kernel, 112 * 1024))) return rc;
+  if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->att_sched), 16))) return rc;
+  HQ_CUDA(ctx, cudaMemset(ctx->att_sched, 0, 16));
+  HQ_CUDA(ctx, cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
   HQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
 
   // ---- parameters ----
@@ -736,14 +742,58 @@ static bool attn_decode_plan(const hq_ctx* ctx, int* CH, int* hpc, int* groups, 
   return *smem <= 64 * 1024;
 }
 
+// Launch plan of attention_decode_mma_kernel (bf16): stages of 8 keys + 8 values in hpc*128+16-byte rows, up to 4 of them
+// within ~52 KB so that four persistent CTAs fit an SM; grid = resident CTAs (each takes one item, then tickets),
+// capped by the number of items.
+static int g_attn_scalar = 0;   // tests: hq_debug_attention may pin the scalar bulk-staged kernel
+static bool attn_mma_plan(const hq_ctx* ctx, int groups, int hpc, int n_items, int* stages, size_t* smem, int* grid) {
+  static const bool off = getenv("HQ_ATTN_SCALAR") != nullptr;      // experiments: the scalar bulk-staged kernel
+  if (off || g_attn_scalar || !ctx->bf16 || ctx->num_sms <= 0) return false;
+  const size_t stage = static_cast<size_t>(2 * ATTM_CH) * (hpc * 128 + 16);
+  int st = static_cast<int>((52 * 1024) / stage);
+  if (st > 4) st = 4;
+  if (const char* f = getenv("HQ_ATTM_STAGES")) st = atoi(f);     // experiments
+  if (st < 2) st = 2;
+  if (st > ATTM_MAXSTAGES) st = ATTM_MAXSTAGES;
+  const size_t bytes = st * stage + 2 * static_cast<size_t>(hpc) * 128 + static_cast<size_t>(hpc) * 64 * 4 +
+                       (2 * ATTM_MAXSTAGES + 4) * 8 + 16;
+  if (bytes > 112 * 1024) return false;
+  int per_sm = static_cast<int>((227 * 1024) / (bytes + 1024));
+  const int by_threads = 2048 / ((hpc + 1) * 32);
+  if (per_sm > by_threads) per_sm = by_threads;
+  if (const char* f = getenv("HQ_ATTM_PER_SM")) per_sm = atoi(f) < per_sm ? atoi(f) : per_sm;   // experiments
+  if (per_sm < 1) per_sm = 1;
+  (void)groups;
+  *stages = st;
+  *smem = bytes;
+  const int cap = ctx->num_sms * per_sm;
+  *grid = n_items < cap ? n_items : cap;
+  return true;
+}
+
+template <typename AT>
+static void launch_attn_mma(hq_ctx*, cudaStream_t, const AT*, const AT*, const AT*, AT*, int, int, int, int, int, int, int, size_t) {}
+template <>
+void launch_attn_mma<bf16>(hq_ctx* ctx, cudaStream_t st, const bf16* q, const bf16* K, const bf16* V, bf16* out, int t_stride,
+                           int n_keys, int hpc, int groups, int n_items, int stages, int grid, size_t smem) {
+  launch_k(ctx, st, "attention_decode", attention_decode_mma_kernel, dim3(grid), dim3((hpc + 1) * 32), smem, q, K, V, out,
+           ctx->D, t_stride, n_keys, hpc, groups, n_items, stages, ctx->att_sched);
+}
+
 template <typename AT>
 static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, const AT* V, AT* out, int M, int Tq,
                       int t_stride, int kbase, int causal) {
   int CH = 0, hpc = 0, groups = 0;
   size_t smem = 0;
   if (Tq == 1 && !causal && getenv("HQ_ATTN_GENERIC") == nullptr && attn_decode_plan<AT>(ctx, &CH, &hpc, &groups, &smem)) {
-    // spatial decode: (image, head group) CTAs, K/V streamed through shared memory by bulk async copies
+    // spatial decode: (image, head group) work items, K/V streamed through shared memory by bulk async copies
     if (ctx->tracing) ctx->tag_suffix = ":t" + std::to_string(kbase) + ":B" + std::to_string(M);
+    int stages = 0, grid = 0;
+    size_t smem2 = 0;
+    if (sizeof(AT) == 2 && attn_mma_plan(ctx, groups, hpc, M * groups, &stages, &smem2, &grid)) {
+      launch_attn_mma<AT>(ctx, st, q, K, V, out, t_stride, kbase, hpc, groups, M * groups, stages, grid, smem2);
+      return;
+    }
     launch_k(ctx, st, "attention_decode", attention_decode_kernel<AT>, dim3(M * groups), dim3((hpc + 1) * 32), smem, q, K, V,
              out, ctx->D, t_stride, kbase, CH, hpc, groups, attn_sleep_ns());
     return;
@@ -778,7 +828,7 @@ static void gemm_fc2_split(hq_ctx*, cudaStream_t, const ABuf&, const Weight&, in
 
 // Tile width and split-K factor for the fc2 GEMM ([M, D] = [M, 4D] x [D, 4D]^T).  Its K = 4D main loop is the longest
 // serial chain of a block while its D-wide output fills few CTA pairs, so when the pair grid leaves SMs idle the K
-// range is cut in up to 3 slices (grid.z); the slices write fp32 partial sums that the next LayerNorm adds in a fixed
+// range is cut in up to LN_MAXFOLD slices; the slices write fp32 partial sums that the next LayerNorm adds in a fixed
 // order (deterministic).  Same cost model as pick_pair_bn.
 struct Fc2Plan { int bn, splits; };
 static Fc2Plan pick_resid_plan(const hq_ctx* ctx, int M, int N, int K) {
@@ -788,12 +838,13 @@ static Fc2Plan pick_resid_plan(const hq_ctx* ctx, int M, int N, int K) {
   const int kb = K / 64;
   if (const char* f = getenv("HQ_FORCE_SPLITK")) {       // tests: pin the split factor (tile width 64)
     const int s = atoi(f);
-    if (s >= 1 && s <= 3 && kb % s == 0 && N % 64 == 0) return Fc2Plan{64, s};
+    if (s >= 1 && s <= LN_MAXFOLD && kb % s == 0 && N % 64 == 0) return Fc2Plan{64, s};
   }
+  static const int max_splits = getenv("HQ_MAX_SPLITK") ? atoi(getenv("HQ_MAX_SPLITK")) : LN_MAXFOLD;
   double best_cost = 1e30;
   for (int bn : cand) {
     if (N % bn != 0) continue;
-    for (int s = 1; s <= 3; ++s) {
+    for (int s = 1; s <= max_splits; ++s) {
       if (kb % s != 0) continue;
       const double cost = pair_gemm_cost(M, N, K, bn, s);
       if (cost < best_cost) {
@@ -1071,6 +1122,45 @@ extern "C" int hq_run_host(hq_ctx* ctx, const hq_run_args* args) {
 // ------------------------------------------------------------------------------------------------
 // test / measurement hooks
 // ------------------------------------------------------------------------------------------------
+extern "C" int hq_debug_attention(int prec, const void* q, const void* K, const void* V, void* out, int B, int n_heads,
+                                  int t_stride, int n_keys, int variant, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B < 1 || n_heads < 1 || n_keys < 1 || n_keys > t_stride || n_keys > ATT_MAX_KEYS || !q || !K || !V || !out) {
+    set_err(nullptr, "hq_debug_attention: bad argument");
+    return HQ_ERR_INVALID;
+  }
+  hq_ctx tmp;   // launch bookkeeping + the fields attention() reads
+  int dev = 0;
+  HQ_CUDA(nullptr, cudaGetDevice(&dev));
+  int rc = check_device(&tmp, dev);
+  if (rc) return rc;
+  tmp.bf16 = prec == HQ_PREC_BF16;
+  tmp.D = n_heads * 64;
+  tmp.nh = n_heads;
+  HQ_CUDA(nullptr, cudaDeviceGetAttribute(&tmp.num_sms, cudaDevAttrMultiProcessorCount, dev));
+  if ((rc = set_smem(&tmp, attention_decode_kernel<bf16>, 64 * 1024))) return rc;
+  if ((rc = set_smem(&tmp, attention_decode_kernel<float>, 64 * 1024))) return rc;
+  if ((rc = set_smem(&tmp, attention_decode_mma_kernel, 112 * 1024))) return rc;
+  HQ_CUDA(nullptr, cudaMalloc(reinterpret_cast<void**>(&tmp.att_sched), 16));
+  cudaMemsetAsync(tmp.att_sched, 0, 16, st);
+  g_attn_scalar = variant == 1;
+  if (tmp.bf16)
+    attention<bf16>(&tmp, st, static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V),
+                    static_cast<bf16*>(out), B, 1, t_stride, n_keys, 0);
+  else
+    attention<float>(&tmp, st, static_cast<const float*>(q), static_cast<const float*>(K), static_cast<const float*>(V),
+                     static_cast<float*>(out), B, 1, t_stride, n_keys, 0);
+  g_attn_scalar = 0;
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(tmp.att_sched);
+  if (e == cudaSuccess) e = tmp.launch_err;
+  if (e != cudaSuccess) {
+    set_err(nullptr, "hq_debug_attention: %s", cudaGetErrorString(e));
+    return HQ_ERR_CUDA;
+  }
+  return HQ_OK;
+}
+
 extern "C" int hq_debug_gemm(int prec, const void* A, const void* W, float* C, int M, int N, int K, int tile,
                              void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1203,6 +1293,57 @@ extern "C" int hq_bench_attention(hq_ctx* ctx, int B, int n_keys, int iters, flo
     return HQ_ERR_CUDA;
   }
   *usec = ms * 1000.f / iters;
+  return HQ_OK;
+}
+
+// One instrumented launch of the decode attention (after `warm` plain ones on other layers' slabs): per-CTA %globaltimer
+// stamps at 8 points of the CTA's life (see phase_mark in kernels.cuh).  out_ns: [max_ctas][8], 0 = phase not reached.
+extern "C" int hq_debug_attention_phases(hq_ctx* ctx, int B, int n_keys, int warm, unsigned long long* out_ns, int max_ctas,
+                                         int* n_ctas, void* stream) {
+  if (!ctx || !out_ns || !n_ctas || B < 1 || B > ctx->max_batch || n_keys < 1 || n_keys > ctx->Tc || max_ctas < 1) {
+    set_err(ctx, "hq_debug_attention_phases: bad argument");
+    return HQ_ERR_INVALID;
+  }
+  HQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* dev = nullptr;
+  const size_t bytes = static_cast<size_t>(max_ctas) * 8 * sizeof(unsigned long long);
+  HQ_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&dev), bytes));
+  HQ_CUDA(ctx, cudaMemsetAsync(dev, 0, bytes, st));
+  const size_t lstride = static_cast<size_t>(ctx->max_batch) * ctx->Tc * ctx->D;
+  ctx->launch_err = cudaSuccess;
+  struct PdlOff { hq_ctx* c; bool saved; PdlOff(hq_ctx* x) : c(x), saved(x->use_pdl) { x->use_pdl = false; } ~PdlOff() { c->use_pdl = saved; } } pdl_off(ctx);
+  const int64_t before = ctx->launches;
+  auto launch = [&](int l) {
+    if (ctx->bf16) {
+      bf16* kc = static_cast<bf16*>(ctx->kc) + l * lstride;
+      bf16* vc = static_cast<bf16*>(ctx->vc) + l * lstride;
+      attention<bf16>(ctx, st, static_cast<bf16*>(ctx->q), kc, vc, static_cast<bf16*>(ctx->att.ptr), B, 1, ctx->Tc, n_keys, 0);
+    } else {
+      float* kc = static_cast<float*>(ctx->kc) + l * lstride;
+      float* vc = static_cast<float*>(ctx->vc) + l * lstride;
+      attention<float>(ctx, st, static_cast<float*>(ctx->q), kc, vc, static_cast<float*>(ctx->att.ptr), B, 1, ctx->Tc, n_keys, 0);
+    }
+  };
+  for (int i = 0; i < warm; ++i) launch(i % ctx->L);
+  HQ_CUDA(ctx, cudaStreamSynchronize(st));
+  HQ_CUDA(ctx, cudaMemcpyToSymbol(g_hq_phase, &dev, sizeof(dev)));
+  launch(warm % ctx->L);
+  cudaError_t e = cudaStreamSynchronize(st);
+  unsigned long long* null_ptr = nullptr;
+  cudaMemcpyToSymbol(g_hq_phase, &null_ptr, sizeof(null_ptr));
+  (void)before;
+  if (e == cudaSuccess) e = ctx->launch_err;
+  if (e == cudaSuccess) e = cudaMemcpy(out_ns, dev, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (e != cudaSuccess) {
+    set_err(ctx, "hq_debug_attention_phases: %s", cudaGetErrorString(e));
+    return HQ_ERR_CUDA;
+  }
+  int n = 0;
+  for (int i = 0; i < max_ctas; ++i)
+    if (out_ns[static_cast<size_t>(i) * 8] != 0) n = i + 1;
+  *n_ctas = n;
   return HQ_OK;
 }
 

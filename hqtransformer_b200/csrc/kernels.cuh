@@ -117,6 +117,7 @@ embed_depth_kernel(int trace_id, float* y, const float* E_top_depth, const float
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_THREADS = 128;
 constexpr int LN_MAXV = 3;    // float4 per thread held in registers: rows up to 3 * 512 = 1536 columns
+constexpr int LN_MAXFOLD = 6; // split-K partial sums a LayerNorm can fold in
 
 template <typename OutT>
 __device__ __forceinline__ void ln_store4(OutT* o, int i, float y0, float y1, float y2, float y3) {
@@ -158,7 +159,7 @@ layernorm_kernel(int trace_id, float* __restrict__ x, const float* __restrict__ 
   OutT* o = out + static_cast<size_t>(r) * D;
   const int tid = threadIdx.x;
   if (D <= LN_MAXV * LN_THREADS * 4) {
-    float4 v[LN_MAXV], g[LN_MAXV], bt[LN_MAXV], ad[LN_MAXV], fb[LN_MAXV], f0[LN_MAXV], f1[LN_MAXV], f2[LN_MAXV];
+    float4 v[LN_MAXV], g[LN_MAXV], bt[LN_MAXV], ad[LN_MAXV], fb[LN_MAXV], f[LN_MAXFOLD][LN_MAXV];
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < LN_MAXV; ++j) {
@@ -168,13 +169,15 @@ layernorm_kernel(int trace_id, float* __restrict__ x, const float* __restrict__ 
       g[j] = *reinterpret_cast<const float4*>(gamma + ic);
       bt[j] = *reinterpret_cast<const float4*>(beta + ic);
       ad[j] = add != nullptr ? *reinterpret_cast<const float4*>(add + ic) : z4;
-      fb[j] = z4; f0[j] = z4; f1[j] = z4; f2[j] = z4;
+      fb[j] = z4;
+#pragma unroll
+      for (int sidx = 0; sidx < LN_MAXFOLD; ++sidx) f[sidx][j] = z4;
       if (fold != nullptr) {
         const float* fr = fold + (static_cast<size_t>(r) * in_mul + in_off) * D + ic;
         fb[j] = fold_bias != nullptr ? *reinterpret_cast<const float4*>(fold_bias + ic) : z4;
-        f0[j] = *reinterpret_cast<const float4*>(fr);
-        if (n_fold > 1) f1[j] = *reinterpret_cast<const float4*>(fr + fold_stride);
-        if (n_fold > 2) f2[j] = *reinterpret_cast<const float4*>(fr + 2 * fold_stride);
+#pragma unroll
+        for (int sidx = 0; sidx < LN_MAXFOLD; ++sidx)
+          if (sidx < n_fold) f[sidx][j] = *reinterpret_cast<const float4*>(fr + sidx * fold_stride);
       }
     }
     float s = 0.f;
@@ -182,10 +185,15 @@ layernorm_kernel(int trace_id, float* __restrict__ x, const float* __restrict__ 
     for (int j = 0; j < LN_MAXV; ++j) {
       const int i = (j * LN_THREADS + tid) * 4;
       if (fold != nullptr) {
-        v[j].x += fb[j].x + ((f0[j].x + f1[j].x) + f2[j].x);
-        v[j].y += fb[j].y + ((f0[j].y + f1[j].y) + f2[j].y);
-        v[j].z += fb[j].z + ((f0[j].z + f1[j].z) + f2[j].z);
-        v[j].w += fb[j].w + ((f0[j].w + f1[j].w) + f2[j].w);
+        float4 a = f[0][j];                               // fixed left-to-right order: deterministic
+#pragma unroll
+        for (int sidx = 1; sidx < LN_MAXFOLD; ++sidx) {
+          a.x += f[sidx][j].x; a.y += f[sidx][j].y; a.z += f[sidx][j].z; a.w += f[sidx][j].w;
+        }
+        v[j].x += fb[j].x + a.x;
+        v[j].y += fb[j].y + a.y;
+        v[j].z += fb[j].z + a.z;
+        v[j].w += fb[j].w + a.w;
         if (i < D) *reinterpret_cast<float4*>(xr + i) = v[j];
       }
       if (i < D) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
@@ -438,6 +446,7 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
   const int nck = (n_keys + CH - 1) / CH;
 
   if (threadIdx.x == 0) {
+    phase_mark(0);
     for (int s = 0; s < ATTD_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], hpc);
@@ -445,6 +454,7 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
     fence_barrier_init();
   }
   __syncthreads();
+  if (threadIdx.x == 0) phase_mark(1);
   pdl_launch_dependents();
 
   if (w == hpc) {
@@ -484,11 +494,13 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
 #pragma unroll
   for (int e = 0; e < 8; ++e) qv[e] *= 0.125f;     // hs^-1/2 = 2^-3 is exact: same products as scaling K (layers.py:102)
   float* row = sc + w * ATT_MAX_KEYS;
+  if (threadIdx.x == 0) phase_mark(2);
   int i = 0;
   for (; i < nck; ++i) {
     const int s = i % ATTD_STAGES;
     if (sleep_ns) mbar_wait_sleep(&full_bar[s], (i / ATTD_STAGES) & 1, sleep_ns);
     else mbar_wait(&full_bar[s], (i / ATTD_STAGES) & 1);
+    if (i == 0 && threadIdx.x == 0) phase_mark(3);
     const AT* st = reinterpret_cast<const AT*>(ring + s * stage_bytes) + w * 64 + c * 8;
     for (int kk = 0; kk < CH; kk += 4) {
       const int t = i * CH + kk + g;
@@ -511,6 +523,7 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
     if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
   // ---- softmax over this head's scores ----
+  if (threadIdx.x == 0) phase_mark(4);
   float mx = -INFINITY;
   for (int t = lane; t < n_keys; t += 32) mx = fmaxf(mx, row[t]);
   mx = warp_max(mx);
@@ -522,6 +535,7 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
   }
   const float inv = 1.0f / warp_sum(sum);
   __syncwarp();
+  if (threadIdx.x == 0) phase_mark(5);
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -550,6 +564,284 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
     acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
   }
   if (g == 0) store8(out + static_cast<size_t>(b) * D + h * 64 + c * 8, acc);
+  if (threadIdx.x == 0) {
+    phase_mark(6);
+    phase_mark(7);
+  }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5a (bf16): the same single-query attention as ONE streaming pass, persistent, on the mma.sync register path.
+// Measured on the scalar kernel above (profiles/r1_attn_phases.txt): with ~25 MB of bulk copies in flight a request
+// takes ~4 us to land, and every point where the computation waits for "all of K" (the softmax between the score pass
+// and the value pass, the next item) pays that latency again; its score pass is also issue-bound (3 shuffles per 4 keys).
+//   * work item = (image, head group); a CTA takes item blockIdx.x first and then draws further items from a global
+//     ticket counter (`sched`), so SMs that finish early take more of them - the ~1000 items of a step balance over the
+//     148 SMs whatever CTA -> SM placement the (PDL-overlapped) launch got.  The last CTA to finish re-arms the counter.
+//   * a ring stage holds 8 keys AND their 8 values (one bulk async copy per row: HPC*128 contiguous bytes; rows sit
+//     16 bytes further apart than they are long, which makes every ldmatrix below bank-conflict free).  The producer
+//     warp streams item after item through the ring without draining; a stage is recycled as soon as its 8 keys are
+//     folded in, so the kernel behaves like a pure stream.
+//   * consumer warp = one head, ONLINE softmax (running max m, running sum l, rescaled accumulator): per stage
+//     scores = mma.m16n8k16(A = 8 keys x 16 dims via ldmatrix.x2, B = q in column 0), then
+//     acc = acc * exp(m_old - m_new) + mma.m16n8k8(A = V^T via ldmatrix.x2.trans, B = (p_hi, p_lo) in columns 0 / 1):
+//     the bf16 head and tail of the fp32 weight p = exp(s - m_new), so p keeps ~16 mantissa bits.  out = acc / l.
+// Same function as the reference's bmm / softmax / bmm (layers.py:102, 183-186); the online form differs from the
+// two-pass form only by fp32 rounding of the rescale factors.  Scores scaled by hs^-1/2 = 2^-3 (exact).
+// ------------------------------------------------------------------------------------------------
+constexpr int ATTM_CH = 8;         // keys (and values) per ring stage
+constexpr int ATTM_MAXSTAGES = 8;
+
+__device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+#endif
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+#endif
+}
+// D (16x8 fp32) += A (16x16 bf16, row) * B (16x8 bf16, col)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+#endif
+}
+// D (16x8 fp32) += A (16x8 bf16, row) * B (8x8 bf16, col)
+__device__ __forceinline__ void mma_bf16_1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(b0));
+#endif
+}
+
+__global__ void __launch_bounds__((ATTD_MAXHPC + 1) * 32)
+attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16* __restrict__ K, const bf16* __restrict__ V,
+                            bf16* __restrict__ out, int D, int t_stride, int n_keys, int hpc, int groups, int n_items,
+                            int stages, unsigned int* __restrict__ sched) {
+#if defined(__CUDA_ARCH__)
+  TraceScope trace_scope(trace_id);
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  const int slice_bytes = hpc * 128;                                // one key row of this head group
+  const int rowb = slice_bytes + 16;                                // staged row pitch
+  const int stage_bytes = 2 * ATTM_CH * rowb;                       // rows 0-7: keys, rows 8-15: their values
+  uint8_t* ring = att_smem;
+  uint8_t* qbuf = ring + stages * stage_bytes;                      // [2][slice_bytes]
+  float* ostage = reinterpret_cast<float*>(qbuf + 2 * slice_bytes); // [hpc][64] output staging
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ostage + hpc * 64);
+  uint64_t* empty_bar = full_bar + ATTM_MAXSTAGES;
+  uint64_t* qfull_bar = empty_bar + ATTM_MAXSTAGES;                 // [2]
+  uint64_t* qempty_bar = qfull_bar + 2;                             // [2]
+  int* qitem = reinterpret_cast<int*>(qempty_bar + 2);              // [2] item id that goes with qbuf[i]; -1 = no more
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nck = (n_keys + ATTM_CH - 1) / ATTM_CH;
+
+  if (threadIdx.x == 0) {
+    phase_mark(0);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], hpc);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qfull_bar[s], 1);
+      mbar_init(&qempty_bar[s], hpc);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) phase_mark(1);
+  pdl_launch_dependents();
+
+  if (w == hpc) {
+    // ---- producer ----
+    if (lane == 0) {
+      bool waited = false;
+      int item = blockIdx.x;
+      uint32_t g = 0;                                               // ring stages issued so far (all items)
+      for (int it = 0;; ++it) {
+        const int ip = it & 1;
+        const bool have = item < n_items;
+        const int b = have ? item / groups : 0, grp = have ? item % groups : 0;
+        const bf16* Kb = K + static_cast<size_t>(b) * t_stride * D + grp * hpc * 64;
+        const bf16* Vb = V + static_cast<size_t>(b) * t_stride * D + grp * hpc * 64;
+        auto issue = [&](int ck, int s) {
+          const int rows = (n_keys - ck * ATTM_CH) < ATTM_CH ? (n_keys - ck * ATTM_CH) : ATTM_CH;
+          mbar_arrive_expect_tx(&full_bar[s], 2u * static_cast<uint32_t>(rows) * slice_bytes);
+          const bf16* ks = Kb + static_cast<size_t>(ck) * ATTM_CH * D;
+          const bf16* vs = Vb + static_cast<size_t>(ck) * ATTM_CH * D;
+          uint8_t* dst = ring + s * stage_bytes;
+          for (int r = 0; r < rows; ++r) {
+            bulk_load_1d(dst + r * rowb, ks + static_cast<size_t>(r) * D, slice_bytes, &full_bar[s]);
+            bulk_load_1d(dst + (ATTM_CH + r) * rowb, vs + static_cast<size_t>(r) * D, slice_bytes, &full_bar[s]);
+          }
+        };
+        int i = 0;
+        if (have && !waited) {
+          // every key but the newest was written by earlier launches: those stages do not wait for the QKV GEMM
+          for (; i < nck - 1 && i < stages; ++i, ++g) issue(i, g % stages);
+        }
+        if (!waited) {
+          pdl_wait();
+          waited = true;
+        }
+        // q slice + item id of this item (or the end marker)
+        mbar_wait(&qempty_bar[ip], ((it >> 1) & 1) ^ 1);
+        qitem[ip] = have ? item : -1;
+        if (!have) {
+          mbar_arrive(&qfull_bar[ip]);
+          break;
+        }
+        if (it == 0) {
+          mbar_arrive(&qfull_bar[ip]);      // first item: the consumers fetch q themselves, ahead of the queued K/V rows
+        } else {
+          mbar_arrive_expect_tx(&qfull_bar[ip], slice_bytes);
+          bulk_load_1d(qbuf + ip * slice_bytes, q + static_cast<size_t>(b) * D + grp * hpc * 64, slice_bytes, &qfull_bar[ip]);
+        }
+        const int next = static_cast<int>(atomicAdd(sched, 1u)) + static_cast<int>(gridDim.x);
+        for (; i < nck; ++i, ++g) {
+          const int s = g % stages;
+          mbar_wait(&empty_bar[s], ((g / stages) & 1) ^ 1);
+          issue(i, s);
+        }
+        item = next;
+      }
+      // the last CTA to run out of work re-arms the ticket counter for the next launch
+      if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) {
+        sched[0] = 0;
+        sched[1] = 0;
+        __threadfence();
+      }
+    }
+    return;
+  }
+  if (w > hpc) return;
+
+  // ---- consumers: warp w owns head grp * hpc + w of every item this CTA takes ----
+  pdl_wait();
+  const int gq = lane >> 2, tq = lane & 3;          // mma fragment coordinates: row / column pair
+  const int lr = lane & 7, lm = (lane >> 3) & 1;    // ldmatrix.x2: row within the matrix, matrix index (lanes 0-15)
+  const uint32_t ring_u32 = smem_u32(ring);
+  // K tile (8 keys x 16 dims): matrices dims 0-7 | 8-15 -> fragments a0 | a2 (rows 8-15 of the MMA are zero)
+  const uint32_t k_off = static_cast<uint32_t>(lr * rowb + w * 128 + lm * 16);
+  // V^T tile (16 dims x 8 keys): stored blocks (8 keys) x (dims 0-7 | 8-15), transposed on load -> a0 | a1
+  const uint32_t v_off = static_cast<uint32_t>((ATTM_CH + lr) * rowb + w * 128 + lm * 16);
+  float* orow = ostage + w * 64;
+  uint32_t g = 0;
+  for (int it = 0;; ++it) {
+    const int ip = it & 1;
+    mbar_wait(&qfull_bar[ip], (it >> 1) & 1);
+    const int item = qitem[ip];
+    if (item < 0) break;
+    if (it == 0 && threadIdx.x == 0) phase_mark(2);
+    // q as the B operand: column 0 (lanes 0-3) holds dims 2*tq, 2*tq+1 (+8) of each 16-dim step
+    uint32_t qb[4][2];
+    {
+      const uint32_t* q32 =
+          it == 0 ? reinterpret_cast<const uint32_t*>(q + static_cast<size_t>(item / groups) * D + ((item % groups) * hpc + w) * 64)
+                  : reinterpret_cast<const uint32_t*>(qbuf + ip * slice_bytes + w * 128);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        qb[ks][0] = gq == 0 ? q32[ks * 8 + tq] : 0u;
+        qb[ks][1] = gq == 0 ? q32[ks * 8 + 4 + tq] : 0u;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&qempty_bar[ip]);
+
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[4][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][e] = 0.f;
+
+    for (int c = 0; c < nck; ++c, ++g) {
+      const int s = g % stages;
+      const int left = n_keys - c * ATTM_CH;          // valid keys in this stage (>= 1)
+      mbar_wait(&full_bar[s], (g / stages) & 1);
+      if (g == 0 && threadIdx.x == 0) phase_mark(3);
+      const uint32_t base = ring_u32 + s * stage_bytes;
+      // ---- scores of the 8 keys: lane (gq, tq = 0) gets key gq ----
+      float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a0, a2;
+        ldmatrix_x2(base + k_off + ks * 32, a0, a2);
+        mma_bf16_16816(sc, a0, 0u, a2, 0u, qb[ks][0], qb[ks][1]);
+      }
+      float sk = __shfl_sync(0xffffffffu, sc[0], lane & ~3) * 0.125f;   // every lane of quad gq: score of key gq
+      if (gq >= left) sk = -INFINITY;                                    // rows past the cache end hold stale bytes
+      float cm = sk;
+      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 4));
+      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
+      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
+      const float m_new = fmaxf(m_run, cm);
+      const float alpha = expf(m_run - m_new);         // first stage: exp(-inf) = 0
+      const float pk = expf(sk - m_new);               // masked keys: exp(-inf) = 0
+      float ps = pk;
+      ps += __shfl_xor_sync(0xffffffffu, ps, 4);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 8);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 16);
+      l_run = l_run * alpha + ps;
+      m_run = m_new;
+      // ---- B operand of the value MMA: keys 2*tq, 2*tq+1; column 0 = bf16 head of p, column 1 = bf16 tail ----
+      const float p0 = __shfl_sync(0xffffffffu, pk, 8 * tq);
+      const float p1 = __shfl_sync(0xffffffffu, pk, 8 * tq + 4);
+      uint32_t pb = 0u;
+      {
+        __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+        if (gq == 1) {
+          const float2 f = __bfloat1622float2(h);
+          h = __floats2bfloat162_rn(p0 - f.x, p1 - f.y);
+        }
+        if (gq < 2) pb = *reinterpret_cast<uint32_t*>(&h);
+      }
+      // stale value rows: 0 * NaN must not reach the accumulator
+      uint32_t vmask = 0xFFFFFFFFu;
+      if (left < ATTM_CH) vmask = (2 * tq < left ? 0x0000FFFFu : 0u) | (2 * tq + 1 < left ? 0xFFFF0000u : 0u);
+      if (alpha != 1.0f) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[mt][e] *= alpha;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        uint32_t a0, a1;
+        ldmatrix_x2_trans(base + v_off + mt * 32, a0, a1);
+        mma_bf16_1688(o[mt], a0 & vmask, a1 & vmask, pb);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    // ---- out: lanes with tq == 0 hold dims mt*16 + gq (columns 0 + 1) and mt*16 + 8 + gq ----
+    const float inv = 1.0f / l_run;
+    if (tq == 0) {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        orow[mt * 16 + gq] = (o[mt][0] + o[mt][1]) * inv;
+        orow[mt * 16 + 8 + gq] = (o[mt][2] + o[mt][3]) * inv;
+      }
+    }
+    __syncwarp();
+    if (lane < 8) {
+      const int b = item / groups, h = (item % groups) * hpc + w;
+      float v[8];
+      const float4 x0 = *reinterpret_cast<const float4*>(orow + lane * 8);
+      const float4 x1 = *reinterpret_cast<const float4*>(orow + lane * 8 + 4);
+      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+      store8(out + static_cast<size_t>(b) * D + h * 64 + lane * 8, v);
+    }
+    __syncwarp();
+    if (it == 0 && threadIdx.x == 0) phase_mark(6);
+  }
+  if (threadIdx.x == 0) phase_mark(7);
 #endif
 }
 

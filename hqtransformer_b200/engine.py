@@ -170,6 +170,16 @@ class Engine:
               "hq_bench_attention")
         return us.value
 
+    def attention_phases(self, batch: int, n_keys: int, warm: int = 3, max_ctas: int = 4096):
+        """Per-CTA timestamps (ns) of one decode-attention launch: int64 array [n_ctas, 8] (hq_debug_attention_phases)."""
+        import numpy as np
+        buf = (C.c_uint64 * (max_ctas * 8))()
+        n = C.c_int()
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._lib.hq_debug_attention_phases(self._ctx, batch, n_keys, warm, buf, max_ctas, C.byref(n), C.c_void_p(st)),
+              self._ctx, "hq_debug_attention_phases")
+        return np.frombuffer(buf, dtype=np.uint64).reshape(max_ctas, 8)[:n.value].astype(np.int64)
+
     def bench_gemm(self, kind: int, M: int, iters: int = 20) -> float:
         """Mean microseconds of one GEMM launch of family `kind` (0 qkv, 1 proj, 2 fc1, 3 fc2, 4 head_top) at M rows,
         L2 evicted between launches."""
@@ -194,6 +204,24 @@ def debug_gemm(A: torch.Tensor, W: torch.Tensor, tile: int = 0) -> torch.Tensor:
         st = torch.cuda.current_stream(A.device).cuda_stream
         check(lib.hq_debug_gemm(prec, A.data_ptr(), W.data_ptr(), out.data_ptr(), M, N, K, tile, C.c_void_p(st)), None,
               "hq_debug_gemm")
+    return out
+
+
+def debug_attention(q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, n_keys: int, variant: int = 0) -> torch.Tensor:
+    """Single-query attention of every row of q [B, D] over the first n_keys rows of its cache K / V [B, T, D]
+    (head size 64) through the engine's decode kernels; variant 0 = engine choice, 1 = scalar bulk-staged kernel."""
+    lib = _lib.load()
+    assert q.is_cuda and q.dtype == K.dtype == V.dtype and q.dtype in (torch.bfloat16, torch.float32)
+    assert q.is_contiguous() and K.is_contiguous() and V.is_contiguous() and K.shape == V.shape
+    B, D = q.shape
+    T = K.shape[1]
+    assert K.shape == (B, T, D) and D % 64 == 0 and 1 <= n_keys <= T
+    out = torch.empty_like(q)
+    prec = _lib.HQ_PREC_BF16 if q.dtype == torch.bfloat16 else _lib.HQ_PREC_FP32
+    with torch.cuda.device(q.device):
+        st = torch.cuda.current_stream(q.device).cuda_stream
+        check(lib.hq_debug_attention(prec, q.data_ptr(), K.data_ptr(), V.data_ptr(), out.data_ptr(), B, D // 64, T, n_keys,
+                                     variant, C.c_void_p(st)), None, "hq_debug_attention")
     return out
 
 

@@ -175,9 +175,21 @@ int hq_debug_sample(const float* logits, int R, int V, float temperature, int to
                     uint64_t seed, uint64_t row_offset, int position, int slot,
                     int64_t* out_codes, float* out_probs /* optional [R, V] */, void* stream);
 
+/* Single-query attention of B rows over `n_keys` cached keys through the kernels the sampler uses: q / out [B, D],
+ * K / V [B, t_stride, D] with D = n_heads * 64, device pointers in the precision's activation type (bf16 / fp32).
+ * variant: 0 = the engine's choice (bf16: persistent ldmatrix/mma kernel), 1 = the scalar bulk-staged kernel. */
+int hq_debug_attention(int prec, const void* q, const void* K, const void* V, void* out, int B, int n_heads,
+                       int t_stride, int n_keys, int variant, void* stream);
+
 /* Times the single-query KV-cache attention kernel alone at cache length `n_keys` for batch B on the
  * ctx's cache (events on `stream`); returns mean microseconds over `iters` launches in *usec. */
 int hq_bench_attention(hq_ctx* ctx, int B, int n_keys, int iters, float* usec, void* stream);
+
+/* One instrumented launch of the decode attention at cache length `n_keys` after `warm` plain ones: out_ns[8*c + p] =
+ * %globaltimer (ns) at which CTA c passed point p (0 start, 1 barriers ready, 2 q ready, 3 first keys landed, 4 scores
+ * done, 5 softmax done, 6 first item written, 7 CTA end); *n_ctas = CTAs that reported. */
+int hq_debug_attention_phases(hq_ctx* ctx, int B, int n_keys, int warm, unsigned long long* out_ns, int max_ctas,
+                              int* n_ctas, void* stream);
 
 /* Times one GEMM family of the loop alone on the ctx's own weights and buffers: kind 0 = fused qkv [3D, D],
  * 1 = attention proj [D, D], 2 = mlp fc1 [4D, D], 3 = mlp fc2 [D, 4D], 4 = head_top [V, D]; M rows.  L2 is evicted

@@ -40,6 +40,70 @@ def test_gemm_tcgen05_every_tile_variant(M, N, K, tile):
     assert err <= 2e-5 * max(ref.abs().max().item(), 1.0) * (K / 64) ** 0.5 + 1e-5, err
 
 
+def _attention_ref(q, K, V, n_keys):
+    """fp64 restatement of layers.py:102, 183-186 for one query per row: softmax(q K^T / 8) V per 64-wide head."""
+    B, D = q.shape
+    nh = D // 64
+    qh = q.double().view(B, nh, 1, 64)
+    Kh = K[:, :n_keys].double().view(B, n_keys, nh, 64).permute(0, 2, 1, 3)
+    Vh = V[:, :n_keys].double().view(B, n_keys, nh, 64).permute(0, 2, 1, 3)
+    att = torch.softmax(qh @ Kh.transpose(-1, -2) * 0.125, dim=-1)
+    return (att @ Vh).reshape(B, D)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("B,nh,T,n_keys", [(3, 4, 64, 1), (5, 4, 64, 7), (4, 24, 64, 16), (7, 24, 64, 17), (9, 24, 64, 33),
+                                           (300, 24, 64, 64), (2, 24, 127, 127), (640, 12, 64, 40), (3, 6, 127, 100),
+                                           (256, 24, 64, 32)])
+def test_attention_decode_bf16_matches_fp64(B, nh, T, n_keys, variant):
+    """KV-cache decode attention (persistent ldmatrix/mma kernel and the scalar kernel) vs an fp64 restatement on the
+    same bf16 inputs: the only error sources are fp32 accumulation and the bf16 rounding of the output
+    (tolerance: 2^-8 relative to the largest |value| of the row's head, i.e. one bf16 ulp, plus 1e-3)."""
+    from hqtransformer_b200.engine import debug_attention
+    g = torch.Generator(device="cuda").manual_seed(B * 131 + nh * 17 + n_keys)
+    D = nh * 64
+    q = (torch.randn(B, D, generator=g, device="cuda") * 1.5).to(torch.bfloat16)
+    K = torch.randn(B, T, D, generator=g, device="cuda").to(torch.bfloat16)
+    V = torch.randn(B, T, D, generator=g, device="cuda").to(torch.bfloat16)
+    K[:, n_keys:] = float("nan")          # rows past the cache length must never be read into the result
+    V[:, n_keys:] = float("nan")
+    out = debug_attention(q, K, V, n_keys, variant=variant)
+    ref = _attention_ref(q, K, V, n_keys)
+    assert torch.isfinite(out.float()).all()
+    err = (out.double() - ref).abs()
+    bound = ref.abs().view(B, nh, 64).amax(-1, keepdim=True).expand(B, nh, 64).reshape(B, D) * 2.0 ** -8 + 1e-3
+    assert (err <= bound).all(), (err.max().item(), (err - bound).max().item())
+    # both kernels read every key exactly once and must agree far below bf16 resolution before rounding
+    if variant == 0:
+        other = debug_attention(q, K, V, n_keys, variant=1)
+        assert (out.float() - other.float()).abs().max().item() <= 2.0 ** -7 * max(1.0, ref.abs().max().item())
+
+
+def test_attention_decode_repeated_launches_rearm_the_ticket_counter():
+    """The persistent kernel's work-ticket counter is re-armed by the last CTA: back-to-back launches on one ctx see
+    a clean counter (a stale one would skip or repeat items)."""
+    from hqtransformer_b200.engine import debug_attention
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, nh, T, n = 777, 24, 64, 48
+    q = torch.randn(B, nh * 64, generator=g, device="cuda").to(torch.bfloat16)
+    K = torch.randn(B, T, nh * 64, generator=g, device="cuda").to(torch.bfloat16)
+    V = torch.randn(B, T, nh * 64, generator=g, device="cuda").to(torch.bfloat16)
+    first = debug_attention(q, K, V, n)
+    for _ in range(3):
+        assert torch.equal(debug_attention(q, K, V, n), first)
+
+
+def test_attention_decode_fp32_matches_fp64():
+    from hqtransformer_b200.engine import debug_attention
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, nh, T, n = 6, 4, 64, 37
+    q = torch.randn(B, nh * 64, generator=g, device="cuda")
+    K = torch.randn(B, T, nh * 64, generator=g, device="cuda")
+    V = torch.randn(B, T, nh * 64, generator=g, device="cuda")
+    out = debug_attention(q, K, V, n)
+    assert (out.double() - _attention_ref(q, K, V, n)).abs().max().item() < 2e-5
+
+
 @pytest.mark.parametrize("M,N,K", [(64, 128, 16), (5, 256, 128), (100, 1032, 256), (257, 384, 1536)])
 def test_gemm_fp32_matches_matmul(M, N, K):
     from hqtransformer_b200.engine import debug_gemm
