@@ -103,6 +103,8 @@ struct hq_ctx {
   float *x = nullptr, *yd = nullptr, *logits = nullptr;
   float* splitk_ws = nullptr;   // [LN_MAXFOLD][rows][D] fp32 partial sums of split-K fc2 GEMMs (folded in by the next LayerNorm)
   unsigned int* att_sched = nullptr;   // [2] work-ticket / finished-CTA counters of attention_decode_mma_kernel (rest at 0)
+  CUtensorMap kmap, vmap;              // spatial KV cache as [rows = L*B*Tc][heads][64] bf16, box {64, hpc, 8}, SWIZZLE_128B
+  bool kv_maps = false;
   int num_sms = 0;
   int ws_rows = 0;
   void *kc = nullptr, *vc = nullptr, *kd = nullptr, *vd = nullptr;
@@ -158,6 +160,23 @@ static int make_map(hq_ctx* ctx, CUtensorMap* m, void* base, uint64_t rows, uint
   if (r != CUDA_SUCCESS) {
     set_err(ctx, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", static_cast<int>(r),
             static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols));
+    return HQ_ERR_CUDA;
+  }
+  return HQ_OK;
+}
+
+// KV cache rows as a 3-D tensor {64 dims, n_heads, rows}: one box = 8 cache rows of one head group (hpc heads)
+static int make_kv_map(hq_ctx* ctx, CUtensorMap* m, const void* base, int n_heads, uint64_t rows, int hpc) {
+  cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(n_heads), rows};
+  cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(n_heads) * 128};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(hpc), 8};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_err(ctx, "cuTensorMapEncodeTiled (KV cache) failed (%d) heads=%d rows=%llu hpc=%d", static_cast<int>(r), n_heads,
+            static_cast<unsigned long long>(rows), hpc);
     return HQ_ERR_CUDA;
   }
   return HQ_OK;
@@ -284,6 +303,18 @@ static int check_device(hq_ctx* ctx, int device) {
 static void free_activations(hq_ctx* ctx);
 static int reserve_impl(hq_ctx* ctx, int max_batch);
 
+// Head groups per image of the decode attention kernels: (image, group) work items, nh / groups heads (warps) each.
+static int attn_groups(int nh) {
+  int g = 0;
+  for (int cand : {4, 3, 2, 1})
+    if (nh % cand == 0 && nh / cand <= ATTD_MAXHPC) { g = cand; break; }
+  if (const char* f = getenv("HQ_ATTN_GROUPS")) {          // experiments: pin the number of head groups per image
+    const int v = atoi(f);
+    if (v >= 1 && nh % v == 0 && nh / v <= ATTD_MAXHPC) g = v;
+  }
+  return g;
+}
+
 extern "C" int hq_abi_version(void) { return HQ_ABI_VERSION; }
 
 extern "C" const char* hq_last_error(const hq_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
@@ -336,6 +367,16 @@ static int reserve_impl(hq_ctx* ctx, int max_batch) {
   const size_t kvn = static_cast<size_t>(ctx->L) * B * ctx->Tc * D * ctx->wsize;
   if ((rc = dev_alloc(ctx, &ctx->kc, kvn))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->vc, kvn))) return rc;
+  ctx->kv_maps = false;
+  if (ctx->bf16) {
+    const int groups = attn_groups(ctx->nh);
+    if (groups > 0) {
+      const uint64_t rows = static_cast<uint64_t>(ctx->L) * B * ctx->Tc;
+      if ((rc = make_kv_map(ctx, &ctx->kmap, ctx->kc, ctx->nh, rows, ctx->nh / groups))) return rc;
+      if ((rc = make_kv_map(ctx, &ctx->vmap, ctx->vc, ctx->nh, rows, ctx->nh / groups))) return rc;
+      ctx->kv_maps = true;
+    }
+  }
   const size_t kdn = static_cast<size_t>(ctx->Ld) * B * 5 * D * ctx->wsize;
   if ((rc = dev_alloc(ctx, &ctx->kd, kdn))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->vd, kdn))) return rc;
@@ -591,6 +632,21 @@ static void launch_k(hq_ctx* ctx, cudaStream_t st, const char* tag, void (*kerne
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+  // experiments only: HQ_ABLATE=tag[,tag...] drops every launch whose tag starts with one of the names, to read a
+  // kernel family's MARGINAL cost in the PDL-overlapped loop off the step time (results are garbage, timing is not)
+  static const char* ablate = getenv("HQ_ABLATE");
+  if (ablate != nullptr) {
+    const size_t n = strlen(tag);
+    for (const char* p = ablate; *p;) {
+      const char* e = strchr(p, ',');
+      const size_t len = e ? static_cast<size_t>(e - p) : strlen(p);
+      if (len > 0 && len <= n && strncmp(p, tag, len) == 0) {
+        ctx->tag_suffix.clear();
+        return;
+      }
+      p += len + (e ? 1 : 0);
+    }
+  }
   int trace_id = -1;
   if (ctx->tracing && static_cast<int>(ctx->trace_tags.size()) < ctx->trace_cap) {
     trace_id = static_cast<int>(ctx->trace_tags.size());
@@ -709,7 +765,9 @@ template <typename AT>
 static void layernorm_act(hq_ctx* ctx, cudaStream_t st, float* x, const float* g, const float* b, AT* out, int rows,
                           Fold* fold = nullptr) {
   Fold f = fold ? *fold : Fold();
-  launch_k(ctx, st, "layernorm", layernorm_kernel<AT>, dim3(rows), dim3(LN_THREADS), 0, x, g, b, nullptr, out, rows,
+  // the lean instantiation (<= 3 partial sums in registers) unless the pending split is wider
+  auto kern = f.n > 3 ? layernorm_kernel<AT, LN_MAXFOLD> : layernorm_kernel<AT, 3>;
+  launch_k(ctx, st, "layernorm", kern, dim3(rows), dim3(LN_THREADS), 0, x, g, b, nullptr, out, rows,
            ctx->D, 1, 0, f.partial, f.n, f.stride, f.bias);
   if (fold) *fold = Fold();
 }
@@ -722,14 +780,8 @@ static int attn_sleep_ns() {
 // Launch plan of attention_decode_kernel for this model: head groups per image, keys per ring stage, dynamic smem.
 template <typename AT>
 static bool attn_decode_plan(const hq_ctx* ctx, int* CH, int* hpc, int* groups, size_t* smem) {
-  int g = 1;
-  for (int cand : {4, 3, 2, 1})
-    if (ctx->nh % cand == 0 && ctx->nh / cand <= ATTD_MAXHPC) { g = cand; break; }
-  if (const char* f = getenv("HQ_ATTN_GROUPS")) {          // experiments: pin the number of head groups per image
-    const int v = atoi(f);
-    if (v >= 1 && ctx->nh % v == 0) g = v;
-  }
-  if (ctx->nh / g > ATTD_MAXHPC) return false;
+  const int g = attn_groups(ctx->nh);
+  if (g <= 0) return false;
   *groups = g;
   *hpc = ctx->nh / g;
   const int row_bytes = *hpc * 64 * static_cast<int>(sizeof(AT));
@@ -748,19 +800,21 @@ static bool attn_decode_plan(const hq_ctx* ctx, int* CH, int* hpc, int* groups, 
 static int g_attn_scalar = 0;   // tests: hq_debug_attention may pin the scalar bulk-staged kernel
 static bool attn_mma_plan(const hq_ctx* ctx, int groups, int hpc, int n_items, int* stages, size_t* smem, int* grid) {
   static const bool off = getenv("HQ_ATTN_SCALAR") != nullptr;      // experiments: the scalar bulk-staged kernel
-  if (off || g_attn_scalar || !ctx->bf16 || ctx->num_sms <= 0) return false;
-  const size_t stage = static_cast<size_t>(2 * ATTM_CH) * (hpc * 128 + 16);
-  int st = static_cast<int>((52 * 1024) / stage);
+  if (off || g_attn_scalar || !ctx->bf16 || ctx->num_sms <= 0 || !ctx->kv_maps) return false;
+  const size_t stage = static_cast<size_t>(2 * ATTM_CH) * hpc * 128;     // K tile + V tile
+  int st = static_cast<int>((50 * 1024) / stage);
   if (st > 4) st = 4;
   if (const char* f = getenv("HQ_ATTM_STAGES")) st = atoi(f);     // experiments
   if (st < 2) st = 2;
   if (st > ATTM_MAXSTAGES) st = ATTM_MAXSTAGES;
-  const size_t bytes = st * stage + 2 * static_cast<size_t>(hpc) * 128 + static_cast<size_t>(hpc) * 64 * 4 +
-                       (2 * ATTM_MAXSTAGES + 4) * 8 + 16;
+  const size_t bytes = 1024 /*tile alignment*/ + st * stage + 2 * static_cast<size_t>(hpc) * 128 +
+                       static_cast<size_t>(hpc) * 64 * 4 + (2 * ATTM_MAXSTAGES + 4) * 8 + 16;
   if (bytes > 112 * 1024) return false;
   int per_sm = static_cast<int>((227 * 1024) / (bytes + 1024));
   const int by_threads = 2048 / ((hpc + 1) * 32);
   if (per_sm > by_threads) per_sm = by_threads;
+  const int by_regs = 65536 / ((hpc + 1) * 32 * 72);              // 72 registers per thread (ptxas)
+  if (by_regs >= 1 && per_sm > by_regs) per_sm = by_regs;
   if (const char* f = getenv("HQ_ATTM_PER_SM")) per_sm = atoi(f) < per_sm ? atoi(f) : per_sm;   // experiments
   if (per_sm < 1) per_sm = 1;
   (void)groups;
@@ -772,12 +826,14 @@ static bool attn_mma_plan(const hq_ctx* ctx, int groups, int hpc, int n_items, i
 }
 
 template <typename AT>
-static void launch_attn_mma(hq_ctx*, cudaStream_t, const AT*, const AT*, const AT*, AT*, int, int, int, int, int, int, int, size_t) {}
+static void launch_attn_mma(hq_ctx*, cudaStream_t, const AT*, const AT*, AT*, int, int, int, int, int, int, int, size_t) {}
 template <>
-void launch_attn_mma<bf16>(hq_ctx* ctx, cudaStream_t st, const bf16* q, const bf16* K, const bf16* V, bf16* out, int t_stride,
-                           int n_keys, int hpc, int groups, int n_items, int stages, int grid, size_t smem) {
-  launch_k(ctx, st, "attention_decode", attention_decode_mma_kernel, dim3(grid), dim3((hpc + 1) * 32), smem, q, K, V, out,
-           ctx->D, t_stride, n_keys, hpc, groups, n_items, stages, ctx->att_sched);
+void launch_attn_mma<bf16>(hq_ctx* ctx, cudaStream_t st, const bf16* q, const bf16* K, bf16* out, int t_stride, int n_keys,
+                           int hpc, int groups, int n_items, int stages, int grid, size_t smem) {
+  // K (and V, at the same offset in its own cache) as a row offset into the cache-wide tensor maps
+  const int row_base = static_cast<int>((K - static_cast<const bf16*>(ctx->kc)) / ctx->D);
+  launch_k(ctx, st, "attention_decode", attention_decode_mma_kernel, dim3(grid), dim3((hpc + 1) * 32), smem, ctx->kmap, ctx->vmap,
+           row_base, q, out, ctx->D, t_stride, n_keys, hpc, groups, n_items, stages, ctx->att_sched);
 }
 
 template <typename AT>
@@ -790,8 +846,11 @@ static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, co
     if (ctx->tracing) ctx->tag_suffix = ":t" + std::to_string(kbase) + ":B" + std::to_string(M);
     int stages = 0, grid = 0;
     size_t smem2 = 0;
-    if (sizeof(AT) == 2 && attn_mma_plan(ctx, groups, hpc, M * groups, &stages, &smem2, &grid)) {
-      launch_attn_mma<AT>(ctx, st, q, K, V, out, t_stride, kbase, hpc, groups, M * groups, stages, grid, smem2);
+    // the tensor maps describe ctx->kc / ctx->vc: the TMA kernel needs K and V at the same offset inside them
+    const bool in_cache = reinterpret_cast<const char*>(K) - static_cast<const char*>(ctx->kc) ==
+                          reinterpret_cast<const char*>(V) - static_cast<const char*>(ctx->vc);
+    if (sizeof(AT) == 2 && in_cache && attn_mma_plan(ctx, groups, hpc, M * groups, &stages, &smem2, &grid)) {
+      launch_attn_mma<AT>(ctx, st, q, K, out, t_stride, kbase, hpc, groups, M * groups, stages, grid, smem2);
       return;
     }
     launch_k(ctx, st, "attention_decode", attention_decode_kernel<AT>, dim3(M * groups), dim3((hpc + 1) * 32), smem, q, K, V,
@@ -948,7 +1007,8 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
     else run_block<AT>(ctx, st, ctx->blocks[l], ctx->x, M, 0, kc + l * lstride, vc + l * lstride, 1, Tc, tok, tok + 1, 0, &fold_x);
   }
   // ---- hs = ln_f(x) (last prefix row for text), depth start token y = hs + sos_depth ----
-  launch_k(ctx, st, "layernorm_f", layernorm_kernel<float>, dim3(B), dim3(LN_THREADS), 0, ctx->x, ctx->lnf_g, ctx->lnf_b,
+  launch_k(ctx, st, "layernorm_f", fold_x.n > 3 ? layernorm_kernel<float, LN_MAXFOLD> : layernorm_kernel<float, 3>, dim3(B),
+           dim3(LN_THREADS), 0, ctx->x, ctx->lnf_g, ctx->lnf_b,
            ctx->sos_depth, ctx->yd, B, D, prefill ? T0 : 1, prefill ? T0 - 1 : 0, fold_x.partial, fold_x.n, fold_x.stride,
            fold_x.bias);
   fold_x = Fold();
@@ -1143,6 +1203,20 @@ extern "C" int hq_debug_attention(int prec, const void* q, const void* K, const 
   if ((rc = set_smem(&tmp, attention_decode_mma_kernel, 112 * 1024))) return rc;
   HQ_CUDA(nullptr, cudaMalloc(reinterpret_cast<void**>(&tmp.att_sched), 16));
   cudaMemsetAsync(tmp.att_sched, 0, 16, st);
+  if (tmp.bf16 && variant != 1) {
+    const int groups = attn_groups(n_heads);
+    tmp.kc = const_cast<void*>(K);
+    tmp.vc = const_cast<void*>(V);
+    if ((rc = get_encode_fn(&tmp, &tmp.encode)) == HQ_OK && groups > 0 &&
+        (rc = make_kv_map(&tmp, &tmp.kmap, K, n_heads, static_cast<uint64_t>(B) * t_stride, n_heads / groups)) == HQ_OK &&
+        (rc = make_kv_map(&tmp, &tmp.vmap, V, n_heads, static_cast<uint64_t>(B) * t_stride, n_heads / groups)) == HQ_OK)
+      tmp.kv_maps = true;
+    if (rc) {
+      cudaFree(tmp.att_sched);
+      set_err(nullptr, "hq_debug_attention: %s", tmp.err.c_str());
+      return rc;
+    }
+  }
   g_attn_scalar = variant == 1;
   if (tmp.bf16)
     attention<bf16>(&tmp, st, static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V),

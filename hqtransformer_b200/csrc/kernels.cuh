@@ -117,7 +117,7 @@ embed_depth_kernel(int trace_id, float* y, const float* E_top_depth, const float
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_THREADS = 128;
 constexpr int LN_MAXV = 3;    // float4 per thread held in registers: rows up to 3 * 512 = 1536 columns
-constexpr int LN_MAXFOLD = 6; // split-K partial sums a LayerNorm can fold in
+constexpr int LN_MAXFOLD = 6; // split-K partial sums a LayerNorm can fold in (kernel instantiated for <= 3 and <= 6)
 
 template <typename OutT>
 __device__ __forceinline__ void ln_store4(OutT* o, int i, float y0, float y1, float y2, float y3) {
@@ -145,7 +145,7 @@ __device__ __forceinline__ float block_sum_128(float v, float* red /*[4]*/) {
 // are ALL requested before the first use - one round trip - then two block reductions and the stores.
 //   fold != nullptr: x[r] += fold_bias + sum_s fold[s][r]  first (split-K partial sums of the preceding GEMM, summed
 //   in a fixed order, so the result is deterministic), and the updated x row is written back.
-template <typename OutT>
+template <typename OutT, int MAXFOLD>
 __global__ void __launch_bounds__(LN_THREADS)
 layernorm_kernel(int trace_id, float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* __restrict__ add, OutT* __restrict__ out, int rows, int D, int in_mul, int in_off,
@@ -159,7 +159,7 @@ layernorm_kernel(int trace_id, float* __restrict__ x, const float* __restrict__ 
   OutT* o = out + static_cast<size_t>(r) * D;
   const int tid = threadIdx.x;
   if (D <= LN_MAXV * LN_THREADS * 4) {
-    float4 v[LN_MAXV], g[LN_MAXV], bt[LN_MAXV], ad[LN_MAXV], fb[LN_MAXV], f[LN_MAXFOLD][LN_MAXV];
+    float4 v[LN_MAXV], g[LN_MAXV], bt[LN_MAXV], ad[LN_MAXV], fb[LN_MAXV], f[MAXFOLD][LN_MAXV];
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < LN_MAXV; ++j) {
@@ -171,12 +171,12 @@ layernorm_kernel(int trace_id, float* __restrict__ x, const float* __restrict__ 
       ad[j] = add != nullptr ? *reinterpret_cast<const float4*>(add + ic) : z4;
       fb[j] = z4;
 #pragma unroll
-      for (int sidx = 0; sidx < LN_MAXFOLD; ++sidx) f[sidx][j] = z4;
+      for (int sidx = 0; sidx < MAXFOLD; ++sidx) f[sidx][j] = z4;
       if (fold != nullptr) {
         const float* fr = fold + (static_cast<size_t>(r) * in_mul + in_off) * D + ic;
         fb[j] = fold_bias != nullptr ? *reinterpret_cast<const float4*>(fold_bias + ic) : z4;
 #pragma unroll
-        for (int sidx = 0; sidx < LN_MAXFOLD; ++sidx)
+        for (int sidx = 0; sidx < MAXFOLD; ++sidx)
           if (sidx < n_fold) f[sidx][j] = *reinterpret_cast<const float4*>(fr + sidx * fold_stride);
       }
     }
@@ -187,7 +187,7 @@ layernorm_kernel(int trace_id, float* __restrict__ x, const float* __restrict__ 
       if (fold != nullptr) {
         float4 a = f[0][j];                               // fixed left-to-right order: deterministic
 #pragma unroll
-        for (int sidx = 1; sidx < LN_MAXFOLD; ++sidx) {
+        for (int sidx = 1; sidx < MAXFOLD; ++sidx) {
           a.x += f[sidx][j].x; a.y += f[sidx][j].y; a.z += f[sidx][j].z; a.w += f[sidx][j].w;
         }
         v[j].x += fb[j].x + a.x;
@@ -579,10 +579,11 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
 //   * work item = (image, head group); a CTA takes item blockIdx.x first and then draws further items from a global
 //     ticket counter (`sched`), so SMs that finish early take more of them - the ~1000 items of a step balance over the
 //     148 SMs whatever CTA -> SM placement the (PDL-overlapped) launch got.  The last CTA to finish re-arms the counter.
-//   * a ring stage holds 8 keys AND their 8 values (one bulk async copy per row: HPC*128 contiguous bytes; rows sit
-//     16 bytes further apart than they are long, which makes every ldmatrix below bank-conflict free).  The producer
-//     warp streams item after item through the ring without draining; a stage is recycled as soon as its 8 keys are
-//     folded in, so the kernel behaves like a pure stream.
+//   * a ring stage holds 8 keys AND their 8 values, each fetched by ONE 3-D TMA tile load (box 64 dims x HPC heads x
+//     8 cache rows, SWIZZLE_128B) - a per-row bulk copy costs ~45 ns of issue time in the producer thread, which at
+//     16 copies per stage was the kernel's start-up and nearly its steady-state limit (profiles/r1_attn_phases.txt).
+//     The producer warp streams item after item through the ring without draining; a stage is recycled as soon as
+//     its 8 keys are folded in, so the kernel behaves like a pure stream.
 //   * consumer warp = one head, ONLINE softmax (running max m, running sum l, rescaled accumulator): per stage
 //     scores = mma.m16n8k16(A = 8 keys x 16 dims via ldmatrix.x2, B = q in column 0), then
 //     acc = acc * exp(m_old - m_new) + mma.m16n8k8(A = V^T via ldmatrix.x2.trans, B = (p_hi, p_lo) in columns 0 / 1):
@@ -622,16 +623,16 @@ __device__ __forceinline__ void mma_bf16_1688(float (&c)[4], uint32_t a0, uint32
 }
 
 __global__ void __launch_bounds__((ATTD_MAXHPC + 1) * 32)
-attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16* __restrict__ K, const bf16* __restrict__ V,
-                            bf16* __restrict__ out, int D, int t_stride, int n_keys, int hpc, int groups, int n_items,
-                            int stages, unsigned int* __restrict__ sched) {
+attention_decode_mma_kernel(int trace_id, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                            int row_base, const bf16* __restrict__ q, bf16* __restrict__ out, int D, int t_stride, int n_keys,
+                            int hpc, int groups, int n_items, int stages, unsigned int* __restrict__ sched) {
 #if defined(__CUDA_ARCH__)
   TraceScope trace_scope(trace_id);
-  extern __shared__ __align__(128) uint8_t att_smem[];
+  extern __shared__ uint8_t att_smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int slice_bytes = hpc * 128;                                // one key row of this head group
-  const int rowb = slice_bytes + 16;                                // staged row pitch
-  const int stage_bytes = 2 * ATTM_CH * rowb;                       // rows 0-7: keys, rows 8-15: their values
-  uint8_t* ring = att_smem;
+  const int tile_bytes = ATTM_CH * slice_bytes;                     // 8 keys (or values) x hpc heads x 128 B, 1 KB multiple
+  const int stage_bytes = 2 * tile_bytes;                           // K tile, then V tile
   uint8_t* qbuf = ring + stages * stage_bytes;                      // [2][slice_bytes]
   float* ostage = reinterpret_cast<float*>(qbuf + 2 * slice_bytes); // [hpc][64] output staging
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ostage + hpc * 64);
@@ -644,6 +645,8 @@ attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16
 
   if (threadIdx.x == 0) {
     phase_mark(0);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], hpc);
@@ -659,7 +662,7 @@ attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16
   pdl_launch_dependents();
 
   if (w == hpc) {
-    // ---- producer ----
+    // ---- producer: two tensor-tile loads per stage (8 keys x hpc heads, 8 values x hpc heads) ----
     if (lane == 0) {
       bool waited = false;
       int item = blockIdx.x;
@@ -668,18 +671,12 @@ attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16
         const int ip = it & 1;
         const bool have = item < n_items;
         const int b = have ? item / groups : 0, grp = have ? item % groups : 0;
-        const bf16* Kb = K + static_cast<size_t>(b) * t_stride * D + grp * hpc * 64;
-        const bf16* Vb = V + static_cast<size_t>(b) * t_stride * D + grp * hpc * 64;
+        const int row0 = row_base + b * t_stride;
         auto issue = [&](int ck, int s) {
-          const int rows = (n_keys - ck * ATTM_CH) < ATTM_CH ? (n_keys - ck * ATTM_CH) : ATTM_CH;
-          mbar_arrive_expect_tx(&full_bar[s], 2u * static_cast<uint32_t>(rows) * slice_bytes);
-          const bf16* ks = Kb + static_cast<size_t>(ck) * ATTM_CH * D;
-          const bf16* vs = Vb + static_cast<size_t>(ck) * ATTM_CH * D;
+          mbar_arrive_expect_tx(&full_bar[s], static_cast<uint32_t>(stage_bytes));   // boxes always land whole
           uint8_t* dst = ring + s * stage_bytes;
-          for (int r = 0; r < rows; ++r) {
-            bulk_load_1d(dst + r * rowb, ks + static_cast<size_t>(r) * D, slice_bytes, &full_bar[s]);
-            bulk_load_1d(dst + (ATTM_CH + r) * rowb, vs + static_cast<size_t>(r) * D, slice_bytes, &full_bar[s]);
-          }
+          tma_load_3d(dst, &tmK, &full_bar[s], 0, grp * hpc, row0 + ck * ATTM_CH);
+          tma_load_3d(dst + tile_bytes, &tmV, &full_bar[s], 0, grp * hpc, row0 + ck * ATTM_CH);
         };
         int i = 0;
         if (have && !waited) {
@@ -698,7 +695,7 @@ attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16
           break;
         }
         if (it == 0) {
-          mbar_arrive(&qfull_bar[ip]);      // first item: the consumers fetch q themselves, ahead of the queued K/V rows
+          mbar_arrive(&qfull_bar[ip]);      // first item: the consumers fetch q themselves
         } else {
           mbar_arrive_expect_tx(&qfull_bar[ip], slice_bytes);
           bulk_load_1d(qbuf + ip * slice_bytes, q + static_cast<size_t>(b) * D + grp * hpc * 64, slice_bytes, &qfull_bar[ip]);
@@ -727,10 +724,15 @@ attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16
   const int gq = lane >> 2, tq = lane & 3;          // mma fragment coordinates: row / column pair
   const int lr = lane & 7, lm = (lane >> 3) & 1;    // ldmatrix.x2: row within the matrix, matrix index (lanes 0-15)
   const uint32_t ring_u32 = smem_u32(ring);
-  // K tile (8 keys x 16 dims): matrices dims 0-7 | 8-15 -> fragments a0 | a2 (rows 8-15 of the MMA are zero)
-  const uint32_t k_off = static_cast<uint32_t>(lr * rowb + w * 128 + lm * 16);
-  // V^T tile (16 dims x 8 keys): stored blocks (8 keys) x (dims 0-7 | 8-15), transposed on load -> a0 | a1
-  const uint32_t v_off = static_cast<uint32_t>((ATTM_CH + lr) * rowb + w * 128 + lm * 16);
+  // SWIZZLE_128B tile: the 128-byte line of (key lr, head w) is line lr*hpc + w; its 16-byte chunk c sits at
+  // c ^ (line & 7).  Step j (16 dims) of this lane's matrix (dims 0-7 | 8-15 -> lm) is chunk 2j + lm.
+  // K: matrices feed fragments a0 | a2 (rows 8-15 of the MMA stay zero); V: transposed on load -> a0 | a1.
+  uint32_t frag_off[4];
+  {
+    const uint32_t line = static_cast<uint32_t>(lr * hpc + w);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) frag_off[j] = line * 128u + (((2u * j + lm) ^ (line & 7u)) << 4);
+  }
   float* orow = ostage + w * 64;
   uint32_t g = 0;
   for (int it = 0;; ++it) {
@@ -738,7 +740,6 @@ attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16
     mbar_wait(&qfull_bar[ip], (it >> 1) & 1);
     const int item = qitem[ip];
     if (item < 0) break;
-    if (it == 0 && threadIdx.x == 0) phase_mark(2);
     // q as the B operand: column 0 (lanes 0-3) holds dims 2*tq, 2*tq+1 (+8) of each 16-dim step
     uint32_t qb[4][2];
     {
@@ -751,6 +752,7 @@ attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16
         qb[ks][1] = gq == 0 ? q32[ks * 8 + 4 + tq] : 0u;
       }
     }
+    if (it == 0 && threadIdx.x == 0) phase_mark(2);
     __syncwarp();
     if (lane == 0) mbar_arrive(&qempty_bar[ip]);
 
@@ -766,17 +768,18 @@ attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16
       const int left = n_keys - c * ATTM_CH;          // valid keys in this stage (>= 1)
       mbar_wait(&full_bar[s], (g / stages) & 1);
       if (g == 0 && threadIdx.x == 0) phase_mark(3);
-      const uint32_t base = ring_u32 + s * stage_bytes;
+      const uint32_t kbase = ring_u32 + s * stage_bytes;
+      const uint32_t vbase = kbase + tile_bytes;
       // ---- scores of the 8 keys: lane (gq, tq = 0) gets key gq ----
       float sc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t a0, a2;
-        ldmatrix_x2(base + k_off + ks * 32, a0, a2);
+        ldmatrix_x2(kbase + frag_off[ks], a0, a2);
         mma_bf16_16816(sc, a0, 0u, a2, 0u, qb[ks][0], qb[ks][1]);
       }
       float sk = __shfl_sync(0xffffffffu, sc[0], lane & ~3) * 0.125f;   // every lane of quad gq: score of key gq
-      if (gq >= left) sk = -INFINITY;                                    // rows past the cache end hold stale bytes
+      if (gq >= left) sk = -INFINITY;                                    // rows past the cache end are not keys
       float cm = sk;
       cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 4));
       cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
@@ -802,7 +805,8 @@ attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16
         }
         if (gq < 2) pb = *reinterpret_cast<uint32_t*>(&h);
       }
-      // stale value rows: 0 * NaN must not reach the accumulator
+      // value rows past the cache end (other cache slots, or whatever the allocation held): 0 * NaN must not
+      // reach the accumulator
       uint32_t vmask = 0xFFFFFFFFu;
       if (left < ATTM_CH) vmask = (2 * tq < left ? 0x0000FFFFu : 0u) | (2 * tq + 1 < left ? 0xFFFF0000u : 0u);
       if (alpha != 1.0f) {
@@ -814,7 +818,7 @@ attention_decode_mma_kernel(int trace_id, const bf16* __restrict__ q, const bf16
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) {
         uint32_t a0, a1;
-        ldmatrix_x2_trans(base + v_off + mt * 32, a0, a1);
+        ldmatrix_x2_trans(vbase + frag_off[mt], a0, a1);
         mma_bf16_1688(o[mt], a0 & vmask, a1 & vmask, pb);
       }
       __syncwarp();
@@ -904,7 +908,7 @@ struct OpMaxI { __device__ int operator()(int a, int b) const { return a > b ? a
 struct OpMinI { __device__ int operator()(int a, int b) const { return a < b ? a : b; } };
 
 template <int NTHR>
-__global__ void __launch_bounds__(NTHR, NTHR == 256 ? 3 : 1) sample_kernel(int trace_id, SampleArgs a) {
+__global__ void __launch_bounds__(NTHR, NTHR == 256 ? 4 : 1) sample_kernel(int trace_id, SampleArgs a) {
   TraceScope trace_scope(trace_id);
   pdl_launch_dependents();   // programmatic dependent launch: let the next kernel get resident ...
   pdl_wait();                // ... and wait for the previous kernel's results (no-ops without the launch attribute)
@@ -947,8 +951,10 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 3 : 1) sample_kernel(int t
   }
   if (a.forced) return;
 
+  if (temperature != 1.0f) {   // z / 1 is the identity: skip 32 fp32 divisions per thread in the default protocol
 #pragma unroll
-  for (int i = 0; i < SMP_IPT; ++i) z[i] = z[i] / temperature;   // -inf padding stays -inf (T > 0)
+    for (int i = 0; i < SMP_IPT; ++i) z[i] = z[i] / temperature;   // -inf padding stays -inf (T > 0)
+  }
 
   int64_t* dst = a.flat_out != nullptr
                      ? a.flat_out + r

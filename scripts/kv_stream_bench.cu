@@ -4,7 +4,8 @@
 //   mode 0: (image, group of 6 heads) items - 768-byte pieces at a 3072-byte stride (today's cache layout), K then V
 //   mode 1: same bytes per CTA, but each item's rows contiguous (a group-major cache layout)
 //   mode 2: (image) items - 3072-byte rows, contiguous, 256 CTAs
-//   mode 3: plain coalesced 16-byte loads of the same total bytes (grid-stride), as the read-only reference
+//   mode 6: 768-byte pieces of a time-major cache [T][B][D] (a step's keys span t/64 of the pages)
+//   mode 5: plain coalesced 16-byte loads of the same total bytes (grid-stride), as the read-only reference
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/kv_stream_bench.bin scripts/kv_stream_bench.cu
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -78,7 +79,7 @@ int main() {
   for (int big = 0; big < 2; ++big)
   for (int keys : {16, 32, 64}) {
     const int Bq = big ? B * L : B;   // big: all 12 layer slabs as one launch (steady-state streaming rate)
-    for (int mode = 0; mode < 6; ++mode) {
+    for (int mode = 0; mode < 7; ++mode) {
       float best = 1e9, sum = 0;
       const int iters = 24;
       for (int it = 0; it < iters + 3; ++it) {
@@ -89,6 +90,7 @@ int main() {
         else if (mode == 2) stream_kernel<<<Bq, 64, STAGES * 8 * 3072 + 64>>>(k, v, keys, 3072, 3072, (size_t)T * 3072, 0, 1, 8, 1);
         else if (mode == 3) stream_kernel<<<Bq * 4, 64, STAGES * 16 * 768 + 64>>>(k, v, keys, 768, 3072, (size_t)T * 3072, 768, 4, 16, 0);
         else if (mode == 4) stream_kernel<<<Bq * 2, 64, STAGES * 8 * 1536 + 64>>>(k, v, keys, 1536, 3072, (size_t)T * 3072, 1536, 2, 8, 0);
+        else if (mode == 6) stream_kernel<<<Bq * 4, 64, STAGES * 8 * 768 + 64>>>(k, v, keys, 768, (size_t)Bq * 3072, 3072, 768, 4, 8, 0);
         else { ldg_kernel<<<148 * 8, 512>>>((const uint4*)k, (size_t)Bq * keys * D * 2 / 16, sink); ldg_kernel<<<148 * 8, 512>>>((const uint4*)v, (size_t)Bq * keys * D * 2 / 16, sink); }
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
@@ -96,8 +98,8 @@ int main() {
         if (it >= 3) { sum += ms; if (ms < best) best = ms; }
       }
       const double bytes = 2.0 * Bq * keys * D * 2;
-      const char* names[6] = {"768B @3072 stride, 1024 CTAs, 8-key stages", "contiguous items (group-major), 1024 CTAs, 1 copy/stage", "3072B rows, 256 CTAs, 1 copy/stage",
-                              "768B @3072 stride, 1024 CTAs, 16-key stages", "1536B @3072 stride, 512 CTAs", "coalesced LDG.128 x2 kernels"};
+      const char* names[7] = {"768B @3072 stride, 1024 CTAs, 8-key stages", "contiguous items (group-major), 1024 CTAs, 1 copy/stage", "3072B rows, 256 CTAs, 1 copy/stage",
+                              "768B @3072 stride, 1024 CTAs, 16-key stages", "1536B @3072 stride, 512 CTAs", "coalesced LDG.128 x2 kernels", "768B pieces, TIME-major cache [T][B][D], 1024 CTAs"};
       printf("B %4d keys %2d mode %d (%s): mean %.2f us min %.2f us -> %.0f GB/s (min-time %.0f)\n", Bq, keys, mode, names[mode], sum / iters * 1e3, best * 1e3,
              bytes / (sum / iters * 1e-3) * 1e-9, bytes / (best * 1e-3) * 1e-9);
     }
