@@ -794,16 +794,18 @@ static bool attn_decode_plan(const hq_ctx* ctx, int* CH, int* hpc, int* groups, 
   return *smem <= 64 * 1024;
 }
 
-// Launch plan of attention_decode_mma_kernel (bf16): stages of 8 keys + 8 values in hpc*128+16-byte rows, up to 4 of them
-// within ~52 KB so that four persistent CTAs fit an SM; grid = resident CTAs (each takes one item, then tickets),
-// capped by the number of items.
+// Launch plan of attention_decode_mma_kernel (bf16): ring stages of one 8-key K tile + one 8-value V tile (hpc KB each);
+// grid = resident CTAs (registers allow four 7-warp CTAs per SM; each takes one item, then tickets), capped by the
+// number of items.
 static int g_attn_scalar = 0;   // tests: hq_debug_attention may pin the scalar bulk-staged kernel
 static bool attn_mma_plan(const hq_ctx* ctx, int groups, int hpc, int n_items, int* stages, size_t* smem, int* grid) {
   static const bool off = getenv("HQ_ATTN_SCALAR") != nullptr;      // experiments: the scalar bulk-staged kernel
   if (off || g_attn_scalar || !ctx->bf16 || ctx->num_sms <= 0 || !ctx->kv_maps) return false;
   const size_t stage = static_cast<size_t>(2 * ATTM_CH) * hpc * 128;     // K tile + V tile
-  int st = static_cast<int>((50 * 1024) / stage);
-  if (st > 4) st = 4;
+  // Two stages (24 KB for 6 heads): measured equal end to end to a 4-deep ring and ~1 us faster per launch in the loop
+  // (profiles/r1_attn_sweep.txt) - requests beyond the bandwidth-delay product only lengthen every request's latency,
+  // and a 27 KB CTA still fits next to a resident GEMM CTA, so its prefetch can start under the QKV GEMM (PDL).
+  int st = 2;
   if (const char* f = getenv("HQ_ATTM_STAGES")) st = atoi(f);     // experiments
   if (st < 2) st = 2;
   if (st > ATTM_MAXSTAGES) st = ATTM_MAXSTAGES;
