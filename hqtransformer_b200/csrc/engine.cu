@@ -711,7 +711,7 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
     dim3 grid(2 * (tiles < 74 ? tiles : 74));               // persistent: at most one CTA pair per SM pair
 #define HQ_LAUNCH2(BN)                                                                                             \
   case BN:                                                                                                         \
-    launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc2_kernel<BN, EPI, bf16>, grid, dim3(192), Tc2Cfg<BN>::SMEM_BYTES, mA, mW16, M, N, K,  \
+    launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc2_kernel<BN, EPI, bf16>, grid, dim3(Tc2Cfg<BN>::THREADS), Tc2Cfg<BN>::SMEM_BYTES, mA, mW16, M, N, K,  \
              w_row_off, splits, ep);                                                                               \
     break;
     switch (bn) {

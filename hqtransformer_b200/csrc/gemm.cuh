@@ -92,16 +92,22 @@ __device__ __forceinline__ void epi_store8(const EpiParams<AT>& ep, int m, int n
 // complete, so the cold bias loads overlap the main loop).  The chunk loop is NOT unrolled and all index arithmetic
 // (section of the fused q/k/v columns, KV-cache row of each output row) is hoisted: the epilogue is straight-line code
 // that every warp fetches once per launch, and a decode step launches ~80 GEMMs with a cold instruction cache.
-template <int BN, int EPI, typename AT>
+// NW = 4: one warp per TMEM lane quarter (warp % 4).  NW = 8 (pair kernel): two warps per quarter, `half` = 0 / 1 taking
+// the even / odd 32-column chunks - the epilogue (tcgen05.ld, smem transpose, bias / GELU, stores) is pure per-element
+// work on the critical path of every launch, so twice the warps halve it.  `ew` = 0..NW-1 indexes the warp's slab.
+template <int BN, int EPI, typename AT, int NW = 4>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, uint8_t* slab_base, float* sbias, int warp, int lane,
                                               int m0, int n0, int M, int N, const EpiParams<AT>& ep,
-                                              uint64_t* tmem_full_bar, uint32_t full_parity = 0) {
+                                              uint64_t* tmem_full_bar, uint32_t full_parity = 0, int ew = -1) {
   const int quarter = warp & 3;
-  const int etid = quarter * 32 + lane;                        // 0..127 over the four epilogue warps
+  if (ew < 0) ew = quarter;
+  const int half = ew >> 2;
+  const int etid = ew * 32 + lane;                             // 0..NW*32-1 over the epilogue warps
   const bool has_bias = (EPI != EPI_F32) && ep.bias != nullptr;
   if (has_bias) {
-    asm volatile("bar.sync 1, 128;" ::: "memory");             // persistent kernel: previous tile's bias fully consumed
-    for (int i = etid; i < BN; i += 128) sbias[i] = (n0 + i < N) ? ep.bias[n0 + i] : 0.f;
+    // persistent kernel: previous tile's bias fully consumed
+    if (NW == 8) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int i = etid; i < BN; i += NW * 32) sbias[i] = (n0 + i < N) ? ep.bias[n0 + i] : 0.f;
   }
   // rows this lane writes: it*4 + (lane >> 3) of the warp's 32; destination row offsets (elements) per row
   const int piece = lane & 7;
@@ -122,14 +128,15 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, uint8_t* slab_
       row_b[it] = 0;
     }
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");               // sbias visible to the four epilogue warps
+  // sbias visible to all epilogue warps
+  if (NW == 8) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
   mbar_wait(tmem_full_bar, full_parity);
   tc_fence_after();
 
-  uint8_t* slab = slab_base + quarter * 4096;                  // this warp's 32 rows x 128 B
+  uint8_t* slab = slab_base + ew * 4096;                       // this warp's 32 rows x 128 B
   const uint32_t slab_u32 = smem_u32(slab);
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = (NW == 8 ? half : 0); c < BN / 32; c += (NW == 8 ? 2 : 1)) {
     uint32_t r[32];
     tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c * 32), r);
     tmem_ld_wait();
@@ -327,7 +334,8 @@ gemm_tc_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __gr
 // tcgen05.mma.cta_group::2 (M = 256, N = BN) which reads both CTAs' shared memory and accumulates rows r*128.. in CTA
 // r's TMEM.  Per SM this halves the weight bytes staged per output row, which is what bounds these GEMMs: measured
 // L2->SM ingest is ~84 GB/s per SM (profiles/r1_*), not the tensor pipe.
-//   grid = (2 * N/BN, ceil(M/256)), cluster (2,1,1); warp roles as in gemm_tc_kernel.
+//   grid = (2 * N/BN, ceil(M/256)), cluster (2,1,1); warps 0 / 1 as in gemm_tc_kernel, warps 2-9 epilogue (two per
+//   TMEM lane quarter, alternating 32-column chunks).
 // tmA: [rows_pad, K] box {64,128}; tmW: [N, K] box {64,16} (BN/32 loads per stage per CTA); both SWIZZLE_128B.
 // ------------------------------------------------------------------------------------------------
 template <int BN>
@@ -339,10 +347,12 @@ struct Tc2Cfg {
   // >= 120 KB of shared memory per CTA on purpose: at most ONE GEMM CTA is resident per SM.  With two (the next
   // kernel's CTA launched early by PDL next to the current one) tcgen05.alloc/dealloc of different CTA pairs interleave
   // on the same SM pair, and the sampling loop was seen to hang in that state (round-1 notes).
-  static constexpr int STAGES = (184320 / STAGE_BYTES) > 8 ? 8 : (184320 / STAGE_BYTES);
+  static constexpr int STAGES = (172032 / STAGE_BYTES) > 8 ? 8 : (172032 / STAGE_BYTES);
   static constexpr int ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // one accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;                                               // double buffered
-  static constexpr int SLAB_BYTES = 16384;              // epilogue staging: 4 warps x (32 rows x 128 B)
+  static constexpr int EPI_WARPS = 8;                   // two per TMEM lane quarter
+  static constexpr int THREADS = (2 + EPI_WARPS) * 32;
+  static constexpr int SLAB_BYTES = EPI_WARPS * 4096;   // epilogue staging: one 32-row x 128 B slab per warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
 };
 
@@ -360,7 +370,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
 // tile i is drained), so a GEMM with more tiles than pairs pays the fixed per-wave cost once.
 // tile index -> (split z, row block, column block), column block fastest.
 template <int BN, int EPI, typename AT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<BN>::THREADS, 1)
 gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M,
                 int N, int K, int w_row_off, int splits, EpiParams<AT> ep) {
 #if defined(__CUDA_ARCH__)
@@ -399,7 +409,7 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);    // one multicast tcgen05.commit per tile
-      mbar_init(&tmem_empty_bar[b], 8);   // 4 epilogue warps of each CTA
+      mbar_init(&tmem_empty_bar[b], 2 * C::EPI_WARPS);   // the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -490,8 +500,9 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
       const int n0 = (rem % nt) * BN;
       EpiParams<AT> ept = ep;
       if (EPI == EPI_F32) ept.outf = ep.outf + static_cast<size_t>(z) * ep.split_stride;
-      epilogue_tile<BN, EPI, AT>(tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS), slab, sbias, warp, lane, m0, n0, M, N,
-                                 ept, &tmem_full_bar[buf], (it >> 1) & 1);
+      epilogue_tile<BN, EPI, AT, C::EPI_WARPS>(tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS), slab, sbias, warp, lane, m0,
+                                               n0, M, N, ept, &tmem_full_bar[buf], (it >> 1) & 1,
+                                               (warp & 3) + ((warp - 2) >> 2) * 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[buf], 0);   // this warp is done with the accumulator
