@@ -40,11 +40,19 @@ static void set_err(hq_ctx* ctx, const char* fmt, ...);
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+// One tensor map per CTA-pair tile width: each CTA of a pair stages BN/2 weight rows per k-block with ONE TMA
+// instruction (a TMA issue costs ~40 ns in the producer thread; 16-row boxes made a 256-wide tile issue-bound).
+struct PairMaps {
+  CUtensorMap m[6];
+  static int index(int bn) { return bn == 32 ? 0 : bn == 64 ? 1 : bn == 96 ? 2 : bn == 128 ? 3 : bn == 192 ? 4 : bn == 256 ? 5 : -1; }
+  static int width(int i) { static const int w[6] = {32, 64, 96, 128, 192, 256}; return w[i]; }
+};
+
 struct Weight {          // a GEMM weight [N, K] in the precision's storage type
   void* ptr = nullptr;
   int N = 0, K = 0;
   CUtensorMap map;       // bf16 only: [N, K], box {64, 64}, SWIZZLE_128B (single-CTA kernel)
-  CUtensorMap map16;     // bf16 only: box {64, 16} (CTA-pair kernel: BN/32 loads per stage per CTA)
+  PairMaps mapp;         // bf16 only: box {64, BN/2} per pair-tile width BN (CTA-pair kernel: one load per stage per CTA)
 };
 struct ABuf {            // a GEMM A operand buffer [rows_pad, K]
   void* ptr = nullptr;
@@ -165,6 +173,16 @@ static int make_map(hq_ctx* ctx, CUtensorMap* m, void* base, uint64_t rows, uint
   return HQ_OK;
 }
 
+static int make_pair_maps(hq_ctx* ctx, PairMaps* pm, void* base, uint64_t rows, uint64_t cols) {
+  memset(pm, 0, sizeof(*pm));
+  for (int i = 0; i < 6; ++i) {
+    if (static_cast<uint64_t>(PairMaps::width(i)) > rows) continue;   // a tile wider than the matrix is never launched
+    int rc = make_map(ctx, &pm->m[i], base, rows, cols, static_cast<uint32_t>(PairMaps::width(i) / 2));
+    if (rc) return rc;
+  }
+  return HQ_OK;
+}
+
 // KV cache rows as a 3-D tensor {64 dims, n_heads, rows}: one box = 8 cache rows of one head group (hpc heads)
 static int make_kv_map(hq_ctx* ctx, CUtensorMap* m, const void* base, int n_heads, uint64_t rows, int hpc) {
   cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(n_heads), rows};
@@ -189,7 +207,7 @@ static int alloc_weight(hq_ctx* ctx, Weight* w, int N, int K) {
   if (rc) return rc;
   if (ctx->bf16) {
     if ((rc = make_map(ctx, &w->map, w->ptr, N, K, 64))) return rc;
-    return make_map(ctx, &w->map16, w->ptr, N, K, 16);
+    return make_pair_maps(ctx, &w->mapp, w->ptr, N, K);
   }
   return HQ_OK;
 }
@@ -697,7 +715,7 @@ static int g_force_bn = 0;   // tests: hq_debug_gemm may pin the tile width (0 =
 
 template <int EPI>
 static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mW64,
-                      const CUtensorMap& mW16, int w_row_off, int M, int N, int K, const EpiParams<bf16>& ep,
+                      const PairMaps& mWp, int w_row_off, int M, int N, int K, const EpiParams<bf16>& ep,
                       int splits = 1, int bn_hint = 0) {
   int bn = g_force_bn ? g_force_bn : bn_hint;
   if (bn == 0) bn = (M > 128) ? pick_pair_bn(M, N, K) : 0;
@@ -711,7 +729,7 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
     dim3 grid(2 * (tiles < 74 ? tiles : 74));               // persistent: at most one CTA pair per SM pair
 #define HQ_LAUNCH2(BN)                                                                                             \
   case BN:                                                                                                         \
-    launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc2_kernel<BN, EPI, bf16>, grid, dim3(Tc2Cfg<BN>::THREADS), Tc2Cfg<BN>::SMEM_BYTES, mA, mW16, M, N, K,  \
+    launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc2_kernel<BN, EPI, bf16>, grid, dim3(Tc2Cfg<BN>::THREADS), Tc2Cfg<BN>::SMEM_BYTES, mA, mWp.m[PairMaps::index(BN)], M, N, K,  \
              w_row_off, splits, ep);                                                                               \
     break;
     switch (bn) {
@@ -744,7 +762,7 @@ static void gemm_f32(hq_ctx* ctx, cudaStream_t st, const float* A, const float* 
 template <int EPI>
 static void gemm_any(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
                      const EpiParams<bf16>& ep) {
-  gemm_bf16<EPI>(ctx, st, A.map, W.map, W.map16, w_row_off, M, N, K, ep);
+  gemm_bf16<EPI>(ctx, st, A.map, W.map, W.mapp, w_row_off, M, N, K, ep);
 }
 template <int EPI>
 static void gemm_any(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
@@ -883,7 +901,7 @@ static void gemm_fc2_split(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const We
   EpiParams<bf16> e;
   memset(&e, 0, sizeof(e));
   e.outf = ctx->splitk_ws; e.ldo = N; e.split_stride = static_cast<size_t>(ctx->ws_rows) * N;
-  gemm_bf16<EPI_F32>(ctx, st, A.map, W.map, W.map16, 0, M, N, K, e, splits, bn);
+  gemm_bf16<EPI_F32>(ctx, st, A.map, W.map, W.mapp, 0, M, N, K, e, splits, bn);
 }
 static void gemm_fc2_split(hq_ctx*, cudaStream_t, const ABuf&, const Weight&, int, int, int, int, int, float*) {}
 
@@ -1272,16 +1290,17 @@ extern "C" int hq_debug_gemm(int prec, const void* A, const void* W, float* C, i
       cudaMemsetAsync(Ap, 0, static_cast<size_t>(Mp) * K * 2, st);
       cudaMemcpyAsync(Ap, A, static_cast<size_t>(M) * K * 2, cudaMemcpyDeviceToDevice, st);
     }
-    CUtensorMap mA, mW, mW16;
+    CUtensorMap mA, mW;
+    PairMaps mWp;
     if (rc == HQ_OK) rc = make_map(&tmp, &mA, Ap, Mp, K, 128);
     if (rc == HQ_OK) rc = make_map(&tmp, &mW, const_cast<void*>(W), N, K, 64);
-    if (rc == HQ_OK) rc = make_map(&tmp, &mW16, const_cast<void*>(W), N, K, 16);
+    if (rc == HQ_OK) rc = make_pair_maps(&tmp, &mWp, const_cast<void*>(W), N, K);
     if (rc == HQ_OK) {
       EpiParams<bf16> e;
       memset(&e, 0, sizeof(e));
       e.outf = C; e.ldo = N;
       g_force_bn = tile;
-      gemm_bf16<EPI_F32>(&tmp, st, mA, mW, mW16, 0, M, N, K, e);
+      gemm_bf16<EPI_F32>(&tmp, st, mA, mW, mWp, 0, M, N, K, e);
       g_force_bn = 0;
     }
     cudaError_t se = cudaStreamSynchronize(st);
@@ -1559,11 +1578,12 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
   cudaMemsetAsync(W, 0, wbytes * copies, st);
   cudaMemsetAsync(flushbuf, 1, flush_bytes, st);
   CUtensorMap mA;
-  std::vector<CUtensorMap> mW(copies), mW16(copies);
+  std::vector<CUtensorMap> mW(copies);
+  std::vector<PairMaps> mWp(copies);
   rc = make_map(&tmp, &mA, A, Mp, K, 128);
   for (int c = 0; rc == HQ_OK && c < copies; ++c) {
     rc = make_map(&tmp, &mW[c], static_cast<char*>(W) + wbytes * c, N, K, 64);
-    if (rc == HQ_OK) rc = make_map(&tmp, &mW16[c], static_cast<char*>(W) + wbytes * c, N, K, 16);
+    if (rc == HQ_OK) rc = make_pair_maps(&tmp, &mWp[c], static_cast<char*>(W) + wbytes * c, N, K);
   }
   std::vector<cudaEvent_t> ev(2 * iters);
   for (auto& e : ev) cudaEventCreate(&e);
@@ -1577,7 +1597,7 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
       if (flush == 1) cudaMemsetAsync(flushbuf, i & 0xff, flush_bytes, st);
       if (flush == 2) read_sweep_kernel<<<1184, 256, 0, st>>>(static_cast<const uint4*>(flushbuf), flush_bytes / 16, sink);
       if (i >= 0) cudaEventRecord(ev[2 * i], st);
-      gemm_bf16<EPI_F32>(&tmp, st, mA, mW[c], mW16[c], 0, M, N, K, e, splits);
+      gemm_bf16<EPI_F32>(&tmp, st, mA, mW[c], mWp[c], 0, M, N, K, e, splits);
       if (i >= 0) cudaEventRecord(ev[2 * i + 1], st);
     }
     g_force_bn = 0;

@@ -336,7 +336,8 @@ gemm_tc_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __gr
 // L2->SM ingest is ~84 GB/s per SM (profiles/r1_*), not the tensor pipe.
 //   grid = (2 * N/BN, ceil(M/256)), cluster (2,1,1); warps 0 / 1 as in gemm_tc_kernel, warps 2-9 epilogue (two per
 //   TMEM lane quarter, alternating 32-column chunks).
-// tmA: [rows_pad, K] box {64,128}; tmW: [N, K] box {64,16} (BN/32 loads per stage per CTA); both SWIZZLE_128B.
+// tmA: [rows_pad, K] box {64,128}; tmW: [N, K] box {64, BN/2} (this CTA's half of the W tile, one load per stage); both
+// SWIZZLE_128B.
 // ------------------------------------------------------------------------------------------------
 template <int BN>
 struct Tc2Cfg {
@@ -442,9 +443,7 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
           const int pre = num_kb < C::STAGES ? num_kb : C::STAGES;
           for (; kb < pre; ++kb) {
             if (leader) mbar_arrive_expect_tx(&full_bar[kb], 2 * C::STAGE_BYTES);
-#pragma unroll
-            for (int j = 0; j < BN / 32; ++j)
-              tma_load_2d_2sm(sB + kb * C::B_BYTES + j * (16 * 128), &tmW, &full_bar[kb], (kb0 + kb) * C::BK, wrow + j * 16);
+            tma_load_2d_2sm(sB + kb * C::B_BYTES, &tmW, &full_bar[kb], (kb0 + kb) * C::BK, wrow);
           }
           pdl_wait();
           for (int k2 = 0; k2 < pre; ++k2)
@@ -457,9 +456,7 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
           mbar_wait(&empty_bar[s], ph ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
           tma_load_2d_2sm(sA + s * C::A_BYTES, &tmA, &full_bar[s], (kb0 + kb) * C::BK, m0);
-#pragma unroll
-          for (int j = 0; j < BN / 32; ++j)
-            tma_load_2d_2sm(sB + s * C::B_BYTES + j * (16 * 128), &tmW, &full_bar[s], (kb0 + kb) * C::BK, wrow + j * 16);
+          tma_load_2d_2sm(sB + s * C::B_BYTES, &tmW, &full_bar[s], (kb0 + kb) * C::BK, wrow);
         }
       }
     }
