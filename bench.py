@@ -338,11 +338,13 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
                 att_us = sum(r["us_per_position"] for r in att)
                 a_bytes = sum(r["bytes"] * r["launches_per_position"] for r in att)
                 line["roofline_attention"] = {
-                    "bound": "hbm", "kernel": "attention_decode_kernel", "achieved": a_bytes / att_us * 1e-3,
+                    "bound": "hbm", "kernel": "attention_decode_mma_kernel", "achieved": a_bytes / att_us * 1e-3,
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a_bytes / att_us * 1e-3 / peaks["hbm_gbs"],
                     "traffic": traffic.get("attention_decode:t64:B256", {}).get("dram_bytes"),
-                    "traffic_note": "ncu capture at 64 keys (100.3 MB DRAM vs 100.7 MB algorithmic); timed launches here have "
-                                    + str(sorted(set(r["keys"] for r in att))) + " keys",
+                    "traffic_note": "ncu capture at 64 keys (DRAM bytes vs 100.7 MB algorithmic); timed launches here have "
+                                    + str(sorted(set(r["keys"] for r in att))) + " keys; a pure streaming kernel of the same "
+                                    "access pattern and size (scripts/kv_stream_bench.cu, profiles/r1_kv_stream_bench.txt) needs "
+                                    "about the same time: a cold 50 MB launch cannot reach the long-copy peak",
                     "share_of_step": att_us / span_us}
             line["kernels"] = [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()
                                 if k not in ("flops", "bytes")} for r in sorted(rows, key=lambda r: -r["us_per_position"])]

@@ -878,6 +878,13 @@ static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, co
     return;
   }
   const int items = M * ctx->nh;
+  if (!causal && kbase <= ATT_DEPTH_KEYS && Tq == 4 && getenv("HQ_ATTN_FEWKEYS_OLD") == nullptr) {
+    // the parallel depth pass: one warp per (image, head) serves the image's four queries
+    const int warps = (M / 4) * ctx->nh;
+    launch_k(ctx, st, "attention_depth4", attention_depth4_kernel<AT>, dim3((warps + ATT_WARPS - 1) / ATT_WARPS),
+             dim3(ATT_WARPS * 32), 0, q, K, V, out, M / 4, ctx->nh, ctx->D, t_stride, kbase);
+    return;
+  }
   if (!causal && kbase <= 8) {
     launch_k(ctx, st, "attention_fewkeys", attention_fewkeys_kernel<AT>, dim3((items + ATT_WARPS - 1) / ATT_WARPS),
              dim3(ATT_WARPS * 32), 0, q, K, V, out, M, ctx->nh, ctx->D, Tq, t_stride, kbase);

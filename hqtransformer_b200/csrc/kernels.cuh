@@ -410,6 +410,102 @@ attention_fewkeys_kernel(int trace_id, const AT* __restrict__ q, const AT* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// K5c: the parallel depth pass proper - FOUR queries of one image over its <= 5 depth keys (5 in the reference:
+// the pass-0 token and the four pass-1 tokens, no mask; hierarchical_ar.py:696-710).  One warp per (image, head):
+// lane = (query g, 16-byte piece c).  Keys and values are fetched once for all four queries (the four lane groups
+// read the same addresses: one L1 transaction each), every load of a lane - its q piece, n_keys key pieces, n_keys value
+// pieces - is issued before anything is used (one memory round trip), and each lane owns one 16-byte piece of one
+// output row, so the value pass needs no cross-lane reduction.
+// ------------------------------------------------------------------------------------------------
+// 8 consecutive activations kept as loaded (bf16: one 16-byte register quad) until they are used
+template <typename AT> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const bf16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float (&o)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      o[2 * i] = f.x;
+      o[2 * i + 1] = f.y;
+    }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void get(float (&o)[8]) const {
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+};
+
+constexpr int ATT_DEPTH_KEYS = 5;   // slots of the depth KV cache: the pass-0 token + the four pass-1 tokens
+
+template <typename AT>
+__global__ void __launch_bounds__(ATT_WARPS * 32, 3)
+attention_depth4_kernel(int trace_id, const AT* __restrict__ q, const AT* __restrict__ K, const AT* __restrict__ V,
+                        AT* __restrict__ out, int B, int n_heads, int D, int t_stride, int n_keys) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * ATT_WARPS + w;
+  if (item >= B * n_heads) return;
+  const int b = item / n_heads, h = item % n_heads;
+  const int g = lane >> 3, c = lane & 7;
+  const size_t qoff = (static_cast<size_t>(b) * 4 + g) * D + h * 64 + c * 8;
+  const size_t kbase = static_cast<size_t>(b) * t_stride * D + h * 64 + c * 8;
+  Raw8<AT> qr, kr[ATT_DEPTH_KEYS], vr[ATT_DEPTH_KEYS];
+  qr.load(q + qoff);
+#pragma unroll
+  for (int t = 0; t < ATT_DEPTH_KEYS; ++t) {
+    const int tc = t < n_keys ? t : 0;               // clamped: loads are unconditional, surplus keys masked below
+    kr[t].load(K + kbase + static_cast<size_t>(tc) * D);
+    vr[t].load(V + kbase + static_cast<size_t>(tc) * D);
+  }
+  float qv[8];
+  qr.get(qv);
+  float s[ATT_DEPTH_KEYS];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < ATT_DEPTH_KEYS; ++t) {
+    float kv[8];
+    kr[t].get(kv);
+    float d = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d = fmaf(qv[e], kv[e] * 0.125f, d);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    s[t] = t < n_keys ? d : -INFINITY;
+    mx = fmaxf(mx, s[t]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < ATT_DEPTH_KEYS; ++t) {
+    s[t] = t < n_keys ? expf(s[t] - mx) : 0.f;
+    sum += s[t];
+  }
+  const float inv = 1.0f / sum;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+  for (int t = 0; t < ATT_DEPTH_KEYS; ++t) {
+    float vv[8];
+    vr[t].get(vv);
+    const float p = s[t] * inv;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vv[e], acc[e]);
+  }
+  store8(out + qoff, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5a: single-query attention over the spatial KV cache - the bandwidth-bound kernel of the loop.
 // One CTA per (batch row, head group): grid = B * G CTAs, HPC = n_heads / G heads (= consumer warps) each, so that
 // the ~1000 small CTAs balance over the 148 SMs (one CTA per image left 40 SMs with half the work of the others).

@@ -6,4 +6,4 @@ show='
 import json,sys
 d=json.loads(sys.stdin.read()); print(d["value"], d["ms_per_top_position"], d["gpu_launches"])
 for k in d.get("kernels", []): print("   ", k["kernel"], k["launches_per_position"], k["us"])'
-echo "=== bench"; timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | tee gpurun_out/bench_wmap.json | python -c "$show"
+echo "=== bench"; timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | tee gpurun_out/bench_depth4.json | python -c "$show"

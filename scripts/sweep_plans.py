@@ -20,5 +20,5 @@ if len(sys.argv) > 1:
             mean, mn = bench_gemm_shape(M, N, K, tile, 12, 2, 1)
             print(f"{M}x{N}x{K} s{s} tile {tile:3d} pairs {pairs:3d}: mean {mean:6.2f} min {mn:6.2f}", flush=True)
 else:
-    for s in ("1", "2", "3"):
+    for s in ("1", "2", "3", "4", "6"):
         subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, HQ_BENCH_SPLITS=s))
