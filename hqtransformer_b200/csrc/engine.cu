@@ -912,31 +912,56 @@ static void gemm_fc2_split(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const We
 }
 static void gemm_fc2_split(hq_ctx*, cudaStream_t, const ABuf&, const Weight&, int, int, int, int, int, float*) {}
 
-// Tile width and split-K factor for the fc2 GEMM ([M, D] = [M, 4D] x [D, 4D]^T).  Its K = 4D main loop is the longest
-// serial chain of a block while its D-wide output fills few CTA pairs, so when the pair grid leaves SMs idle the K
-// range is cut in up to LN_MAXFOLD slices; the slices write fp32 partial sums that the next LayerNorm adds in a fixed
-// order (deterministic).  Same cost model as pick_pair_bn.
+// Residual GEMMs (proj [D, D], fc2 [D, 4D]): the narrowest outputs of a block (few CTA pairs) and, for fc2, the longest
+// serial K loop.  The K range is cut in up to LN_MAXFOLD slices; the slices write fp32 partial sums that the next
+// LayerNorm adds in a fixed order (deterministic).  Same cost model as pick_pair_bn.
 struct Fc2Plan { int bn, splits; };
-static Fc2Plan pick_resid_plan(const hq_ctx* ctx, int M, int N, int K) {
-  Fc2Plan best{0, 1};
-  if (!ctx->bf16 || M <= 128 || getenv("HQ_NO_SPLITK") != nullptr) return best;
+
+// Split factor of a residual GEMM as a function of its weight shape and of the call site's rows per image (1: spatial
+// step / depth pass 0, 4: depth pass 1, T0: text prefill) only - the cost model evaluated at the reference batch of 256
+// images, never at the actual batch.  The K slices and the order in which the LayerNorm adds their partial sums fix how
+// every output element is rounded; tile widths and kernels (pair / single CTA) do not.  A split that does not depend on
+// the batch therefore makes a row's result independent of the batch it sits in - and of how a batch is sharded over GPUs.
+static int resid_splits(int N, int K, int rows_per_image) {
   static const int cand[6] = {256, 192, 128, 96, 64, 32};
-  const int kb = K / 64;
-  if (const char* f = getenv("HQ_FORCE_SPLITK")) {       // tests: pin the split factor (tile width 64)
-    const int s = atoi(f);
-    if (s >= 1 && s <= LN_MAXFOLD && kb % s == 0 && N % 64 == 0) return Fc2Plan{64, s};
-  }
   static const int max_splits = getenv("HQ_MAX_SPLITK") ? atoi(getenv("HQ_MAX_SPLITK")) : LN_MAXFOLD;
+  const int kb = K / 64;
+  int best = 1;
   double best_cost = 1e30;
   for (int bn : cand) {
     if (N % bn != 0) continue;
-    for (int s = 1; s <= max_splits; ++s) {
+    for (int s = 1; s <= max_splits && s <= LN_MAXFOLD; ++s) {
       if (kb % s != 0) continue;
-      const double cost = pair_gemm_cost(M, N, K, bn, s);
+      const double cost = pair_gemm_cost(256 * (rows_per_image < 1 ? 1 : rows_per_image), N, K, bn, s);
       if (cost < best_cost) {
         best_cost = cost;
-        best = Fc2Plan{bn, s};
+        best = s;
       }
+    }
+  }
+  return best;
+}
+
+// Tile width for this M given the split (bn = 0: the single-CTA kernel, M <= 128, K slices on grid.z).
+static Fc2Plan pick_resid_plan(const hq_ctx* ctx, int M, int N, int K, int rows_per_image) {
+  Fc2Plan best{0, 1};
+  if (!ctx->bf16 || N % 64 != 0 || K % 64 != 0 || getenv("HQ_NO_SPLITK") != nullptr) return best;
+  static const int cand[6] = {256, 192, 128, 96, 64, 32};
+  const int kb = K / 64;
+  int s = resid_splits(N, K, rows_per_image);
+  if (const char* f = getenv("HQ_FORCE_SPLITK")) {       // tests: pin the split factor
+    const int v = atoi(f);
+    if (v >= 1 && v <= LN_MAXFOLD && kb % v == 0) s = v;
+  }
+  best.splits = s;
+  if (M <= 128) return best;
+  double best_cost = 1e30;
+  for (int bn : cand) {
+    if (N % bn != 0) continue;
+    const double cost = pair_gemm_cost(M, N, K, bn, s);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best.bn = bn;
     }
   }
   return best;
@@ -946,8 +971,8 @@ static Fc2Plan pick_resid_plan(const hq_ctx* ctx, int M, int N, int K) {
 // residual stream folds in; `fold` carries that pending state to the LayerNorm launch.
 template <typename AT>
 static void gemm_resid(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, const float* bias, float* x, int M,
-                       int N, int K, Fold* fold) {
-  const Fc2Plan plan = pick_resid_plan(ctx, M, N, K);
+                       int N, int K, int rows_per_image, Fold* fold) {
+  const Fc2Plan plan = pick_resid_plan(ctx, M, N, K, rows_per_image);
   if (plan.splits > 1 && M <= ctx->ws_rows) {
     gemm_fc2_split(ctx, st, A, W, M, N, K, plan.splits, plan.bn, static_cast<AT*>(nullptr));
     fold->partial = ctx->splitk_ws;
@@ -982,13 +1007,13 @@ static void run_block(hq_ctx* ctx, cudaStream_t st, const BlockW& w, float* x, i
     gemm_any<EPI_QKV>(ctx, st, ctx->h, w.qkv, 0, M, 3 * D, D, ep);
     attention<AT>(ctx, st, q, kdst, vdst, att, M, rpb, t_stride, n_keys_base, causal);
   }
-  gemm_resid<AT>(ctx, st, ctx->att, w.proj, w.bproj, x, M, D, D, fold);
+  gemm_resid<AT>(ctx, st, ctx->att, w.proj, w.bproj, x, M, D, D, rpb, fold);
   layernorm_act<AT>(ctx, st, x, w.ln2g, w.ln2b, h, M, fold);
   EpiParams<AT> eg;
   memset(&eg, 0, sizeof(eg));
   eg.bias = w.b1; eg.out = mlp;
   gemm_any<EPI_GELU>(ctx, st, ctx->h, w.fc1, 0, M, 4 * D, D, eg);
-  gemm_resid<AT>(ctx, st, ctx->mlp, w.fc2, w.b2, x, M, D, 4 * D, fold);
+  gemm_resid<AT>(ctx, st, ctx->mlp, w.fc2, w.b2, x, M, D, 4 * D, rpb, fold);
 }
 
 struct RunFlags {

@@ -93,6 +93,28 @@ def test_bf16_sampling_is_deterministic_and_launch_mode_invariant(graph, pdl):
         assert torch.equal(ct, ct0) and torch.equal(cb, cb0)
 
 
+@pytest.mark.parametrize("cuts", [(0, 19, 37), (0, 1, 36, 37), (0, 150, 300)])
+def test_bf16_results_do_not_depend_on_how_the_batch_is_cut(cuts):
+    """A row's codes are a function of (weights, its conditioning, seed, GLOBAL row index) only: sampling the batch in
+    one call equals sampling it shard by shard (what `sampling_ihqgpt_sharded` does across GPUs), bit for bit, greedy
+    and stochastic, although the shards run other GEMM kernels (single CTA for <= 128 rows, CTA pairs above).  Holds
+    because the split-K factor of the residual GEMMs depends on the weight shape only (engine.cu: resid_splits)."""
+    import hqtransformer_b200 as H
+    cfg = O.SMALL
+    P = O.make_params(cfg, seed=5, init="rich")
+    B = cuts[-1]
+    g = torch.Generator().manual_seed(0)
+    labels = torch.randint(0, cfg.n_classes, (B,), generator=g).cuda()
+    model = build_model(cfg, P, precision="bf16", max_batch=B, max_seq_len=16)
+    for kw in (dict(top_k_top=1, top_k_bot=1),
+               dict(top_k_top=50, top_p_top=0.9, top_k_bot=50, top_p_bot=0.9, softmax_temperature=[0.9, 0.9])):
+        ct, cb = H.sampling_ihqgpt(model, B, labels, max_seq_len=16, is_tqdm=False, use_fp16=True, seed=3, **kw)
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            ct_s, cb_s = H.sampling_ihqgpt(model, hi - lo, labels[lo:hi], max_seq_len=16, is_tqdm=False, use_fp16=True,
+                                           seed=3, row_offset=lo, **kw)
+            assert torch.equal(ct_s, ct[lo:hi]) and torch.equal(cb_s, cb[lo:hi]), (lo, hi, kw)
+
+
 @pytest.mark.parametrize("B,force_split", [(40, None), (150, None), (40, "2"), (150, "2")])
 def test_step_logits_bf16_wide_batch_vs_oracle(B, force_split, monkeypatch):
     """Batches wide enough to take the CTA-pair GEMM kernel (M > 128) and the split-K fc2 + LayerNorm fold path;
