@@ -116,3 +116,27 @@ def test_graft_entry_build_is_idempotent():
     import __graft_entry__ as G
     G.build()
     assert os.path.isfile(os.path.join(ROOT, "hqtransformer_b200", "libhqgraft.so"))
+
+
+def test_committed_bench_evidence_carries_the_contract_keys():
+    """profiles/r1_bench_B256.json is the bench line the docs quote: it must hold every key of the bench contract
+    (roofline with achieved / peak / frac / traffic for the dominant kernel, cpu_baseline, e2e with copy sizes, clocks,
+    launch count), with internally consistent numbers."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, "profiles", "r1_bench_B256.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+              "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "images_per_sec_sampled_256x256" and d["unit"] == "images/s" and d["n_gpus"] == 1
+    assert d["warmup"] >= 3 and d["config"]["batch_per_gpu"] == 256 and "workload" in d["config"]
+    assert abs(d["value"] - 256 * d["steps"] / (d["ms_per_step"] * d["steps"] * 1e-3)) < 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 256 * 64 * 5 * 8
+    assert d["gpu_launches"] == d["steps"] * 64 * 145
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    ra = d["roofline_attention"]
+    assert ra["bound"] == "hbm" and abs(ra["frac"] - ra["achieved"] / ra["peak"]) < 1e-9
