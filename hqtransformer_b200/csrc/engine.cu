@@ -130,6 +130,7 @@ struct hq_ctx {
   bool tracing = false;
   int trace_cap = 0;
   std::vector<std::string> trace_tags;
+  bool full_dependency_next = false;   // the next launch is an ordinary (complete-then-start) dependency even under PDL
   std::string tag_suffix;   // shape annotation appended to the next launch tag (tracing only)
 };
 
@@ -649,7 +650,8 @@ static void launch_k(hq_ctx* ctx, cudaStream_t st, const char* tag, void (*kerne
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+  cfg.numAttrs = (ctx->use_pdl && !ctx->full_dependency_next) ? 1 : 0;
+  ctx->full_dependency_next = false;
   // experiments only: HQ_ABLATE=tag[,tag...] drops every launch whose tag starts with one of the names, to read a
   // kernel family's MARGINAL cost in the PDL-overlapped loop off the step time (results are garbage, timing is not)
   static const char* ablate = getenv("HQ_ABLATE");
@@ -790,6 +792,13 @@ static void layernorm_act(hq_ctx* ctx, cudaStream_t st, float* x, const float* g
   if (fold) *fold = Fold();
 }
 
+// May the decode attention request cached keys BEFORE griddepcontrol.wait?  Yes: run_position orders positions with a
+// full dependency, so every earlier position's keys are in place.  (HQ_ATTN_NO_PREFETCH: experiment switch.)
+static bool attn_prefetch_ok(const hq_ctx* ctx) {
+  (void)ctx;
+  return getenv("HQ_ATTN_NO_PREFETCH") == nullptr;
+}
+
 static int attn_sleep_ns() {
   static const int v = getenv("HQ_ATTN_SLEEP") ? atoi(getenv("HQ_ATTN_SLEEP")) : 0;
   return v;
@@ -853,7 +862,8 @@ void launch_attn_mma<bf16>(hq_ctx* ctx, cudaStream_t st, const bf16* q, const bf
   // K (and V, at the same offset in its own cache) as a row offset into the cache-wide tensor maps
   const int row_base = static_cast<int>((K - static_cast<const bf16*>(ctx->kc)) / ctx->D);
   launch_k(ctx, st, "attention_decode", attention_decode_mma_kernel, dim3(grid), dim3((hpc + 1) * 32), smem, ctx->kmap, ctx->vmap,
-           row_base, q, out, ctx->D, t_stride, n_keys, hpc, groups, n_items, stages, ctx->att_sched);
+           row_base, q, out, ctx->D, t_stride, n_keys, hpc, groups, n_items, attn_prefetch_ok(ctx) ? stages : -stages,
+           ctx->att_sched);
 }
 
 template <typename AT>
@@ -874,7 +884,7 @@ static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, co
       return;
     }
     launch_k(ctx, st, "attention_decode", attention_decode_kernel<AT>, dim3(M * groups), dim3((hpc + 1) * 32), smem, q, K, V,
-             out, ctx->D, t_stride, kbase, CH, hpc, groups, attn_sleep_ns());
+             out, ctx->D, t_stride, kbase, CH, hpc, groups, attn_prefetch_ok(ctx) ? attn_sleep_ns() : -1);
     return;
   }
   const int items = M * ctx->nh;
@@ -1040,6 +1050,13 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
   const int eb = (D / 4 + 31) / 32 * 32 > 1024 ? 1024 : (D / 4 + 31) / 32 * 32;
   Fold fold_x, fold_y;   // split-K partial sums pending on the spatial / depth residual stream
   // ---- K1: input token(s) ----
+  // The first kernel of a position is NOT a programmatic dependent: it starts only when the previous position has
+  // completed.  Programmatic launches cascade - kernel N+1 may become resident as soon as N has started, N+2 as soon as
+  // N+1 has, ... - and with small models (a few CTAs per kernel, < 128 launches per position) the hardware keeps a whole
+  // position of not-yet-run kernels resident.  The decode attention requests the keys of EARLIER positions before its
+  // griddepcontrol.wait; a barrier per position is what makes "earlier positions are complete" true.  (Found by the
+  // asymmetric golden: without it a second run read the previous run's keys, graph + PDL only.)  Cost: ~1 us per position.
+  ctx->full_dependency_next = true;
   if (prefill) {
     launch_k(ctx, st, "embed_txt", embed_txt_kernel, dim3(M), dim3(eb), 0, ctx->x, f.sos_override ? ctx->sos_override : nullptr,
              ctx->cond, ctx->E_txt, ctx->P_txt, T0, D);

@@ -559,6 +559,11 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
       const AT* Kb = K + static_cast<size_t>(b) * t_stride * D + h0 * 64;
       const AT* Vb = V + static_cast<size_t>(b) * t_stride * D + h0 * 64;
       bool waited = false;
+      if (sleep_ns < 0) {        // no prefetch ahead of griddepcontrol.wait
+        pdl_wait();
+        waited = true;
+        sleep_ns = 0;
+      }
       for (int i = 0; i < 2 * nck; ++i) {
         const int s = i % ATTD_STAGES;
         const uint32_t ph = (i / ATTD_STAGES) & 1;
@@ -583,6 +588,7 @@ attention_decode_kernel(int trace_id, const AT* __restrict__ q, const AT* __rest
 
   // ---- consumers: warp w owns head h0 + w ----
   pdl_wait();
+  if (sleep_ns < 0) sleep_ns = 0;
   const int g = lane >> 3, c = lane & 7;
   const int h = h0 + w;
   float qv[8];
@@ -724,6 +730,8 @@ attention_decode_mma_kernel(int trace_id, const __grid_constant__ CUtensorMap tm
                             int hpc, int groups, int n_items, int stages, unsigned int* __restrict__ sched) {
 #if defined(__CUDA_ARCH__)
   TraceScope trace_scope(trace_id);
+  const bool prefetch = stages > 0;      // stages < 0: no tile load ahead of griddepcontrol.wait
+  if (stages < 0) stages = -stages;
   extern __shared__ uint8_t att_smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int slice_bytes = hpc * 128;                                // one key row of this head group
@@ -738,7 +746,6 @@ attention_decode_mma_kernel(int trace_id, const __grid_constant__ CUtensorMap tm
   int* qitem = reinterpret_cast<int*>(qempty_bar + 2);              // [2] item id that goes with qbuf[i]; -1 = no more
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nck = (n_keys + ATTM_CH - 1) / ATTM_CH;
-
   if (threadIdx.x == 0) {
     phase_mark(0);
     tma_prefetch_desc(&tmK);
@@ -775,7 +782,7 @@ attention_decode_mma_kernel(int trace_id, const __grid_constant__ CUtensorMap tm
           tma_load_3d(dst + tile_bytes, &tmV, &full_bar[s], 0, grp * hpc, row0 + ck * ATTM_CH);
         };
         int i = 0;
-        if (have && !waited) {
+        if (have && !waited && prefetch) {
           // every key but the newest was written by earlier launches: those stages do not wait for the QKV GEMM
           for (; i < nck - 1 && i < stages; ++i, ++g) issue(i, g % stages);
         }

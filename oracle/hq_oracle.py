@@ -68,6 +68,10 @@ SMALL = HQConfig(embed_dim=256, n_heads=4, n_layers=4, n_layers_depth=4, vocab_t
                  vocab_txt=512, n_classes=10, ctx_len_img=64, ctx_len_txt=64)
 TINY = HQConfig(embed_dim=128, n_heads=2, n_layers=2, n_layers_depth=2, vocab_top=256, vocab_bot=256,
                 vocab_txt=128, n_classes=10, ctx_len_img=64, ctx_len_txt=64)
+# nothing symmetric: spatial depth != depth-transformer depth (hparams_dec given explicitly, as in the L42 yaml),
+# top vocabulary != bottom vocabulary, 6 heads (2 per attention work item)
+ASYM = HQConfig(embed_dim=384, n_heads=6, n_layers=3, n_layers_depth=2, vocab_top=512, vocab_bot=768,
+                vocab_txt=128, n_classes=7, ctx_len_img=64, ctx_len_txt=64)
 
 
 def _block_shapes(prefix: str, D: int) -> "OrderedDict[str, Tuple[int, ...]]":

@@ -64,7 +64,12 @@ def run_with_logit_capture(model, sos, max_seq_len, **kw):
     lg = []
     for p in LOGIT_POSITIONS:
         if p < max_seq_len:
-            lg.append(torch.cat([cap["top"][p].unsqueeze(1), cap["bot"][p]], dim=1))   # [B,5,V]
+            top, bot = cap["top"][p], cap["bot"][p]                                     # [B,Vt], [B,4,Vb]
+            V = max(top.shape[-1], bot.shape[-1])                                       # zero-padded like O.sample
+            row = torch.zeros(top.shape[0], 5, V)
+            row[:, 0, : top.shape[-1]] = top
+            row[:, 1:, : bot.shape[-1]] = bot
+            lg.append(row)                                                              # [B,5,V]
     return ct, cb, torch.stack(lg, dim=1)                                               # [B,P,5,V]
 
 
@@ -79,7 +84,7 @@ def full_run_margin(cfg, P, cond, B):
     margin is >= 1e-4: an fp32 GPU run (different summation order, ~1e-6 error) then cannot flip an
     argmax, which is what makes 'bit-exact greedy code grids' a meaningful assertion."""
     _, _, lg = O.sample(P, cfg, cond, B, top_k_top=1, top_k_bot=1, return_logits=True)
-    return min_margin(lg)
+    return min(min_margin(lg[:, :, 0, : cfg.vocab_top]), min_margin(lg[:, :, 1:, : cfg.vocab_bot]))
 
 
 def meta(cfg, seed, init, **extra):
@@ -166,6 +171,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     golden_cls(O.SMALL, "small_cls_greedy.npz", seed=5, init="rich", labels=[0, 1, 2, 3])
     golden_cls(O.TINY, "tiny_cls_greedy.npz", seed=7, init="reference", labels=[9, 4, 4, 0, 7])
+    golden_cls(O.ASYM, "asym_cls_greedy.npz", seed=4, init="rich", labels=[0, 3, 6, 2, 5])
     golden_txt(O.HQConfig(**{**O.TINY.to_dict(), "cond": "txt"}), "tiny_txt_greedy.npz", seed=2, init="rich", B=3)
     golden_uncond(O.HQConfig(**{**O.TINY.to_dict(), "cond": "uncond"}), "tiny_uncond_stochastic.npz", seed=3,
                   init="rich", B=4)

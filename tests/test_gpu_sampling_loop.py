@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 GREEDY = dict(top_k_top=1, top_p_top=1.0, top_k_bot=1, top_p_bot=1.0, softmax_temperature=[1.0, 1.0])
 
 
-@pytest.mark.parametrize("name", ["tiny_cls_greedy.npz", "small_cls_greedy.npz"])
+@pytest.mark.parametrize("name", ["tiny_cls_greedy.npz", "small_cls_greedy.npz", "asym_cls_greedy.npz"])
 @pytest.mark.parametrize("graph,pdl", [(False, False), (True, False), (False, True), (True, True)])
 def test_greedy_codes_bit_exact_vs_reference_fp32(name, graph, pdl):
     """Config 1 of BASELINE.json: greedy code grids from the reference's own sampler (CPU, fp32) must be reproduced
@@ -33,7 +33,7 @@ def test_greedy_codes_bit_exact_vs_reference_fp32(name, graph, pdl):
     assert np.array_equal(cb_s.cpu().numpy(), g["codes_bot_scalar_class"])
 
 
-@pytest.mark.parametrize("name", ["tiny_cls_greedy.npz", "small_cls_greedy.npz"])
+@pytest.mark.parametrize("name", ["tiny_cls_greedy.npz", "small_cls_greedy.npz", "asym_cls_greedy.npz"])
 def test_step_logits_fp32_vs_reference(name):
     """Per-position head outputs captured from the reference (hooks on head_top/head_bot) at 5 positions."""
     import hqtransformer_b200 as H
@@ -49,7 +49,7 @@ def test_step_logits_fp32_vs_reference(name):
     assert err < 2e-5, err                              # stated fp32 tolerance: 2e-5 absolute (logit scale ~1)
 
 
-@pytest.mark.parametrize("name", ["tiny_cls_greedy.npz", "small_cls_greedy.npz"])
+@pytest.mark.parametrize("name", ["tiny_cls_greedy.npz", "small_cls_greedy.npz", "asym_cls_greedy.npz"])
 def test_step_logits_bf16_vs_oracle_and_reference(name):
     """bf16 production path (tcgen05 GEMMs, bf16 KV cache).  Two bars, both written here:
     (a) against the oracle run with the SAME rounding points (emulate='bf16'): max-abs <= 2e-2, mean-abs <= 2e-3

@@ -12,7 +12,7 @@ from tests.helpers import cfg_from_meta, load_golden
 GREEDY = dict(top_k_top=1, top_p_top=1.0, top_k_bot=1, top_p_bot=1.0)
 
 
-@pytest.mark.parametrize("name", ["tiny_cls_greedy.npz", "small_cls_greedy.npz"])
+@pytest.mark.parametrize("name", ["tiny_cls_greedy.npz", "small_cls_greedy.npz", "asym_cls_greedy.npz"])
 def test_oracle_greedy_codes_and_logits_equal_reference(name):
     g, meta = load_golden(name)
     assert meta["torch"].split("+")[0] == torch.__version__.split("+")[0], "goldens depend on torch's RNG stream"
