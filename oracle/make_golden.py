@@ -173,6 +173,7 @@ def main():
     golden_cls(O.TINY, "tiny_cls_greedy.npz", seed=7, init="reference", labels=[9, 4, 4, 0, 7])
     golden_cls(O.ASYM, "asym_cls_greedy.npz", seed=4, init="rich", labels=[0, 3, 6, 2, 5])
     golden_txt(O.HQConfig(**{**O.TINY.to_dict(), "cond": "txt"}), "tiny_txt_greedy.npz", seed=2, init="rich", B=3)
+    golden_txt(O.HQConfig(**{**O.ASYM.to_dict(), "cond": "txt"}), "asym_txt_greedy.npz", seed=6, init="rich", B=2)
     golden_uncond(O.HQConfig(**{**O.TINY.to_dict(), "cond": "uncond"}), "tiny_uncond_stochastic.npz", seed=3,
                   init="rich", B=4)
     golden_filters("filters.npz")

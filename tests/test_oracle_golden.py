@@ -30,8 +30,9 @@ def test_oracle_greedy_codes_and_logits_equal_reference(name):
     assert np.array_equal(cb_s.numpy(), g["codes_bot_scalar_class"])
 
 
-def test_oracle_text_prefix_equals_reference():
-    g, meta = load_golden("tiny_txt_greedy.npz")
+@pytest.mark.parametrize("name", ["tiny_txt_greedy.npz", "asym_txt_greedy.npz"])
+def test_oracle_text_prefix_equals_reference(name):
+    g, meta = load_golden(name)
     cfg = cfg_from_meta(meta)
     P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
     ids = torch.from_numpy(g["text_ids"])
