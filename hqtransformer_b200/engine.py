@@ -26,9 +26,16 @@ class SamplingParams:
     row_offset: int = 0
 
     def to_c(self) -> HQSamplingParams:
+        # top_p <= 0 (not None): the reference's nucleus cut then drops every sorted entry but the first
+        # (cumulative mass of the preceding entries >= 0 always, utils/sampling.py:27-31) - i.e. greedy.  The ABI
+        # reserves 0 for "no cut", so that case is sent as top_k = 1.
+        def k_of(k, p):
+            if p is not None and float(p) <= 0.0:
+                return 1
+            return int(k) if k else 0
         return HQSamplingParams(
-            top_k_top=int(self.top_k_top) if self.top_k_top else 0,
-            top_k_bot=int(self.top_k_bot) if self.top_k_bot else 0,
+            top_k_top=k_of(self.top_k_top, self.top_p_top),
+            top_k_bot=k_of(self.top_k_bot, self.top_p_bot),
             top_p_top=float(self.top_p_top) if self.top_p_top is not None else 0.0,
             top_p_bot=float(self.top_p_bot) if self.top_p_bot is not None else 0.0,
             temperature_top=float(self.temperature_top), temperature_bot=float(self.temperature_bot),
@@ -107,12 +114,13 @@ class Engine:
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True) -> None:
         """`load_state_dict(strict=True)` semantics (sampling_hqmodel.py:79): unknown keys, wrong shapes and
-        missing keys raise."""
+        missing keys raise.  strict=False ignores unknown and missing keys only - a shape mismatch or a CUDA failure
+        still raises, as torch's `load_state_dict(strict=False)` does."""
         for k, v in sd.items():
             try:
                 self.load_param(k, v)
-            except _lib.HQError:
-                if strict:
+            except _lib.HQError as e:
+                if strict or "unexpected key" not in str(e):
                     raise
         if strict:
             check(self._lib.hq_params_complete(self._ctx), self._ctx, "load_state_dict")

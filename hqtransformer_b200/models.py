@@ -27,6 +27,13 @@ def _temps(softmax_temperature) -> Tuple[float, float]:
     return float(softmax_temperature[0]), float(softmax_temperature[1])
 
 
+def fresh_seed() -> int:
+    """Philox key for one sampling call: 63 random bits from torch's default CPU generator.  Every call advances that
+    generator (as `torch.multinomial` does in the reference), so two consecutive default calls draw different
+    samples, and `set_seed` / `torch.manual_seed` reproduces the whole sequence of calls."""
+    return int(torch.empty((), dtype=torch.int64).random_())
+
+
 def _block_shapes(prefix: str, D: int) -> "OrderedDict[str, Tuple[int, ...]]":
     s = OrderedDict()
     for ln in ("ln1", "ln2"):
@@ -204,7 +211,7 @@ class iHQGPT:
         if past is None:
             if codes_t is not None:
                 raise AssertionError("first position: codes must be None when past is None")
-            st = dict(pos=0, B=B, eng=eng,
+            st = dict(pos=0, B=B, eng=eng, seed=fresh_seed() if seed is None else seed,   # one key per batch
                       codes_top=torch.zeros(B, S, dtype=torch.int64, device=self.device),
                       codes_bot=torch.zeros(B, S, 4, dtype=torch.int64, device=self.device))
             self._step_state = st
@@ -222,7 +229,7 @@ class iHQGPT:
             raise ValueError(f"position {cnt} beyond max_seq_len {S}")
         t_top, t_bot = _temps(softmax_temperature)
         sp = SamplingParams(top_k_top, top_p_top, top_k_bot, top_p_bot, t_top, t_bot,
-                            seed=torch.initial_seed() if seed is None else seed)
+                            seed=st["seed"] if seed is None else seed)
         given = None
         if given_top_code is not None:
             given = st["codes_top"].clone()

@@ -11,7 +11,7 @@ from typing import List, Optional, Tuple
 import torch
 
 from .engine import SamplingParams, debug_sample
-from .models import _temps
+from .models import _temps, fresh_seed
 
 
 @torch.no_grad()
@@ -27,8 +27,10 @@ def sampling_ihqgpt(model, num_candidates: int, cond, top_k_top: Optional[float]
     classes), text ids int64 [B, ctx_len_txt], or None for unconditional models.  For text models the batch is
     `cond.shape[0]` (the reference ignores num_candidates there too).
     `is_tqdm` / `model_stage1` are accepted and unused (no per-position host loop exists to decorate).
-    seed: Philox key of the draws; defaults to torch.initial_seed() so that `set_seed` (utils/utils.py:6-10)
-    keeps controlling reproducibility."""
+    seed: Philox key of the draws.  Default: a fresh 63-bit value drawn from torch's default CPU generator on every
+    call - like the reference's `torch.multinomial`, consecutive calls advance the global generator (the scripts call
+    the sampler many times per class with identical arguments, sampling_hqmodel.py:180-193) and `set_seed`
+    (utils/utils.py:6-10) reproduces the whole run."""
     if max_seq_len > model.max_seq_len:
         raise ValueError(f"max_seq_len={max_seq_len} exceeds the engine's {model.max_seq_len} top positions "
                          "(the scripts pass 64 for 8x8 top codes)")
@@ -37,13 +39,16 @@ def sampling_ihqgpt(model, num_candidates: int, cond, top_k_top: Optional[float]
     eng = model._engine_for(use_fp16, B)
     t_top, t_bot = _temps(softmax_temperature)
     sp = SamplingParams(top_k_top, top_p_top, top_k_bot, top_p_bot, t_top, t_bot,
-                        seed=torch.initial_seed() if seed is None else seed, row_offset=row_offset)
+                        seed=fresh_seed() if seed is None else seed, row_offset=row_offset)
     dev = model.device
     codes_top = torch.empty(B, max_seq_len, dtype=torch.int64, device=dev)
     codes_bot = torch.empty(B, max_seq_len, 4, dtype=torch.int64, device=dev)
     given = None
     if given_top_code is not None:
-        given = given_top_code[:, :max_seq_len].to(device=dev, dtype=torch.int64).contiguous()
+        given = given_top_code[:, :max_seq_len].to(device=dev, dtype=torch.int64)
+        if given.shape[0] == 1 and B > 1:          # the reference broadcasts a [1, S] grid over the batch (:771-772)
+            given = given.expand(B, -1)
+        given = given.contiguous()
         if tuple(given.shape) != (B, max_seq_len):
             raise ValueError(f"given_top_code must be [B, >= {max_seq_len}], got {tuple(given_top_code.shape)}")
         if int(given.min()) < 0 or int(given.max()) >= model.vocab_size_top:

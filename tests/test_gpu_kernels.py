@@ -162,6 +162,30 @@ def test_sample_filters_match_reference_golden():
         np.testing.assert_allclose(out[rows], g[f"topp_small_{p}"][rows], rtol=1e-5, atol=1e-9)
 
 
+def test_sample_topp_edges_vs_reference_golden():
+    """p = 1.0: the reference still sorts and cuts, and on these goldens keeps everything - same support here (the
+    engine skips the cut for p >= 1).  The exactly-on-boundary row (0.5 + 0.3 vs p = 0.8 in fp32) is implementation
+    defined: the reference keeps 2 entries; moving p by one part in 1e6 either way must reproduce the reference's
+    answer for the neighbouring, well-defined problems.  p = 0 keeps the first sorted entry only."""
+    import hqtransformer_b200 as H
+    from hqtransformer_b200.engine import SamplingParams
+    g, _ = load_golden("filters.npz")
+    pin = torch.from_numpy(g["topp_in"]).cuda()
+    out = H.cutoff_topp_probs(pin, 1.0).cpu().numpy()
+    assert np.array_equal(out > 0, g["topp_1.0"] > 0)
+    np.testing.assert_allclose(out, g["topp_1.0"], rtol=1e-4, atol=1e-9)
+    small = torch.from_numpy(g["topp_small_in"]).cuda()
+    out = H.cutoff_topp_probs(small, 1.0).cpu().numpy()
+    np.testing.assert_allclose(out, g["topp_small_1.0"], rtol=1e-5, atol=1e-9)
+    row = small[0:1]
+    kept = int((H.cutoff_topp_probs(row, 0.8) > 0).sum())
+    assert kept in (2, 3), kept
+    assert int((H.cutoff_topp_probs(row, 0.8 - 1e-4) > 0).sum()) == 2      # reference: [.625, .375, 0, 0]
+    assert int((H.cutoff_topp_probs(row, 0.8 + 1e-4) > 0).sum()) == 3
+    sp = SamplingParams(top_k_top=None, top_p_top=0.0, top_k_bot=50, top_p_bot=0.5).to_c()
+    assert sp.top_k_top == 1 and sp.top_k_bot == 50
+
+
 def test_sample_greedy_is_lowest_index_argmax():
     from hqtransformer_b200.engine import debug_sample
     logits = torch.randn(32, 1024)
