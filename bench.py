@@ -45,8 +45,12 @@ def parse_args():
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=16)
-    ap.add_argument("--cpu-positions", type=int, default=4)
+    ap.add_argument("--cpu-batch", type=int, default=16, help="cpu_baseline leg of the default run: images per step")
+    ap.add_argument("--cpu-positions", type=int, default=4, help="cpu_baseline leg of the default run: top positions per step")
+    ap.add_argument("--ref-batch", type=int, default=64, help="--impl reference: images per step (all 64 positions)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the timed steps")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip extras.reference_gpu_fp16_autocast")
+    ap.add_argument("--ref-gpu-batch", type=int, default=0, help="batch of the reference-on-GPU extra (0 = --batch)")
     return ap.parse_args()
 
 
@@ -130,19 +134,117 @@ def cpu_reference_rate(model_name: str, batch: int, positions: int, steps: int, 
                               f"positions per step (rate scaled by {positions}/64), {len(times)} timed steps")
 
 
+def _oracle_cfg(model_name: str):
+    from oracle import hq_oracle as O
+    return {"imagenet_l12": O.IMAGENET_L12, "imagenet_l24": O.IMAGENET_L24, "imagenet_l42": O.IMAGENET_L42,
+            "cc15m_l12": O.CC15M_L12}[model_name]
+
+
+def reference_cpu_rates(model_name: str, plan, budget_s: float):
+    """The UNMODIFIED reference sampler (`sampling_ihqgpt` -> `iHQGPT.sampling_step`, imported through oracle/ref_shim.py
+    from the verbatim copy under baseline/_ref/) on the host CPU cores: fp32 (`use_fp16=False`, the reference's CPU mode),
+    its own random init, measure_throughput protocol (one class per batch, top-k / top-p None, T = 1), ALL 64 top
+    positions per step.  plan = [(batch, steps, warmup), ...]; returns {batch: (images/s, s/step, steps timed)} - at most
+    `steps` steps per batch size, fewer when `budget_s` runs out (what was really timed is what is reported)."""
+    import random
+    import torch
+    from oracle import ref_shim as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = _oracle_cfg(model_name)
+    model = R.build_reference_model_random(cfg)
+    out = {}
+    t_begin = time.perf_counter()
+    for B, steps, warmup in plan:
+        def one():
+            if cfg.cond == "txt":
+                cond = torch.randint(0, cfg.vocab_txt, (B, cfg.ctx_len_txt))
+            else:
+                cond = random.randint(0, cfg.n_classes - 1)
+            t0 = time.perf_counter()
+            ct, cb = R.reference_sample(model, B, cond, top_k_top=None, top_p_top=None, top_k_bot=None, top_p_bot=None,
+                                        softmax_temperature=[1.0, 1.0], max_seq_len=64)
+            assert tuple(ct.shape) == (B, 64) and tuple(cb.shape) == (B, 64, 4)
+            return time.perf_counter() - t0
+        for _ in range(warmup):
+            one()
+        times = []
+        for _ in range(steps):
+            times.append(one())
+            if time.perf_counter() - t_begin > budget_s:
+                break
+        sec = sum(times) / len(times)
+        out[B] = (B / sec, sec, len(times))
+    return out
+
+
 def run_reference_arm(args, rank: int):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
     if rank != 0:
         return
-    rate, sec, cores, sample = cpu_reference_rate(args.model, args.cpu_batch, args.cpu_positions, max(1, min(args.steps, 3)),
-                                                  min(args.warmup, 1))
-    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.model} class-conditional sampling, CPU bounded sample", "model": args.model},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+    from oracle import ref_shim as R
+    cores = os.cpu_count() or 1
+    B = args.ref_batch
+    if R.reference_available():
+        kind = "reference"
+        plan = [(B, args.steps, min(args.warmup, 1))] + [(b, 1, 0) for b in (4, 16) if b != B]   # BASELINE.md 3: B in {4, 16, 64}
+        rates = reference_cpu_rates(args.model, plan, budget_s=args.ref_budget_s)
+        rate, sec, timed = rates[B]
+        extra = {f"B{b}": {"images_per_s": r[0], "s_per_step": r[1]} for b, r in rates.items() if b != B}
+        sample = (f"{args.model}: UNMODIFIED reference sampler (sampling_ihqgpt, baseline/_ref copy) fp32 on {cores} host "
+                  f"threads, batch {B}, all 64 top positions per step, own random init, {timed} timed step(s)")
+        positions = 64
+    else:       # no copy of the reference on this box: the oracle port on a bounded sample
+        kind = "port"
+        rate, sec, cores, sample = cpu_reference_rate(args.model, args.cpu_batch, args.cpu_positions, max(1, min(args.steps, 3)),
+                                                      min(args.warmup, 1))
+        timed, extra, positions, B = max(1, min(args.steps, 3)), {}, args.cpu_positions, args.cpu_batch
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
+            "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.model}: class-conditional HQ-Transformer sampling, 64 top positions x (1 top + 4 "
+                                   f"bottom codes), random-init weights, top_k=None top_p=None T=1.0; CPU sample: batch {B}, "
+                                   f"{positions} positions per step",
+                       "model": args.model, "batch": B, "positions": positions, "same_config_as_gpu_arm": False,
+                       "note": "the GPU arm runs batch 256 per GPU; the reference on CPU is timed on a bounded batch"},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "other_batches": extra},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def reference_gpu_rate(model_name: str, B: int, device, steps: int = 2):
+    """The honest "before" number: the UNMODIFIED reference sampler in its native mode on this same GPU - fp16 autocast,
+    PyTorch eager, measure_throughput protocol (measure_throughput/__main__.py:93-104).  Returns a dict for `extras`."""
+    import random
+    import torch
+    from oracle import ref_shim as R
+    if not R.reference_available():
+        return {"unavailable": "no copy of the reference under baseline/_ref on this box"}
+    cfg = _oracle_cfg(model_name)
+    try:
+        model = R.build_reference_model_random(cfg).to(device)
+        def one():
+            cond = (torch.randint(0, cfg.vocab_txt, (B, cfg.ctx_len_txt)) if cfg.cond == "txt"
+                    else random.randint(0, cfg.n_classes - 1))
+            return R.reference_sample(model, B, cond, device="cuda", use_fp16=True, top_k_top=None, top_p_top=None,
+                                      top_k_bot=None, top_p_bot=None, softmax_temperature=[1.0, 1.0], max_seq_len=64)
+        with torch.no_grad():
+            one()
+            torch.cuda.synchronize(device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                ct, _ = one()
+            e1.record()
+            torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1) / steps
+        del model
+        torch.cuda.empty_cache()
+        return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "ms_per_top_position": ms / 64, "batch": B,
+                "steps": steps, "what": "unmodified reference sampler (PyTorch eager, torch.cuda.amp.autocast fp16) on the "
+                                        "same B200, same protocol and batch; baseline/_ref copy via oracle/ref_shim.py"}
+    except Exception as e:      # a reference that cannot run on this torch / GPU must not take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -257,6 +359,30 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
     launches = eng.last_launch_count * args.steps
     assert int(ct.min()) >= 0 and int(ct.max()) < s2.vocab_size_top and tuple(ct.shape) == (world * B, S)
 
+    # ---- sharding invariance, checked on the grids of the last timed step: rank 0 re-samples ANOTHER shard of the global
+    #      batch on its own GPU (that shard's conditioning, its global row offset, the same Philox key) and compares it
+    #      bit for bit with the rows the all-gather delivered.  N = 1: rows [B/4, B/2) re-sampled as a shard of their own
+    #      (another GEMM kernel: single CTA instead of CTA pairs). ----
+    sharded_equal = None
+    if rank == 0:
+        last_seed = args.warmup + args.steps - 1
+        if world > 1:
+            other = 1
+            g_o = torch.Generator().manual_seed(1234 + other)
+            if s2.use_txt_cond:
+                cond_o = torch.randint(0, s2.vocab_size_txt, (B, s2.ctx_len_txt), generator=g_o).to(dev)
+            else:
+                cond_o = torch.randint(0, s2.n_classes, (B,), generator=g_o).to(dev)
+            ct_o, cb_o = H.sampling_ihqgpt(s2, B, cond_o, seed=last_seed, row_offset=other * B, **kw)
+            sharded_equal = bool(torch.equal(ct_o, ct[other * B:(other + 1) * B]) and
+                                 torch.equal(cb_o, cb[other * B:(other + 1) * B]))
+        else:
+            lo, hi = B // 4, B // 2
+            if hi > lo:
+                ct_o, cb_o = H.sampling_ihqgpt(s2, hi - lo, cond_dev[lo:hi], seed=last_seed, row_offset=lo, **kw)
+                sharded_equal = bool(torch.equal(ct_o, ct[lo:hi]) and torch.equal(cb_o, cb[lo:hi]))
+        note(f"sharded_equals_single: {sharded_equal}")
+
     # ---- end to end through the C-ABI host call: pinned host buffers, H2D of the conditioning and D2H of the grids
     #      inside the timed region ----
     cond_pin = cond_host.clone().pin_memory()
@@ -301,7 +427,11 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
             "ms_per_top_position": ms / args.steps / S,
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": clocks, "device_bytes": eng.device_bytes}
+            "gpu_launches": launches, "clocks": clocks, "device_bytes": eng.device_bytes,
+            "sharded_equals_single": sharded_equal,
+            "parity_note": "bf16 tcgen05 engine: validated by teacher-forced logits against the reference / oracle within the "
+                           "stated bf16 tolerance; bit-exact greedy grids vs the reference are shown for the fp32 engine "
+                           "(tests/test_gpu_sampling_loop.py, tests/test_gpu_full_size.py)"}
 
     if rank == 0:
         D = s2.embed_dim
@@ -351,7 +481,12 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
             line["trace_us_per_position"] = span_us
         if world == 1 and not args.no_cpu_baseline:
             rate, sec, cores, sample = cpu_reference_rate(args.model, args.cpu_batch, args.cpu_positions, 1, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                    "see_also": "`bench.py --impl reference` times the unmodified reference (kind \"reference\") "
+                                                "over all 64 positions"}
+        if world == 1 and not args.no_ref_gpu:
+            del local_ct, local_cb
+            line["extras"] = {"reference_gpu_fp16_autocast": reference_gpu_rate(args.model, args.ref_gpu_batch or B, dev)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

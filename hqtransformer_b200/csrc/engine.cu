@@ -75,6 +75,51 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// Experiment / test switches.  They are read from the environment ONCE, when a ctx is created (or a stand-alone debug
+// hook is entered), and ONLY when HQ_DEBUG=1 is set: a stray HQ_* variable in a production environment changes nothing.
+struct DebugSwitches {
+  std::string ablate;          // HQ_ABLATE=tag[,tag...]: drop launches whose tag starts with one of the names (timing only)
+  int attn_groups = 0;         // HQ_ATTN_GROUPS: head groups per image of the decode attention
+  int attn_no_prefetch = 0;    // HQ_ATTN_NO_PREFETCH: no K/V request ahead of griddepcontrol.wait
+  int attn_sleep = 0;          // HQ_ATTN_SLEEP (ns), scalar kernel
+  int attn_scalar = 0;         // HQ_ATTN_SCALAR: the scalar bulk-staged kernel (also pinned by hq_debug_attention variant 1)
+  int attm_stages = 0;         // HQ_ATTM_STAGES
+  int attm_per_sm = 0;         // HQ_ATTM_PER_SM
+  int attn_generic = 0;        // HQ_ATTN_GENERIC
+  int attn_fewkeys_old = 0;    // HQ_ATTN_FEWKEYS_OLD
+  int max_splitk = 0;          // HQ_MAX_SPLITK
+  int no_splitk = 0;           // HQ_NO_SPLITK
+  int force_splitk = 0;        // HQ_FORCE_SPLITK (tests: pin the split-K factor of the residual GEMMs)
+  int trace_pdl = 0;           // HQ_TRACE_PDL: keep PDL on while tracing
+  int bench_splits = 0;        // HQ_BENCH_SPLITS (hq_bench_gemm_shape)
+  int force_bn = 0;            // hq_debug_gemm: pinned tile width (0 = heuristic, -64 / -128 = single-CTA kernel)
+};
+
+static int env_int(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+static DebugSwitches read_debug_switches() {
+  DebugSwitches d;
+  const char* on = getenv("HQ_DEBUG");
+  if (on == nullptr || atoi(on) == 0) return d;
+  if (const char* a = getenv("HQ_ABLATE")) d.ablate = a;
+  d.attn_groups = env_int("HQ_ATTN_GROUPS");
+  d.attn_no_prefetch = getenv("HQ_ATTN_NO_PREFETCH") != nullptr;
+  d.attn_sleep = env_int("HQ_ATTN_SLEEP");
+  d.attn_scalar = getenv("HQ_ATTN_SCALAR") != nullptr;
+  d.attm_stages = env_int("HQ_ATTM_STAGES");
+  d.attm_per_sm = env_int("HQ_ATTM_PER_SM");
+  d.attn_generic = getenv("HQ_ATTN_GENERIC") != nullptr;
+  d.attn_fewkeys_old = getenv("HQ_ATTN_FEWKEYS_OLD") != nullptr;
+  d.max_splitk = env_int("HQ_MAX_SPLITK");
+  d.no_splitk = getenv("HQ_NO_SPLITK") != nullptr;
+  d.force_splitk = env_int("HQ_FORCE_SPLITK");
+  d.trace_pdl = getenv("HQ_TRACE_PDL") != nullptr;
+  d.bench_splits = env_int("HQ_BENCH_SPLITS");
+  return d;
+}
+
 struct GraphKey {
   int B, S, p0, p1, forced_top, forced_bot, sos_override, tracing;
   bool operator<(const GraphKey& o) const {
@@ -121,7 +166,8 @@ struct hq_ctx {
   hq_sampling_params* d_sp = nullptr;
 
   cudaStream_t own_stream = nullptr;
-  struct GraphEntry { cudaGraphExec_t exec; int64_t launches; };
+  struct GraphEntry { cudaGraphExec_t exec; int64_t launches; uint64_t stamp; };
+  static constexpr size_t kMaxGraphs = 96;   // LRU-capped: the per-position sampling_step API captures one graph per position
   std::map<GraphKey, GraphEntry> graphs;
   int64_t launches = 0;
   int64_t last_launches = 0;
@@ -132,6 +178,8 @@ struct hq_ctx {
   std::vector<std::string> trace_tags;
   bool full_dependency_next = false;   // the next launch is an ordinary (complete-then-start) dependency even under PDL
   std::string tag_suffix;   // shape annotation appended to the next launch tag (tracing only)
+  DebugSwitches dbg = read_debug_switches();
+  uint64_t graph_clock = 0;   // LRU stamp source of the graph cache
 };
 
 static void set_err(hq_ctx* ctx, const char* fmt, ...) {
@@ -323,14 +371,12 @@ static void free_activations(hq_ctx* ctx);
 static int reserve_impl(hq_ctx* ctx, int max_batch);
 
 // Head groups per image of the decode attention kernels: (image, group) work items, nh / groups heads (warps) each.
-static int attn_groups(int nh) {
+static int attn_groups(const hq_ctx* ctx, int nh) {
   int g = 0;
   for (int cand : {4, 3, 2, 1})
     if (nh % cand == 0 && nh / cand <= ATTD_MAXHPC) { g = cand; break; }
-  if (const char* f = getenv("HQ_ATTN_GROUPS")) {          // experiments: pin the number of head groups per image
-    const int v = atoi(f);
-    if (v >= 1 && nh % v == 0 && nh / v <= ATTD_MAXHPC) g = v;
-  }
+  const int v = ctx->dbg.attn_groups;                       // experiments: pin the number of head groups per image
+  if (v >= 1 && nh % v == 0 && nh / v <= ATTD_MAXHPC) g = v;
   return g;
 }
 
@@ -358,7 +404,32 @@ static void free_activations(hq_ctx* ctx) {
 }
 
 // batch-sized state: activations, KV cache [L][B][Tc][D] x2, depth KV [Ld][B][5][D] x2, code buffers
+static int reserve_alloc(hq_ctx* ctx, int max_batch);
+
+// On failure (e.g. out of memory while growing the batch) the ctx keeps NO batch state: every batch-sized buffer is
+// freed, the pointers are nulled and max_batch is 0, so validate_run rejects any run until a reserve succeeds.
 static int reserve_impl(hq_ctx* ctx, int max_batch) {
+  const int rc = reserve_alloc(ctx, max_batch);
+  if (rc != HQ_OK) {
+    const std::string why = ctx->err;
+    cudaGetLastError();                        // clear the sticky-free allocation error
+    free_activations(ctx);
+    ctx->max_batch = 0;
+    ctx->ws_rows = 0;
+    ctx->kv_maps = false;
+    ctx->h = ABuf(); ctx->att = ABuf(); ctx->mlp = ABuf();
+    ctx->q = nullptr; ctx->x = nullptr; ctx->yd = nullptr; ctx->logits = nullptr; ctx->splitk_ws = nullptr;
+    ctx->kc = ctx->vc = ctx->kd = ctx->vd = nullptr;
+    ctx->cond = ctx->codes_top = ctx->codes_bot = nullptr;
+    ctx->sos_override = nullptr;
+    ctx->d_sp = nullptr;
+    set_err(ctx, "hq_reserve_batch(%d) failed, the ctx holds no batch state until a reserve succeeds: %s", max_batch,
+            why.c_str());
+  }
+  return rc;
+}
+
+static int reserve_alloc(hq_ctx* ctx, int max_batch) {
   int rc;
   if (max_batch < 1) {
     set_err(ctx, "max_batch must be >= 1");
@@ -388,7 +459,7 @@ static int reserve_impl(hq_ctx* ctx, int max_batch) {
   if ((rc = dev_alloc(ctx, &ctx->vc, kvn))) return rc;
   ctx->kv_maps = false;
   if (ctx->bf16) {
-    const int groups = attn_groups(ctx->nh);
+    const int groups = attn_groups(ctx, ctx->nh);
     if (groups > 0) {
       const uint64_t rows = static_cast<uint64_t>(ctx->L) * B * ctx->Tc;
       if ((rc = make_kv_map(ctx, &ctx->kmap, ctx->kc, ctx->nh, rows, ctx->nh / groups))) return rc;
@@ -654,7 +725,7 @@ static void launch_k(hq_ctx* ctx, cudaStream_t st, const char* tag, void (*kerne
   ctx->full_dependency_next = false;
   // experiments only: HQ_ABLATE=tag[,tag...] drops every launch whose tag starts with one of the names, to read a
   // kernel family's MARGINAL cost in the PDL-overlapped loop off the step time (results are garbage, timing is not)
-  static const char* ablate = getenv("HQ_ABLATE");
+  const char* ablate = ctx->dbg.ablate.empty() ? nullptr : ctx->dbg.ablate.c_str();
   if (ablate != nullptr) {
     const size_t n = strlen(tag);
     for (const char* p = ablate; *p;) {
@@ -713,13 +784,11 @@ static int pick_pair_bn(int M, int N, int K) {
   return best;
 }
 
-static int g_force_bn = 0;   // tests: hq_debug_gemm may pin the tile width (0 = heuristic, -64 / -128 = single-CTA kernel)
-
 template <int EPI>
 static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mW64,
                       const PairMaps& mWp, int w_row_off, int M, int N, int K, const EpiParams<bf16>& ep,
                       int splits = 1, int bn_hint = 0) {
-  int bn = g_force_bn ? g_force_bn : bn_hint;
+  int bn = ctx->dbg.force_bn ? ctx->dbg.force_bn : bn_hint;
   if (bn == 0) bn = (M > 128) ? pick_pair_bn(M, N, K) : 0;
   if (ctx->tracing) {
     char buf[48];
@@ -794,20 +863,14 @@ static void layernorm_act(hq_ctx* ctx, cudaStream_t st, float* x, const float* g
 
 // May the decode attention request cached keys BEFORE griddepcontrol.wait?  Yes: run_position orders positions with a
 // full dependency, so every earlier position's keys are in place.  (HQ_ATTN_NO_PREFETCH: experiment switch.)
-static bool attn_prefetch_ok(const hq_ctx* ctx) {
-  (void)ctx;
-  return getenv("HQ_ATTN_NO_PREFETCH") == nullptr;
-}
+static bool attn_prefetch_ok(const hq_ctx* ctx) { return !ctx->dbg.attn_no_prefetch; }
 
-static int attn_sleep_ns() {
-  static const int v = getenv("HQ_ATTN_SLEEP") ? atoi(getenv("HQ_ATTN_SLEEP")) : 0;
-  return v;
-}
+static int attn_sleep_ns(const hq_ctx* ctx) { return ctx->dbg.attn_sleep; }
 
 // Launch plan of attention_decode_kernel for this model: head groups per image, keys per ring stage, dynamic smem.
 template <typename AT>
 static bool attn_decode_plan(const hq_ctx* ctx, int* CH, int* hpc, int* groups, size_t* smem) {
-  const int g = attn_groups(ctx->nh);
+  const int g = attn_groups(ctx, ctx->nh);
   if (g <= 0) return false;
   *groups = g;
   *hpc = ctx->nh / g;
@@ -824,16 +887,14 @@ static bool attn_decode_plan(const hq_ctx* ctx, int* CH, int* hpc, int* groups, 
 // Launch plan of attention_decode_mma_kernel (bf16): ring stages of one 8-key K tile + one 8-value V tile (hpc KB each);
 // grid = resident CTAs (registers allow four 7-warp CTAs per SM; each takes one item, then tickets), capped by the
 // number of items.
-static int g_attn_scalar = 0;   // tests: hq_debug_attention may pin the scalar bulk-staged kernel
 static bool attn_mma_plan(const hq_ctx* ctx, int groups, int hpc, int n_items, int* stages, size_t* smem, int* grid) {
-  static const bool off = getenv("HQ_ATTN_SCALAR") != nullptr;      // experiments: the scalar bulk-staged kernel
-  if (off || g_attn_scalar || !ctx->bf16 || ctx->num_sms <= 0 || !ctx->kv_maps) return false;
+  if (ctx->dbg.attn_scalar || !ctx->bf16 || ctx->num_sms <= 0 || !ctx->kv_maps) return false;
   const size_t stage = static_cast<size_t>(2 * ATTM_CH) * hpc * 128;     // K tile + V tile
   // Two stages (24 KB for 6 heads): measured equal end to end to a 4-deep ring and ~1 us faster per launch in the loop
   // (profiles/r1_attn_sweep.txt) - requests beyond the bandwidth-delay product only lengthen every request's latency,
   // and a 27 KB CTA still fits next to a resident GEMM CTA, so its prefetch can start under the QKV GEMM (PDL).
   int st = 2;
-  if (const char* f = getenv("HQ_ATTM_STAGES")) st = atoi(f);     // experiments
+  if (ctx->dbg.attm_stages) st = ctx->dbg.attm_stages;            // experiments
   if (st < 2) st = 2;
   if (st > ATTM_MAXSTAGES) st = ATTM_MAXSTAGES;
   const size_t bytes = 1024 /*tile alignment*/ + st * stage + 2 * static_cast<size_t>(hpc) * 128 +
@@ -844,7 +905,7 @@ static bool attn_mma_plan(const hq_ctx* ctx, int groups, int hpc, int n_items, i
   if (per_sm > by_threads) per_sm = by_threads;
   const int by_regs = 65536 / ((hpc + 1) * 32 * 72);              // 72 registers per thread (ptxas)
   if (by_regs >= 1 && per_sm > by_regs) per_sm = by_regs;
-  if (const char* f = getenv("HQ_ATTM_PER_SM")) per_sm = atoi(f) < per_sm ? atoi(f) : per_sm;   // experiments
+  if (ctx->dbg.attm_per_sm > 0 && ctx->dbg.attm_per_sm < per_sm) per_sm = ctx->dbg.attm_per_sm;   // experiments
   if (per_sm < 1) per_sm = 1;
   (void)groups;
   *stages = st;
@@ -871,7 +932,7 @@ static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, co
                       int t_stride, int kbase, int causal) {
   int CH = 0, hpc = 0, groups = 0;
   size_t smem = 0;
-  if (Tq == 1 && !causal && getenv("HQ_ATTN_GENERIC") == nullptr && attn_decode_plan<AT>(ctx, &CH, &hpc, &groups, &smem)) {
+  if (Tq == 1 && !causal && !ctx->dbg.attn_generic && attn_decode_plan<AT>(ctx, &CH, &hpc, &groups, &smem)) {
     // spatial decode: (image, head group) work items, K/V streamed through shared memory by bulk async copies
     if (ctx->tracing) ctx->tag_suffix = ":t" + std::to_string(kbase) + ":B" + std::to_string(M);
     int stages = 0, grid = 0;
@@ -884,11 +945,11 @@ static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, co
       return;
     }
     launch_k(ctx, st, "attention_decode", attention_decode_kernel<AT>, dim3(M * groups), dim3((hpc + 1) * 32), smem, q, K, V,
-             out, ctx->D, t_stride, kbase, CH, hpc, groups, attn_prefetch_ok(ctx) ? attn_sleep_ns() : -1);
+             out, ctx->D, t_stride, kbase, CH, hpc, groups, attn_prefetch_ok(ctx) ? attn_sleep_ns(ctx) : -1);
     return;
   }
   const int items = M * ctx->nh;
-  if (!causal && kbase <= ATT_DEPTH_KEYS && Tq == 4 && getenv("HQ_ATTN_FEWKEYS_OLD") == nullptr) {
+  if (!causal && kbase <= ATT_DEPTH_KEYS && Tq == 4 && !ctx->dbg.attn_fewkeys_old) {
     // the parallel depth pass: one warp per (image, head) serves the image's four queries
     const int warps = (M / 4) * ctx->nh;
     launch_k(ctx, st, "attention_depth4", attention_depth4_kernel<AT>, dim3((warps + ATT_WARPS - 1) / ATT_WARPS),
@@ -932,9 +993,9 @@ struct Fc2Plan { int bn, splits; };
 // images, never at the actual batch.  The K slices and the order in which the LayerNorm adds their partial sums fix how
 // every output element is rounded; tile widths and kernels (pair / single CTA) do not.  A split that does not depend on
 // the batch therefore makes a row's result independent of the batch it sits in - and of how a batch is sharded over GPUs.
-static int resid_splits(int N, int K, int rows_per_image) {
+static int resid_splits(const hq_ctx* ctx, int N, int K, int rows_per_image) {
   static const int cand[6] = {256, 192, 128, 96, 64, 32};
-  static const int max_splits = getenv("HQ_MAX_SPLITK") ? atoi(getenv("HQ_MAX_SPLITK")) : LN_MAXFOLD;
+  const int max_splits = ctx->dbg.max_splitk > 0 ? ctx->dbg.max_splitk : LN_MAXFOLD;
   const int kb = K / 64;
   int best = 1;
   double best_cost = 1e30;
@@ -955,12 +1016,12 @@ static int resid_splits(int N, int K, int rows_per_image) {
 // Tile width for this M given the split (bn = 0: the single-CTA kernel, M <= 128, K slices on grid.z).
 static Fc2Plan pick_resid_plan(const hq_ctx* ctx, int M, int N, int K, int rows_per_image) {
   Fc2Plan best{0, 1};
-  if (!ctx->bf16 || N % 64 != 0 || K % 64 != 0 || getenv("HQ_NO_SPLITK") != nullptr) return best;
+  if (!ctx->bf16 || N % 64 != 0 || K % 64 != 0 || ctx->dbg.no_splitk) return best;
   static const int cand[6] = {256, 192, 128, 96, 64, 32};
   const int kb = K / 64;
-  int s = resid_splits(N, K, rows_per_image);
-  if (const char* f = getenv("HQ_FORCE_SPLITK")) {       // tests: pin the split factor
-    const int v = atoi(f);
+  int s = resid_splits(ctx, N, K, rows_per_image);
+  {
+    const int v = ctx->dbg.force_splitk;                  // tests: pin the split factor
     if (v >= 1 && v <= LN_MAXFOLD && kb % v == 0) s = v;
   }
   best.splits = s;
@@ -1212,8 +1273,18 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
         set_err(ctx, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
         return HQ_ERR_CUDA;
       }
-      it = ctx->graphs.emplace(key, hq_ctx::GraphEntry{exec, ctx->launches}).first;
+      if (ctx->graphs.size() >= hq_ctx::kMaxGraphs) {     // evict the least recently used graph
+        auto victim = ctx->graphs.begin();
+        for (auto g = ctx->graphs.begin(); g != ctx->graphs.end(); ++g)
+          if (g->second.stamp < victim->second.stamp) victim = g;
+        // a replay of the victim may still be in flight on the caller's stream
+        HQ_CUDA(ctx, cudaStreamSynchronize(st));
+        cudaGraphExecDestroy(victim->second.exec);
+        ctx->graphs.erase(victim);
+      }
+      it = ctx->graphs.emplace(key, hq_ctx::GraphEntry{exec, ctx->launches, 0}).first;
     }
+    it->second.stamp = ++ctx->graph_clock;
     HQ_CUDA(ctx, cudaGraphLaunch(it->second.exec, st));
     ctx->last_launches = it->second.launches;
   } else {
@@ -1273,7 +1344,7 @@ extern "C" int hq_debug_attention(int prec, const void* q, const void* K, const 
   HQ_CUDA(nullptr, cudaMalloc(reinterpret_cast<void**>(&tmp.att_sched), 16));
   cudaMemsetAsync(tmp.att_sched, 0, 16, st);
   if (tmp.bf16 && variant != 1) {
-    const int groups = attn_groups(n_heads);
+    const int groups = attn_groups(&tmp, n_heads);
     tmp.kc = const_cast<void*>(K);
     tmp.vc = const_cast<void*>(V);
     if ((rc = get_encode_fn(&tmp, &tmp.encode)) == HQ_OK && groups > 0 &&
@@ -1286,14 +1357,13 @@ extern "C" int hq_debug_attention(int prec, const void* q, const void* K, const 
       return rc;
     }
   }
-  g_attn_scalar = variant == 1;
+  if (variant == 1) tmp.dbg.attn_scalar = 1;
   if (tmp.bf16)
     attention<bf16>(&tmp, st, static_cast<const bf16*>(q), static_cast<const bf16*>(K), static_cast<const bf16*>(V),
                     static_cast<bf16*>(out), B, 1, t_stride, n_keys, 0);
   else
     attention<float>(&tmp, st, static_cast<const float*>(q), static_cast<const float*>(K), static_cast<const float*>(V),
                      static_cast<float*>(out), B, 1, t_stride, n_keys, 0);
-  g_attn_scalar = 0;
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(tmp.att_sched);
   if (e == cudaSuccess) e = tmp.launch_err;
@@ -1348,9 +1418,8 @@ extern "C" int hq_debug_gemm(int prec, const void* A, const void* W, float* C, i
       EpiParams<bf16> e;
       memset(&e, 0, sizeof(e));
       e.outf = C; e.ldo = N;
-      g_force_bn = tile;
+      tmp.dbg.force_bn = tile;
       gemm_bf16<EPI_F32>(&tmp, st, mA, mW, mWp, 0, M, N, K, e);
-      g_force_bn = 0;
     }
     cudaError_t se = cudaStreamSynchronize(st);
     if (Ap) cudaFree(Ap);
@@ -1596,13 +1665,13 @@ __global__ void read_sweep_kernel(const uint4* __restrict__ p, size_t n, unsigne
 
 extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int flush, int copies, float* usec_mean,
                                    float* usec_min, void* stream) {
-  const int splits = getenv("HQ_BENCH_SPLITS") ? atoi(getenv("HQ_BENCH_SPLITS")) : 1;
   if (M < 1 || N % 64 != 0 || K % 64 != 0 || iters < 1 || copies < 1 || !usec_mean || !usec_min) {
     set_err(nullptr, "hq_bench_gemm_shape: bad argument");
     return HQ_ERR_INVALID;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   hq_ctx tmp;
+  const int splits = tmp.dbg.bench_splits > 0 ? tmp.dbg.bench_splits : 1;
   int dev = 0;
   HQ_CUDA(nullptr, cudaGetDevice(&dev));
   int rc = check_device(&tmp, dev);
@@ -1640,7 +1709,7 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
     EpiParams<bf16> e;
     memset(&e, 0, sizeof(e));
     e.outf = C; e.ldo = N; e.split_stride = static_cast<size_t>(M) * N;
-    g_force_bn = tile;
+    tmp.dbg.force_bn = tile;
     for (int i = -3; i < iters; ++i) {
       const int c = ((i % copies) + copies) % copies;
       if (flush == 1) cudaMemsetAsync(flushbuf, i & 0xff, flush_bytes, st);
@@ -1649,7 +1718,6 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
       gemm_bf16<EPI_F32>(&tmp, st, mA, mW[c], mWp[c], 0, M, N, K, e, splits);
       if (i >= 0) cudaEventRecord(ev[2 * i + 1], st);
     }
-    g_force_bn = 0;
   }
   cudaError_t se = cudaStreamSynchronize(st);
   double tot = 0.0, mn = 1e30;
@@ -1695,7 +1763,7 @@ extern "C" int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, 
   }
   const bool saved_pdl = ctx->use_pdl;
   // with PDL a kernel is resident (waiting) long before it can run, so lifetimes overlap: off unless asked for
-  if (getenv("HQ_TRACE_PDL") == nullptr) ctx->use_pdl = false;
+  if (!ctx->dbg.trace_pdl) ctx->use_pdl = false;
   ctx->tracing = true;
   ctx->trace_cap = max_entries;
   ctx->trace_tags.clear();

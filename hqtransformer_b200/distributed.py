@@ -50,13 +50,27 @@ def sampling_ihqgpt_sharded(model, num_candidates: int, cond, *, gather: bool = 
     """`sampling_ihqgpt` for a global batch of `num_candidates` rows split over the ranks of `group`.
     cond: class id (int) | int64 [B] per-row classes | int64 [B, ctx_len_txt] text ids | None.
     Returns the full [B, S] / [B, S, 4] grids on every rank (gather=True) or this rank's shard."""
+    from .models import fresh_seed
     from .sampling import sampling_ihqgpt
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     B = num_candidates if not torch.is_tensor(cond) or cond.numel() == 1 else cond.shape[0]
     lo, hi = shard_range(B, rank, world)
     local_cond = cond[lo:hi] if torch.is_tensor(cond) and cond.numel() > 1 else cond
-    ct, cb = sampling_ihqgpt(model, hi - lo, local_cond, row_offset=lo, **kw)
+    kw = dict(kw)
+    if kw.get("seed") is None:
+        # one Philox key for the whole global batch: rank 0 draws it from its default generator, everyone uses it
+        box = [fresh_seed() if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        kw["seed"] = box[0]
+    if hi > lo:
+        ct, cb = sampling_ihqgpt(model, hi - lo, local_cond, row_offset=lo, **kw)
+    else:
+        # more ranks than rows: this rank has nothing to sample but still joins the collective below
+        S = kw.get("max_seq_len", 256)
+        ct = torch.empty(0, S, dtype=torch.int64, device=model.device)
+        cb = torch.empty(0, S, 4, dtype=torch.int64, device=model.device)
     if gather and world > 1:
         return gather_codes(ct, cb, B, group)
     return ct, cb

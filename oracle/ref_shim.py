@@ -17,7 +17,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("HQ_REFERENCE_ROOT", "/root/reference")
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    """The live tree in the build container; on the GPU box the verbatim copy `oracle/install_reference.py` placed under
+    the git-ignored baseline/_ref/ (used by bench.py's reference arm only)."""
+    env = os.environ.get("HQ_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/hqvae"):
+        return "/root/reference"
+    return os.path.join(_REPO_ROOT, "baseline", "_ref")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
@@ -80,13 +94,18 @@ def build_reference_model(cfg, state_dict):
     return model.eval()
 
 
-def reference_sample(model, num_candidates, cond, **kw):
-    """Run the reference's own `sampling_ihqgpt` (utils/sampling.py:164-237) on CPU.
+def reference_sample(model, num_candidates, cond, device="cpu", use_fp16=False, **kw):
+    """Run the reference's own `sampling_ihqgpt` (utils/sampling.py:164-237).
 
-    The reference hard-codes `.cuda()` at sampling.py:184,188; on a CPU-only box that call is
-    neutralised for the duration of the run (tensor stays where it is)."""
+    device='cpu': the reference hard-codes `.cuda()` at sampling.py:184,188; that call is neutralised for the duration
+    of the run (tensor stays where it is) and fp32 is used (`use_fp16=False`).
+    device='cuda': untouched - the reference in its native mode (fp16 autocast when use_fp16=True), model already on
+    the GPU."""
     import torch
     _, ref_sampling = import_reference()
+    if device != "cpu":
+        return ref_sampling.sampling_ihqgpt(model, num_candidates=num_candidates, cond=cond, is_tqdm=False,
+                                            use_fp16=use_fp16, **kw)
     saved = torch.Tensor.cuda
     torch.Tensor.cuda = lambda self, *a, **k: self
     try:
@@ -94,3 +113,20 @@ def reference_sample(model, num_candidates, cond, **kw):
                                             is_tqdm=False, use_fp16=False, **kw)
     finally:
         torch.Tensor.cuda = saved
+
+
+def build_reference_model_random(cfg):
+    """The reference iHQGPT for `cfg` with its OWN random initialisation (`_init_weights`) - what `measure_throughput`
+    times (config only, no checkpoint: measure_throughput/__main__.py:25-31)."""
+    import contextlib
+    import io
+    iHQGPT, _ = import_reference()
+    hp = make_hparams(cfg.embed_dim, cfg.n_layers, cfg.n_heads, n_classes=cfg.n_classes,
+                      ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt)
+    hp_dec = make_hparams(cfg.embed_dim, cfg.n_layers_depth, cfg.n_heads, n_classes=cfg.n_classes,
+                          ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = iHQGPT(vocab_size_top=cfg.vocab_top, vocab_size_bot=cfg.vocab_bot, vocab_size_txt=cfg.vocab_txt,
+                       ratio_bot2top=4, use_cls_cond=(cfg.cond == "cls"), use_txt_cond=(cfg.cond == "txt"),
+                       model_type="parallel", hparams=hp, hparams_dec=hp_dec)
+    return model.eval()

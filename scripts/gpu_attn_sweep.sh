@@ -7,6 +7,6 @@ print("   %.1f img/s  %.1f us/pos  attention in-loop %.2f us avg (%s)  %.0f GB/s
 for cfg in "4 4" "4 2" "8 4" "8 2" "8 3" "12 4" "6 4" "2 2"; do
   set -- $cfg
   echo "=== groups=$1 stages=$2"
-  HQ_ATTN_GROUPS=$1 HQ_ATTM_STAGES=$2 timeout 120 python scripts/attn_phases.py 256 32 2>&1 | grep -E "first_keys|first_item|cta_end" | head -3
-  HQ_ATTN_GROUPS=$1 HQ_ATTM_STAGES=$2 timeout 200 python bench.py --steps 2 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "$show"
+  HQ_DEBUG=1 HQ_ATTN_GROUPS=$1 HQ_ATTM_STAGES=$2 timeout 120 python scripts/attn_phases.py 256 32 2>&1 | grep -E "first_keys|first_item|cta_end" | head -3
+  HQ_DEBUG=1 HQ_ATTN_GROUPS=$1 HQ_ATTM_STAGES=$2 timeout 200 python bench.py --steps 2 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "$show"
 done

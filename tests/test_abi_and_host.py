@@ -112,6 +112,34 @@ def test_sampling_params_marshalling():
     assert c.seed == 5 and c.row_offset == 512 and abs(c.temperature_top - 0.95) < 1e-7
 
 
+def test_sampling_params_top_p_zero_is_keep_first():
+    """The reference's nucleus cut with p = 0 keeps only the first sorted entry (utils/sampling.py:27-31); the ABI reserves
+    0 for "no cut", so the host sends greedy."""
+    from hqtransformer_b200.engine import SamplingParams
+    c = SamplingParams(top_k_top=None, top_p_top=0.0, top_k_bot=50, top_p_bot=0.5).to_c()
+    assert c.top_k_top == 1 and c.top_k_bot == 50 and abs(c.top_p_bot - 0.5) < 1e-7
+
+
+def test_fresh_seed_follows_the_torch_generator():
+    from hqtransformer_b200.models import fresh_seed
+    torch.manual_seed(9)
+    a, b = fresh_seed(), fresh_seed()
+    torch.manual_seed(9)
+    assert (a, b) == (fresh_seed(), fresh_seed()) and a != b and 0 <= a < 2 ** 63
+
+
+def test_measure_throughput_cli_matches_the_reference_keys():
+    """measure_throughput/__main__.py:34-48 fields as key=value; the README's `code-level` spelling is accepted too."""
+    from hqtransformer_b200.measure_throughput import Experiment, parse_cli
+    a = parse_cli(["model_path=x.yaml", "batch_size=32", "code-level=2"])
+    assert (a.model_path, a.batch_size, a.code_levels, a.n_loop, a.warmup, a.top_resolution) == ("x.yaml", 32, 2, 6, 1, 8)
+    assert Experiment().batch_size == 50
+    with pytest.raises(SystemExit):
+        parse_cli(["batch_size=3"])                    # model_path is required
+    with pytest.raises(SystemExit):
+        parse_cli(["model_path=x.yaml", "bogus=1"])
+
+
 def test_graft_entry_build_is_idempotent():
     import __graft_entry__ as G
     G.build()

@@ -121,7 +121,8 @@ def test_step_logits_bf16_wide_batch_vs_oracle(B, force_split, monkeypatch):
     same tolerance as the narrow-batch logits test."""
     import hqtransformer_b200 as H
     if force_split is not None:
-        monkeypatch.setenv("HQ_FORCE_SPLITK", force_split)      # pin the split-K factor of the fc2 GEMMs
+        monkeypatch.setenv("HQ_DEBUG", "1")                    # switches are honoured only in debug mode ...
+        monkeypatch.setenv("HQ_FORCE_SPLITK", force_split)      # ... pin the split-K factor of the fc2 GEMMs
     g, meta = load_golden("small_cls_greedy.npz")
     cfg = cfg_from_meta(meta)
     P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
@@ -164,23 +165,93 @@ def test_bf16_greedy_margin_aware():
     assert not bad.any() or margin[bad].max() < 0.15
 
 
-def test_text_prefix_greedy_bit_exact_fp32():
-    """Config 5 shape (text prefix -> 64-token causal prefill, then cached decode), tiny model, vs the reference."""
+@pytest.mark.parametrize("name", ["tiny_txt_greedy.npz", "asym_txt_greedy.npz"])
+@pytest.mark.parametrize("graph,pdl", [(False, False), (True, False), (False, True), (True, True)])
+def test_text_prefix_greedy_bit_exact_fp32(name, graph, pdl):
+    """Config 5 shape (text prefix -> 64-token causal prefill of B*64 rows, then cached decode over 64..127 keys) vs the
+    reference-made goldens, in every launch mode; the asymmetric model (L != Ld, vocab_top != vocab_bot, 6 heads, B = 2)
+    is the one that caught the cross-position PDL race on the class-conditional path."""
     import hqtransformer_b200 as H
-    g, meta = load_golden("tiny_txt_greedy.npz")
+    g, meta = load_golden(name)
     cfg = cfg_from_meta(meta)
     P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
-    model = build_model(cfg, P, precision="fp32")
+    model = build_model(cfg, P, precision="fp32", use_cuda_graph=graph, use_pdl=pdl)
     ids = torch.from_numpy(g["text_ids"])
-    ct, cb = H.sampling_ihqgpt(model, 1, ids, use_fp16=False, max_seq_len=64, is_tqdm=False, **GREEDY)
-    assert np.array_equal(ct.cpu().numpy(), g["codes_top"]) and np.array_equal(cb.cpu().numpy(), g["codes_bot"])
-    # bf16 path: teacher-forced logits against the emulated oracle
+    for _ in range(2):                                   # a second run on the same ctx must not see the first one's cache
+        ct, cb = H.sampling_ihqgpt(model, 1, ids, use_fp16=False, max_seq_len=64, is_tqdm=False, **GREEDY)
+        assert np.array_equal(ct.cpu().numpy(), g["codes_top"]) and np.array_equal(cb.cpu().numpy(), g["codes_bot"])
+
+
+@pytest.mark.parametrize("name", ["tiny_txt_greedy.npz", "asym_txt_greedy.npz"])
+def test_text_prefix_bf16_logits_and_launch_mode_invariance(name):
+    """bf16 text path: teacher-forced logits against the emulating oracle, and stochastic sampling of a B > 1 batch that
+    must not change across launch modes (graph + PDL vs plain stream launches) or repeats."""
+    import hqtransformer_b200 as H
+    g, meta = load_golden(name)
+    cfg = cfg_from_meta(meta)
+    P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
+    ids = torch.from_numpy(g["text_ids"])
     model16 = build_model(cfg, P, precision="bf16")
     ctg, cbg = torch.from_numpy(g["codes_top"]), torch.from_numpy(g["codes_bot"])
     lg = H.step_logits(model16, ids, ctg, cbg, use_fp16=True).cpu()
     emu = O.step_logits(P, cfg, ids, ctg, cbg, emulate="bf16")
     d = (lg - emu).abs()
     assert d.max() <= 2e-2 and d.mean() <= 2e-3, (d.max(), d.mean())
+    B = 6
+    gen = torch.Generator().manual_seed(3)
+    ids6 = torch.randint(0, cfg.vocab_txt, (B, cfg.ctx_len_txt), generator=gen)
+    kw = dict(top_k_top=50, top_p_top=0.9, top_k_bot=50, top_p_bot=0.9, softmax_temperature=[0.9, 0.9], use_fp16=True,
+              max_seq_len=64, is_tqdm=False, seed=21)
+    plain = build_model(cfg, P, precision="bf16", use_cuda_graph=False, use_pdl=False)
+    ct0, cb0 = H.sampling_ihqgpt(plain, B, ids6, **kw)
+    for graph, pdl in ((True, True), (True, False), (False, True)):
+        m = build_model(cfg, P, precision="bf16", use_cuda_graph=graph, use_pdl=pdl)
+        for _ in range(2):
+            ct, cb = H.sampling_ihqgpt(m, B, ids6, **kw)
+            assert torch.equal(ct, ct0) and torch.equal(cb, cb0), (graph, pdl)
+
+
+def test_default_seed_advances_like_the_reference_generator():
+    """The reference draws with `torch.multinomial` from the global generator: consecutive calls with identical arguments
+    give different samples (sampling_hqmodel.py:180-193 relies on it) and `set_seed` reproduces the whole sequence of
+    calls.  Here the default Philox key of a call is drawn from torch's default generator."""
+    import hqtransformer_b200 as H
+    g, meta = load_golden("tiny_uncond_stochastic.npz")
+    cfg = cfg_from_meta(meta)
+    P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
+    model = build_model(cfg, P, precision="fp32", max_batch=64, max_seq_len=4)
+    kw = dict(use_fp16=False, max_seq_len=4, is_tqdm=False, top_k_top=20, top_k_bot=20)
+    torch.manual_seed(77)
+    a = H.sampling_ihqgpt(model, 64, None, **kw)
+    b = H.sampling_ihqgpt(model, 64, None, **kw)
+    assert not torch.equal(a[0], b[0]), "two default-seed calls returned the same grids"
+    torch.manual_seed(77)
+    a2 = H.sampling_ihqgpt(model, 64, None, **kw)
+    b2 = H.sampling_ihqgpt(model, 64, None, **kw)
+    assert torch.equal(a[0], a2[0]) and torch.equal(a[1], a2[1]) and torch.equal(b[0], b2[0]) and torch.equal(b[1], b2[1])
+    # the per-position API draws ONE key per batch (at past=None) and keeps it for the rest of the batch
+    sos = P["sos"].repeat(8, 1, 1).cuda()
+    torch.manual_seed(5)
+    t0, b0, past = model.sampling_step(sos, None, None, None, use_fp16=False, top_k_top=20, top_k_bot=20, past=None)
+    k0 = model._step_state["seed"]
+    t1, b1, past = model.sampling_step(sos, t0, b0[:, 0], torch.zeros(8, 1, dtype=torch.long), use_fp16=False,
+                                       top_k_top=20, top_k_bot=20, past=past)
+    assert model._step_state["seed"] == k0
+    torch.manual_seed(5)
+    t0b, _, _ = model.sampling_step(sos, None, None, None, use_fp16=False, top_k_top=20, top_k_bot=20, past=None)
+    assert torch.equal(t0, t0b) and model._step_state["seed"] == k0
+
+
+def test_given_top_code_broadcast_row():
+    """hierarchical_ar.py:771-772 accepts a [1, S] given_top_code for a batch of B rows."""
+    import hqtransformer_b200 as H
+    g, meta = load_golden("tiny_cls_greedy.npz")
+    cfg = cfg_from_meta(meta)
+    P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
+    model = build_model(cfg, P, precision="fp32")
+    given = torch.from_numpy(g["codes_top"])[:1]
+    ct, _ = H.sampling_ihqgpt(model, 3, 4, use_fp16=False, max_seq_len=64, is_tqdm=False, given_top_code=given, **GREEDY)
+    assert torch.equal(ct.cpu(), given.expand(3, -1))
 
 
 def test_sampling_step_api_matches_full_loop():

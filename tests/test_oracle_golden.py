@@ -30,6 +30,19 @@ def test_oracle_greedy_codes_and_logits_equal_reference(name):
     assert np.array_equal(cb_s.numpy(), g["codes_bot_scalar_class"])
 
 
+def test_oracle_equals_reference_at_imagenet_l12_size():
+    """BASELINE config 1 at the reference's real scale: ImageNet-L12 architecture (530 M parameters), batch 4, greedy,
+    64 positions - the grids the unmodified reference produced (tests/golden/l12_cls_greedy_b4.npz)."""
+    g, meta = load_golden("l12_cls_greedy_b4.npz")
+    cfg = cfg_from_meta(meta)
+    assert cfg == O.IMAGENET_L12 and meta["min_logit_margin"] >= 1e-4
+    P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
+    labels = torch.from_numpy(g["labels"])
+    ct, cb, lg = O.sample(P, cfg, labels, len(labels), return_logits=True, **GREEDY)
+    assert np.array_equal(ct.numpy(), g["codes_top"]) and np.array_equal(cb.numpy(), g["codes_bot"])
+    assert np.abs(lg[:, meta["logit_positions"]].numpy() - g["logits"]).max() < 1e-5
+
+
 @pytest.mark.parametrize("name", ["tiny_txt_greedy.npz", "asym_txt_greedy.npz"])
 def test_oracle_text_prefix_equals_reference(name):
     g, meta = load_golden(name)
