@@ -6,7 +6,7 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libhqgraft.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 HQ_OK = 0
 HQ_COND_CLS, HQ_COND_TXT, HQ_COND_UNCOND = 0, 1, 2
@@ -17,7 +17,7 @@ HQ_F32, HQ_BF16, HQ_F16 = 0, 1, 2
 class HQConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "embed_dim", "n_heads", "n_layers", "n_layers_depth", "vocab_top", "vocab_bot", "vocab_txt", "n_classes",
-        "ctx_len_img", "ctx_len_txt", "cond_kind", "precision", "max_seq_len", "use_cuda_graph", "use_pdl")]
+        "ctx_len_img", "ctx_len_txt", "cond_kind", "precision", "max_seq_len", "use_cuda_graph", "use_pdl", "use_chain")]
 
 
 class HQSamplingParams(C.Structure):
@@ -48,6 +48,7 @@ PROTOTYPES = {
     "hq_run_host": (C.c_int, [C.c_void_p, C.POINTER(HQRunArgs)]),
     "hq_last_launch_count": (C.c_int64, [C.c_void_p]),
     "hq_device_bytes": (C.c_size_t, [C.c_void_p]),
+    "hq_chain_launch_count": (C.c_int64, [C.c_void_p]),
     "hq_debug_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                              C.c_void_p]),
     "hq_debug_philox": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
@@ -57,6 +58,8 @@ PROTOTYPES = {
                                      C.c_int, C.c_int, C.c_void_p]),
     "hq_debug_attention_phases": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int,
                                             C.POINTER(C.c_int), C.c_void_p]),
+    "hq_debug_chain_phases": (C.c_int, [C.c_void_p, C.POINTER(HQRunArgs), C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64),
+                                        C.c_int, C.POINTER(C.c_int)]),
     "hq_bench_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "hq_trace_run": (C.c_int, [C.c_void_p, C.POINTER(HQRunArgs), C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p, C.c_int,
                                C.POINTER(C.c_int)]),

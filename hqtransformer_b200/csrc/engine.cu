@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "chain.cuh"
 
 using namespace hq;
 
@@ -53,11 +54,13 @@ struct Weight {          // a GEMM weight [N, K] in the precision's storage type
   int N = 0, K = 0;
   CUtensorMap map;       // bf16 only: [N, K], box {64, 64}, SWIZZLE_128B (single-CTA kernel)
   PairMaps mapp;         // bf16 only: box {64, BN/2} per pair-tile width BN (CTA-pair kernel: one load per stage per CTA)
+  int map_idx = -1;      // index of mapp.m[0] in the ctx's device tensor-map table (chain kernel)
 };
 struct ABuf {            // a GEMM A operand buffer [rows_pad, K]
   void* ptr = nullptr;
   int rows = 0, K = 0;
   CUtensorMap map;       // bf16 only: box {64, 128}
+  int map_idx = -1;      // index in the ctx's device tensor-map table (chain kernel)
 };
 struct BlockW {
   Weight qkv, proj, fc1, fc2;
@@ -93,6 +96,9 @@ struct DebugSwitches {
   int trace_pdl = 0;           // HQ_TRACE_PDL: keep PDL on while tracing
   int bench_splits = 0;        // HQ_BENCH_SPLITS (hq_bench_gemm_shape)
   int force_bn = 0;            // hq_debug_gemm: pinned tile width (0 = heuristic, -64 / -128 = single-CTA kernel)
+  int no_chain = 0;            // HQ_NO_CHAIN: one kernel per op even where the persistent chain kernel applies
+  int chain_min_batch = 0;     // HQ_CHAIN_MIN_BATCH: smallest batch that takes the chain kernel (default 129)
+  int chain_no_l2pf = 0;       // HQ_CHAIN_NO_L2PF: chain kernel without the L2 prefetch of later weight tiles
 };
 
 static int env_int(const char* name) {
@@ -117,6 +123,9 @@ static DebugSwitches read_debug_switches() {
   d.force_splitk = env_int("HQ_FORCE_SPLITK");
   d.trace_pdl = getenv("HQ_TRACE_PDL") != nullptr;
   d.bench_splits = env_int("HQ_BENCH_SPLITS");
+  d.no_chain = getenv("HQ_NO_CHAIN") != nullptr;
+  d.chain_min_batch = env_int("HQ_CHAIN_MIN_BATCH");
+  d.chain_no_l2pf = getenv("HQ_CHAIN_NO_L2PF") != nullptr;
   return d;
 }
 
@@ -180,6 +189,27 @@ struct hq_ctx {
   std::string tag_suffix;   // shape annotation appended to the next launch tag (tracing only)
   DebugSwitches dbg = read_debug_switches();
   uint64_t graph_clock = 0;   // LRU stamp source of the graph cache
+
+  // ---- persistent op-chain kernel (chain.cuh) ----
+  bool chain_ok = false;               // kernel attributes set and enough CTA pairs co-resident
+  int chain_grid = 0;                  // CTAs of every chain launch (2 x co-resident pairs)
+  CUtensorMap* d_maps = nullptr;       // tensor-map table: A buffers, then six pair maps per weight (rebuilt by reserve)
+  ChainOp* d_ops = nullptr;            // arena of op tables, deduplicated by content
+  int ops_cap = 0, ops_used = 0;
+  std::map<std::string, int> chain_index;   // op-table bytes -> first op in d_ops
+  unsigned long long* d_chain_bar = nullptr;
+  unsigned long long chain_epoch = 0;  // arrivals of the chain launches enqueued so far in this run
+  enum { CHAIN_OFF = 0, CHAIN_PLAN = 1, CHAIN_RUN = 2 };
+  int chain_mode = CHAIN_OFF;          // PLAN: build + upload op tables, launch nothing (done before graph capture)
+  bool recording = false;              // ops are appended to `rec` instead of being launched
+  std::vector<ChainOp> rec;
+  std::vector<std::string> rec_tags;
+  int rec_flags = 0;                   // flags of the next recorded GEMM op (CH_F_T0_RT)
+  ChainRt chain_rt;                    // t0 / pos / S of the position being recorded
+  std::vector<char> trace_chain_cont;  // tracing: entry i is op > 0 of a chain launch (its start is entry i-1's end)
+  int64_t chain_launches = 0, chain_ops = 0;
+  int chain_launches_run = 0;          // chain launches of the current run (selects the instrumented one)
+  int phase_launch = -1, phase_op = -1;   // hq_debug_chain_phases: which launch of the run / which of its ops is stamped
 };
 
 static void set_err(hq_ctx* ctx, const char* fmt, ...) {
@@ -401,6 +431,9 @@ static void free_activations(hq_ctx* ctx) {
   for (void* p : ctx->act_allocs) cudaFree(p);
   ctx->act_allocs.clear();
   ctx->act_bytes = 0;
+  ctx->d_maps = nullptr;          // (an activation allocation) the op tables point into the freed buffers
+  ctx->chain_index.clear();
+  ctx->ops_used = 0;
 }
 
 // batch-sized state: activations, KV cache [L][B][Tc][D] x2, depth KV [Ld][B][5][D] x2, code buffers
@@ -475,6 +508,25 @@ static int reserve_alloc(hq_ctx* ctx, int max_batch) {
   if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->codes_bot), static_cast<size_t>(B) * ctx->Smax * 32))) return rc;
   if ((rc = alloc_f32(ctx, &ctx->sos_override, static_cast<size_t>(Mx) * D))) return rc;
   if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->d_sp), sizeof(hq_sampling_params)))) return rc;
+  if (ctx->bf16) {
+    // tensor-map table of the chain kernel: the three A buffers, then the six pair-tile maps of every GEMM weight
+    std::vector<CUtensorMap> table;
+    ABuf* abufs[3] = {&ctx->h, &ctx->att, &ctx->mlp};
+    for (ABuf* a : abufs) {
+      a->map_idx = static_cast<int>(table.size());
+      table.push_back(a->map);
+    }
+    auto add_w = [&](Weight& w) {
+      w.map_idx = static_cast<int>(table.size());
+      for (int i = 0; i < 6; ++i) table.push_back(w.mapp.m[i]);
+    };
+    for (auto& b : ctx->blocks) { add_w(b.qkv); add_w(b.proj); add_w(b.fc1); add_w(b.fc2); }
+    for (auto& b : ctx->depths) { add_w(b.qkv); add_w(b.proj); add_w(b.fc1); add_w(b.fc2); }
+    add_w(ctx->head_top);
+    add_w(ctx->head_bot);
+    if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->d_maps), table.size() * sizeof(CUtensorMap)))) return rc;
+    HQ_CUDA(ctx, cudaMemcpy(ctx->d_maps, table.data(), table.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  }
   return HQ_OK;
 }
 
@@ -527,6 +579,26 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
   HQ_CUDA(ctx, cudaMemset(ctx->att_sched, 0, 16));
   HQ_CUDA(ctx, cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
   HQ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  if (ctx->bf16 && cfg->use_chain && !ctx->dbg.no_chain) {
+    // persistent chain kernel: every launch uses the same grid of co-resident CTA pairs (its ops are separated by a
+    // grid barrier, so a CTA that is not resident would deadlock the rest)
+    if ((rc = set_smem(ctx, chain_kernel, CH_SMEM_BYTES))) return rc;
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(2 * 74);
+    lc.blockDim = dim3(CH_THREADS);
+    lc.dynamicSmemBytes = CH_SMEM_BYTES;
+    int clusters = 0;
+    HQ_CUDA(ctx, cudaOccupancyMaxActiveClusters(&clusters, chain_kernel, &lc));
+    if (clusters > ctx->num_sms / 2) clusters = ctx->num_sms / 2;
+    if (clusters >= 32) {
+      ctx->chain_grid = 2 * clusters;
+      ctx->ops_cap = 2048;
+      if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->d_ops), sizeof(ChainOp) * ctx->ops_cap))) return rc;
+      if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->d_chain_bar), 256))) return rc;
+      ctx->chain_ok = true;
+    }
+  }
 
   // ---- parameters ----
   ctx->blocks.resize(ctx->L);
@@ -697,6 +769,7 @@ extern "C" int hq_reserve_batch(hq_ctx* ctx, int max_batch) {
 extern "C" int hq_max_batch(const hq_ctx* ctx) { return ctx ? ctx->max_batch : 0; }
 
 extern "C" int64_t hq_last_launch_count(const hq_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+extern "C" int64_t hq_chain_launch_count(const hq_ctx* ctx) { return ctx ? ctx->chain_launches : 0; }
 extern "C" size_t hq_device_bytes(const hq_ctx* ctx) { return ctx ? ctx->device_bytes + ctx->act_bytes : 0; }
 
 // ------------------------------------------------------------------------------------------------
@@ -711,6 +784,10 @@ extern "C" size_t hq_device_bytes(const hq_ctx* ctx) { return ctx ? ctx->device_
 template <typename... KArgs, typename... Args>
 static void launch_k(hq_ctx* ctx, cudaStream_t st, const char* tag, void (*kernel)(int, KArgs...), dim3 grid, dim3 block,
                      size_t smem, Args&&... args) {
+  if (ctx->chain_mode == hq_ctx::CHAIN_PLAN) {     // planning pass of the chain kernel: op tables only
+    ctx->tag_suffix.clear();
+    return;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -750,6 +827,90 @@ static void launch_k(hq_ctx* ctx, cudaStream_t st, const char* tag, void (*kerne
   if (e != cudaSuccess && ctx->launch_err == cudaSuccess) ctx->launch_err = e;
 }
 
+// ------------------------------------------------------------------------------------------------
+// persistent chain kernel: op recording and launch (chain.cuh)
+// ------------------------------------------------------------------------------------------------
+static bool chain_enabled(const hq_ctx* ctx, int B) {
+  const int min_b = ctx->dbg.chain_min_batch > 0 ? ctx->dbg.chain_min_batch : 129;   // every GEMM on CTA-pair tiles
+  return ctx->chain_ok && ctx->d_maps != nullptr && B >= min_b && ctx->D <= LN_MAXV * LN_THREADS * 4 &&
+         ctx->chain_mode != hq_ctx::CHAIN_OFF;
+}
+
+static ChainOp* chain_push(hq_ctx* ctx, int kind, const std::string& tag) {
+  ChainOp op;
+  memset(&op, 0, sizeof(op));
+  op.kind = kind;
+  ctx->rec.push_back(op);
+  ctx->rec_tags.push_back(tag);
+  return &ctx->rec.back();
+}
+
+static void chain_begin(hq_ctx* ctx, int t0, int pos, int S) {
+  ctx->recording = true;
+  ctx->rec.clear();
+  ctx->rec_tags.clear();
+  ctx->chain_rt.t0 = t0;
+  ctx->chain_rt.pos = pos;
+  ctx->chain_rt.S = S;
+}
+
+// Launches the ops recorded so far as ONE chain_kernel launch (recording stays on: the caller may go on appending).
+// PLAN pass: the op table is deduplicated by content and uploaded; RUN pass: it must already be on the device.
+static void chain_flush(hq_ctx* ctx, cudaStream_t st) {
+  const int n = static_cast<int>(ctx->rec.size());
+  if (n == 0) return;
+  const std::string key(reinterpret_cast<const char*>(ctx->rec.data()), sizeof(ChainOp) * static_cast<size_t>(n));
+  auto it = ctx->chain_index.find(key);
+  if (ctx->chain_mode == hq_ctx::CHAIN_PLAN) {
+    if (it == ctx->chain_index.end()) {
+      if (ctx->ops_used + n > ctx->ops_cap) {
+        if (ctx->launch_err == cudaSuccess) ctx->launch_err = cudaErrorMemoryAllocation;
+      } else {
+        cudaError_t e = cudaMemcpy(ctx->d_ops + ctx->ops_used, ctx->rec.data(), sizeof(ChainOp) * static_cast<size_t>(n),
+                                   cudaMemcpyHostToDevice);
+        if (e != cudaSuccess && ctx->launch_err == cudaSuccess) ctx->launch_err = e;
+        ctx->chain_index.emplace(key, ctx->ops_used);
+        ctx->ops_used += n;
+      }
+    }
+  } else {
+    if (it == ctx->chain_index.end()) {
+      if (ctx->launch_err == cudaSuccess) ctx->launch_err = cudaErrorInvalidValue;   // not planned: a host logic error
+    } else {
+      ChainRt rt = ctx->chain_rt;
+      rt.bar = ctx->d_chain_bar;
+      rt.bar_base = ctx->chain_epoch;
+      rt.trace_base = -1;
+      rt.no_l2_prefetch = ctx->dbg.chain_no_l2pf;
+      rt.phase_op = (ctx->phase_launch >= 0 && ctx->chain_launches_run == ctx->phase_launch) ? ctx->phase_op : -1;
+      ++ctx->chain_launches_run;
+      if (ctx->tracing && static_cast<int>(ctx->trace_tags.size()) + n <= ctx->trace_cap) {
+        rt.trace_base = static_cast<int>(ctx->trace_tags.size());
+        for (int i = 0; i < n; ++i) {
+          ctx->trace_tags.push_back(ctx->rec_tags[i]);
+          ctx->trace_chain_cont.resize(ctx->trace_tags.size(), 0);
+          ctx->trace_chain_cont.back() = i > 0 ? 1 : 0;
+        }
+      }
+      const bool was_tracing = ctx->tracing;
+      ctx->tracing = false;                        // the launch itself takes no timeline entry: its ops do
+      launch_k(ctx, st, "chain", chain_kernel, dim3(ctx->chain_grid), dim3(CH_THREADS), CH_SMEM_BYTES,
+               static_cast<const ChainOp*>(ctx->d_ops + it->second), n, static_cast<const CUtensorMap*>(ctx->d_maps), rt);
+      ctx->tracing = was_tracing;
+      ctx->chain_epoch += static_cast<unsigned long long>(n) * static_cast<unsigned long long>(ctx->chain_grid);
+      ++ctx->chain_launches;
+      ctx->chain_ops += n;
+    }
+  }
+  ctx->rec.clear();
+  ctx->rec_tags.clear();
+}
+
+static void chain_end(hq_ctx* ctx, cudaStream_t st) {
+  chain_flush(ctx, st);
+  ctx->recording = false;
+}
+
 template <int EPI>
 static const char* gemm_tag(int M) {
   (void)M;
@@ -787,9 +948,26 @@ static int pick_pair_bn(int M, int N, int K) {
 template <int EPI>
 static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mW64,
                       const PairMaps& mWp, int w_row_off, int M, int N, int K, const EpiParams<bf16>& ep,
-                      int splits = 1, int bn_hint = 0) {
+                      int splits = 1, int bn_hint = 0, int ia = -1, int iw = -1) {
   int bn = ctx->dbg.force_bn ? ctx->dbg.force_bn : bn_hint;
   if (bn == 0) bn = (M > 128) ? pick_pair_bn(M, N, K) : 0;
+  if (ctx->recording) {
+    // an op of the persistent chain kernel: CTA-pair tiles only (chain_enabled guarantees M > 128)
+    if (bn <= 0 || N % bn != 0 || ia < 0 || iw < 0 || (K / 64) % splits != 0) {
+      if (ctx->launch_err == cudaSuccess) ctx->launch_err = cudaErrorInvalidValue;
+      return;
+    }
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%s:%dx%dx%d:s%d", gemm_tag<EPI>(M), M, N, K, splits);
+    ChainOp* op = chain_push(ctx, CH_OP_GEMM, buf);
+    op->flags = ctx->rec_flags;
+    op->map_a = ia;
+    op->map_w = iw + PairMaps::index(bn);
+    op->M = M; op->N = N; op->K = K; op->bn = bn; op->splits = splits; op->epi = EPI; op->w_row_off = w_row_off;
+    op->ep = ep;
+    if (op->flags & CH_F_T0_RT) op->ep.t0 = 0;
+    return;
+  }
   if (ctx->tracing) {
     char buf[48];
     snprintf(buf, sizeof(buf), ":%dx%dx%d:s%d", M, N, K, splits);
@@ -833,7 +1011,7 @@ static void gemm_f32(hq_ctx* ctx, cudaStream_t st, const float* A, const float* 
 template <int EPI>
 static void gemm_any(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
                      const EpiParams<bf16>& ep) {
-  gemm_bf16<EPI>(ctx, st, A.map, W.map, W.mapp, w_row_off, M, N, K, ep);
+  gemm_bf16<EPI>(ctx, st, A.map, W.map, W.mapp, w_row_off, M, N, K, ep, 1, 0, A.map_idx, W.map_idx);
 }
 template <int EPI>
 static void gemm_any(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
@@ -854,6 +1032,15 @@ template <typename AT>
 static void layernorm_act(hq_ctx* ctx, cudaStream_t st, float* x, const float* g, const float* b, AT* out, int rows,
                           Fold* fold = nullptr) {
   Fold f = fold ? *fold : Fold();
+  if (ctx->recording) {
+    ChainOp* op = chain_push(ctx, CH_OP_LN, "layernorm");
+    op->flags = sizeof(AT) == 4 ? CH_F_OUT_F32 : 0;
+    op->x = x; op->gamma = g; op->beta = b; op->add = nullptr; op->out = out;
+    op->rows = rows; op->in_mul = 1; op->in_off = 0; op->D = ctx->D;
+    op->fold = f.partial; op->n_fold = f.n; op->fold_stride = f.stride; op->fold_bias = f.bias;
+    if (fold) *fold = Fold();
+    return;
+  }
   // the lean instantiation (<= 3 partial sums in registers) unless the pending split is wider
   auto kern = f.n > 3 ? layernorm_kernel<AT, LN_MAXFOLD> : layernorm_kernel<AT, 3>;
   launch_k(ctx, st, "layernorm", kern, dim3(rows), dim3(LN_THREADS), 0, x, g, b, nullptr, out, rows,
@@ -932,6 +1119,18 @@ static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, co
                       int t_stride, int kbase, int causal) {
   int CH = 0, hpc = 0, groups = 0;
   size_t smem = 0;
+  if (ctx->recording && sizeof(AT) == 2 && !causal && kbase <= ATT_DEPTH_KEYS && Tq == 4) {
+    ChainOp* op = chain_push(ctx, CH_OP_ATTN4, "attention_depth4");
+    op->q = reinterpret_cast<const bf16*>(q); op->kc = reinterpret_cast<const bf16*>(K);
+    op->vc = reinterpret_cast<const bf16*>(V); op->att = reinterpret_cast<bf16*>(out);
+    op->B = M / 4; op->n_heads = ctx->nh; op->D = ctx->D; op->t_stride = t_stride; op->n_keys = kbase;
+    return;
+  }
+  // any other attention is a kernel of its own: the ops recorded so far go out first, recording resumes after it
+  const bool resume = ctx->recording;
+  if (resume) chain_flush(ctx, st);
+  struct Resume { hq_ctx* c; bool on; ~Resume() { c->recording = on; } } resume_guard{ctx, resume};
+  ctx->recording = false;
   if (Tq == 1 && !causal && !ctx->dbg.attn_generic && attn_decode_plan<AT>(ctx, &CH, &hpc, &groups, &smem)) {
     // spatial decode: (image, head group) work items, K/V streamed through shared memory by bulk async copies
     if (ctx->tracing) ctx->tag_suffix = ":t" + std::to_string(kbase) + ":B" + std::to_string(M);
@@ -979,7 +1178,7 @@ static void gemm_fc2_split(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const We
   EpiParams<bf16> e;
   memset(&e, 0, sizeof(e));
   e.outf = ctx->splitk_ws; e.ldo = N; e.split_stride = static_cast<size_t>(ctx->ws_rows) * N;
-  gemm_bf16<EPI_F32>(ctx, st, A.map, W.map, W.mapp, 0, M, N, K, e, splits, bn);
+  gemm_bf16<EPI_F32>(ctx, st, A.map, W.map, W.mapp, 0, M, N, K, e, splits, bn, A.map_idx, W.map_idx);
 }
 static void gemm_fc2_split(hq_ctx*, cudaStream_t, const ABuf&, const Weight&, int, int, int, int, int, float*) {}
 
@@ -1075,7 +1274,9 @@ static void run_block(hq_ctx* ctx, cudaStream_t st, const BlockW& w, float* x, i
     gemm_any<EPI_QKV>(ctx, st, ctx->h, w.qkv, D, M, 2 * D, D, ep);
   } else {
     ep.bias = w.bqkv; ep.sec0 = 0; ep.vdup = nullptr;
+    if (mode == 0) ctx->rec_flags = CH_F_T0_RT;     // chain op: the cache slot is a per-launch value, not part of the table
     gemm_any<EPI_QKV>(ctx, st, ctx->h, w.qkv, 0, M, 3 * D, D, ep);
+    ctx->rec_flags = 0;
     attention<AT>(ctx, st, q, kdst, vdst, att, M, rpb, t_stride, n_keys_base, causal);
   }
   gemm_resid<AT>(ctx, st, ctx->att, w.proj, w.bproj, x, M, D, D, rpb, fold);
@@ -1132,15 +1333,26 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
 
   // ---- spatial transformer: L blocks over the KV cache ----
   const int tok = (pos == 0) ? 0 : T0 + pos - 1;     // cache slot of this position's (first) token
+  // persistent chain kernel: every run of ops between two cache attentions (and the whole depth transformer) is one launch
+  const bool chain = sizeof(AT) == 2 && !prefill && chain_enabled(ctx, B);
+  if (chain) chain_begin(ctx, tok, pos, S);
   for (int l = 0; l < ctx->L; ++l) {
     if (prefill) run_block<AT>(ctx, st, ctx->blocks[l], ctx->x, M, 0, kc + l * lstride, vc + l * lstride, T0, Tc, 0, 0, 1, &fold_x);
     else run_block<AT>(ctx, st, ctx->blocks[l], ctx->x, M, 0, kc + l * lstride, vc + l * lstride, 1, Tc, tok, tok + 1, 0, &fold_x);
   }
   // ---- hs = ln_f(x) (last prefix row for text), depth start token y = hs + sos_depth ----
-  launch_k(ctx, st, "layernorm_f", fold_x.n > 3 ? layernorm_kernel<float, LN_MAXFOLD> : layernorm_kernel<float, 3>, dim3(B),
-           dim3(LN_THREADS), 0, ctx->x, ctx->lnf_g, ctx->lnf_b,
-           ctx->sos_depth, ctx->yd, B, D, prefill ? T0 : 1, prefill ? T0 - 1 : 0, fold_x.partial, fold_x.n, fold_x.stride,
-           fold_x.bias);
+  if (ctx->recording) {
+    ChainOp* op = chain_push(ctx, CH_OP_LN, "layernorm_f");
+    op->flags = CH_F_OUT_F32;
+    op->x = ctx->x; op->gamma = ctx->lnf_g; op->beta = ctx->lnf_b; op->add = ctx->sos_depth; op->out = ctx->yd;
+    op->rows = B; op->in_mul = 1; op->in_off = 0; op->D = D;
+    op->fold = fold_x.partial; op->n_fold = fold_x.n; op->fold_stride = fold_x.stride; op->fold_bias = fold_x.bias;
+  } else {
+    launch_k(ctx, st, "layernorm_f", fold_x.n > 3 ? layernorm_kernel<float, LN_MAXFOLD> : layernorm_kernel<float, 3>, dim3(B),
+             dim3(LN_THREADS), 0, ctx->x, ctx->lnf_g, ctx->lnf_b,
+             ctx->sos_depth, ctx->yd, B, D, prefill ? T0 : 1, prefill ? T0 - 1 : 0, fold_x.partial, fold_x.n, fold_x.stride,
+             fold_x.bias);
+  }
   fold_x = Fold();
 
   // ---- depth pass 0 -> top logits ----
@@ -1158,11 +1370,18 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
   sa.logits = ctx->logits; sa.ldl = ctx->Vmax; sa.V = ctx->Vt; sa.R = B; sa.rows_per_b = 1; sa.slot0 = 0;
   sa.sp = ctx->d_sp; sa.pos = pos; sa.S = S; sa.codes_top = ctx->codes_top; sa.codes_bot = ctx->codes_bot;
   sa.forced = f.forced_top; sa.logits_out = f.logits_out; sa.Vmax = ctx->Vmax;
+  if (chain) chain_end(ctx, st);
   if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
 
   // ---- depth pass 1 -> 4 bottom logits ----
-  launch_k(ctx, st, "embed_depth", embed_depth_kernel, dim3(B), dim3(eb), 0, ctx->yd, ctx->E_top_depth, ctx->P_depth, ctx->codes_top,
-           S, pos, D);
+  if (chain) {
+    chain_begin(ctx, tok, pos, S);
+    ChainOp* op = chain_push(ctx, CH_OP_EMBED_DEPTH, "embed_depth");
+    op->y = ctx->yd; op->E = ctx->E_top_depth; op->P = ctx->P_depth; op->codes_top = ctx->codes_top; op->B = B; op->D = D;
+  } else {
+    launch_k(ctx, st, "embed_depth", embed_depth_kernel, dim3(B), dim3(eb), 0, ctx->yd, ctx->E_top_depth, ctx->P_depth,
+             ctx->codes_top, S, pos, D);
+  }
   for (int l = 0; l < ctx->Ld; ++l)
     run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, 4 * B, 2, kd + l * dstride, vd + l * dstride, 4, 5, 1, 5, 0, &fold_y);
   layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnb_g, ctx->lnb_b, h, 4 * B, &fold_y);
@@ -1173,6 +1392,7 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
     gemm_any<EPI_F32>(ctx, st, ctx->h, ctx->head_bot, 0, 4 * B, ctx->Vb, D, e);
   }
   sa.V = ctx->Vb; sa.R = 4 * B; sa.rows_per_b = 4; sa.slot0 = 1; sa.forced = f.forced_bot;
+  if (chain) chain_end(ctx, st);
   if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
 }
 
@@ -1253,10 +1473,47 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
   ctx->launches = 0;
   ctx->launch_err = cudaSuccess;
   const bool use_graph = ctx->cfg.use_cuda_graph && f.logits_out == nullptr;
+  // persistent chain kernel: its grid-barrier counter restarts at zero with every run (the captured launches carry the
+  // absolute arrival counts they start from), and the op tables are built by a planning pass BEFORE any capture
+  ctx->chain_mode = hq_ctx::CHAIN_OFF;
+  ctx->recording = false;
+  ctx->chain_epoch = 0;
+  ctx->chain_launches_run = 0;
+  if (ctx->chain_ok) {
+    ctx->chain_mode = hq_ctx::CHAIN_RUN;
+    if (chain_enabled(ctx, B)) HQ_CUDA(ctx, cudaMemsetAsync(ctx->d_chain_bar, 0, 8, st));
+    else ctx->chain_mode = hq_ctx::CHAIN_OFF;
+  }
+  auto plan_chains = [&]() {
+    if (ctx->chain_mode != hq_ctx::CHAIN_RUN) return;
+    ctx->chain_mode = hq_ctx::CHAIN_PLAN;
+    run_range(ctx, st, B, S, a->pos_begin, a->pos_end, f);
+    if (ctx->launch_err == cudaErrorMemoryAllocation) {
+      // op-table arena full (many distinct batch sizes): drop every table and every graph that points at one, re-plan
+      cudaDeviceSynchronize();
+      for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second.exec);
+      ctx->graphs.clear();
+      ctx->chain_index.clear();
+      ctx->ops_used = 0;
+      ctx->launch_err = cudaSuccess;
+      ctx->recording = false;
+      run_range(ctx, st, B, S, a->pos_begin, a->pos_end, f);
+    }
+    ctx->chain_mode = hq_ctx::CHAIN_RUN;
+    ctx->recording = false;
+    ctx->chain_epoch = 0;
+    ctx->chain_launches_run = 0;
+    ctx->launches = 0;
+  };
   if (use_graph) {
     GraphKey key{B, S, a->pos_begin, a->pos_end, f.forced_top, f.forced_bot, f.sos_override, ctx->tracing ? 1 : 0};
     auto it = ctx->graphs.find(key);
     if (it == ctx->graphs.end()) {
+      plan_chains();
+      if (ctx->launch_err != cudaSuccess) {
+        set_err(ctx, "chain planning failed: %s", cudaGetErrorString(ctx->launch_err));
+        return HQ_ERR_CUDA;
+      }
       cudaGraph_t graph = nullptr;
       HQ_CUDA(ctx, cudaStreamBeginCapture(ctx->own_stream, cudaStreamCaptureModeThreadLocal));
       run_range(ctx, ctx->own_stream, B, S, a->pos_begin, a->pos_end, f);
@@ -1288,6 +1545,7 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
     HQ_CUDA(ctx, cudaGraphLaunch(it->second.exec, st));
     ctx->last_launches = it->second.launches;
   } else {
+    plan_chains();
     run_range(ctx, st, B, S, a->pos_begin, a->pos_end, f);
     ctx->last_launches = ctx->launches;
     if (ctx->launch_err != cudaSuccess) {
@@ -1742,6 +2000,43 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
   return HQ_OK;
 }
 
+// One hq_run as plain stream launches in which op `op_idx` of the `launch_idx`-th chain launch stamps %globaltimer per CTA:
+// out_ns[8*c + p], p = 0 op begins, 1 grid barrier seen, 2 epilogue warps released, 3 work done, 4 proxy fence done,
+// 5 all epilogue warps done, 6 arrival posted.  The op's tag (e.g. "layernorm", "gemm_qkv:...") is returned in `tag`.
+extern "C" int hq_debug_chain_phases(hq_ctx* ctx, const hq_run_args* args, void* stream, int launch_idx, int op_idx,
+                                     unsigned long long* out_ns, int max_ctas, int* n_ctas) {
+  if (!ctx || !args || !out_ns || !n_ctas || max_ctas < 1 || launch_idx < 0 || op_idx < 0) return HQ_ERR_INVALID;
+  HQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* dev = nullptr;
+  const size_t bytes = static_cast<size_t>(max_ctas) * 8 * sizeof(unsigned long long);
+  HQ_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&dev), bytes));
+  HQ_CUDA(ctx, cudaMemset(dev, 0, bytes));
+  HQ_CUDA(ctx, cudaMemcpyToSymbol(g_hq_chain_phase, &dev, sizeof(dev)));
+  const int saved_graph = ctx->cfg.use_cuda_graph;
+  ctx->cfg.use_cuda_graph = 0;
+  ctx->phase_launch = launch_idx;
+  ctx->phase_op = op_idx;
+  int rc = run_impl(ctx, args, st, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);
+  ctx->phase_launch = ctx->phase_op = -1;
+  ctx->cfg.use_cuda_graph = saved_graph;
+  cudaError_t e = cudaStreamSynchronize(st);
+  unsigned long long* null_ptr = nullptr;
+  cudaMemcpyToSymbol(g_hq_chain_phase, &null_ptr, sizeof(null_ptr));
+  if (rc == HQ_OK && e == cudaSuccess) e = cudaMemcpy(out_ns, dev, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (rc != HQ_OK) return rc;
+  if (e != cudaSuccess) {
+    set_err(ctx, "hq_debug_chain_phases: %s", cudaGetErrorString(e));
+    return HQ_ERR_CUDA;
+  }
+  int n = 0;
+  for (int i = 0; i < max_ctas; ++i)
+    if (out_ns[static_cast<size_t>(i) * 8] != 0) n = i + 1;
+  *n_ctas = n;
+  return HQ_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // hq_trace_run: one hq_run with the per-kernel timeline recorded on the device (%globaltimer, ns).
 // out_ns[2*i], out_ns[2*i+1] = first-CTA start / last-CTA end of launch i (in launch order); tags[i*24..] = kernel tag.
@@ -1767,6 +2062,7 @@ extern "C" int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, 
   ctx->tracing = true;
   ctx->trace_cap = max_entries;
   ctx->trace_tags.clear();
+  ctx->trace_chain_cont.clear();
   int rc = run_impl(ctx, args, st, cudaMemcpyDeviceToDevice, cudaMemcpyDeviceToDevice);
   ctx->tracing = false;
   ctx->use_pdl = saved_pdl;
@@ -1778,6 +2074,10 @@ extern "C" int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, 
   if (rc == HQ_OK) {
     const int n = static_cast<int>(ctx->trace_tags.size());
     cudaMemcpy(out_ns, dbuf, sizeof(unsigned long long) * 2 * n, cudaMemcpyDeviceToHost);
+    // ops of a chain launch: op i's span runs from the completion of op i-1 (grid barrier included) to its own
+    ctx->trace_chain_cont.resize(static_cast<size_t>(n), 0);
+    for (int i = 1; i < n; ++i)
+      if (ctx->trace_chain_cont[i]) out_ns[2 * i] = out_ns[2 * (i - 1) + 1];
     for (int i = 0; i < n; ++i) {
       strncpy(tags + static_cast<size_t>(i) * 48, ctx->trace_tags[i].c_str(), 47);
       tags[static_cast<size_t>(i) * 48 + 47] = 0;

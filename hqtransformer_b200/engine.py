@@ -53,7 +53,7 @@ class Engine:
                  vocab_bot: int, vocab_txt: int = 16384, n_classes: int = 1000, ctx_len_img: int = 256,
                  ctx_len_txt: int = 64, cond: str = "cls", precision: str = "bf16", max_seq_len: int = 64,
                  max_batch: int = 16, device: Union[int, str, torch.device] = 0, use_cuda_graph: bool = True,
-                 use_pdl: bool = True):
+                 use_pdl: bool = True, use_chain: bool = False):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
@@ -70,7 +70,7 @@ class Engine:
                        cond_kind={"cls": _lib.HQ_COND_CLS, "txt": _lib.HQ_COND_TXT, "uncond": _lib.HQ_COND_UNCOND}[cond],
                        precision={"bf16": _lib.HQ_PREC_BF16, "fp32": _lib.HQ_PREC_FP32}[precision],
                        max_seq_len=max_seq_len, use_cuda_graph=1 if use_cuda_graph else 0,
-                       use_pdl=1 if use_pdl else 0)
+                       use_pdl=1 if use_pdl else 0, use_chain=1 if use_chain else 0)
         check(self._lib.hq_create(C.byref(cfg), self.device.index, int(max_batch), C.byref(self._ctx)), None, "hq_create")
 
     # ---- lifetime ----
@@ -99,6 +99,11 @@ class Engine:
     @property
     def last_launch_count(self) -> int:
         return self._lib.hq_last_launch_count(self._ctx)
+
+    @property
+    def chain_launches(self) -> int:
+        """Launches of the persistent chain kernel since the ctx was created (0: every op ran as its own kernel)."""
+        return self._lib.hq_chain_launch_count(self._ctx)
 
     # ---- parameters ----
     def load_param(self, name: str, t: torch.Tensor) -> None:
@@ -186,6 +191,21 @@ class Engine:
         st = torch.cuda.current_stream(self.device).cuda_stream
         check(self._lib.hq_debug_attention_phases(self._ctx, batch, n_keys, warm, buf, max_ctas, C.byref(n), C.c_void_p(st)),
               self._ctx, "hq_debug_attention_phases")
+        return np.frombuffer(buf, dtype=np.uint64).reshape(max_ctas, 8)[:n.value].astype(np.int64)
+
+    def chain_phases(self, *, batch: int, seq_len: int, pos_begin: int, pos_end: int, sampling: SamplingParams,
+                     cond: Optional[torch.Tensor], codes_top: torch.Tensor, codes_bot: torch.Tensor, launch_idx: int,
+                     op_idx: int, max_ctas: int = 256):
+        """Per-CTA timestamps (ns) of one op of one persistent chain launch: int64 array [n_ctas, 8] (hq_debug_chain_phases)."""
+        import numpy as np
+        args = HQRunArgs(batch=batch, seq_len=seq_len, pos_begin=pos_begin, pos_end=pos_end, cond=_ptr(cond), sos=None,
+                         given_top=None, given_bot=None, codes_top=_ptr(codes_top), codes_bot=_ptr(codes_bot),
+                         logits=None, sampling=sampling.to_c())
+        buf = (C.c_uint64 * (max_ctas * 8))()
+        n = C.c_int()
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._lib.hq_debug_chain_phases(self._ctx, C.byref(args), C.c_void_p(st), launch_idx, op_idx, buf, max_ctas,
+                                              C.byref(n)), self._ctx, "hq_debug_chain_phases")
         return np.frombuffer(buf, dtype=np.uint64).reshape(max_ctas, 8)[:n.value].astype(np.int64)
 
     def bench_gemm(self, kind: int, M: int, iters: int = 20) -> float:

@@ -55,7 +55,8 @@ class iHQGPT:
     def __init__(self, vocab_size_top: int, vocab_size_bot: int, vocab_size_txt: int, ratio_bot2top: int,
                  use_cls_cond: bool, use_txt_cond: bool, model_type: str, hparams, hparams_dec=None, *,
                  device: Union[int, str, torch.device] = 0, precision: str = "bf16", max_batch: int = 16,
-                 max_seq_len: int = 64, use_cuda_graph: bool = True, use_pdl: bool = True) -> None:
+                 max_seq_len: int = 64, use_cuda_graph: bool = True, use_pdl: bool = True,
+                 use_chain: bool = False) -> None:
         if model_type != "parallel":
             raise NotImplementedError(
                 f"model_type={model_type!r}: only 'parallel' (1 top + 4 bottom codes in two depth passes) is implemented; "
@@ -92,7 +93,8 @@ class iHQGPT:
                                n_layers_depth=self.n_layers_depth, vocab_top=vocab_size_top, vocab_bot=vocab_size_bot,
                                vocab_txt=vocab_size_txt, n_classes=self.n_classes or 0, ctx_len_img=self.ctx_len_img,
                                ctx_len_txt=self.ctx_len_txt, cond=self.cond, max_seq_len=self.max_seq_len,
-                               device=self.device, use_cuda_graph=use_cuda_graph, use_pdl=use_pdl)
+                               device=self.device, use_cuda_graph=use_cuda_graph, use_pdl=use_pdl,
+                               use_chain=use_chain)
         self._max_batch = max_batch
         self._engines: Dict[str, Engine] = {}
         self._source: Optional[Dict[str, torch.Tensor]] = None    # retained only when asked (other-precision engine)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HQ_ABI_VERSION 2
+#define HQ_ABI_VERSION 3
 
 enum hq_status {
   HQ_OK = 0,
@@ -67,6 +67,10 @@ typedef struct hq_config {
   int32_t use_cuda_graph;  /* 1: capture each run shape once and replay it; 0: plain stream launches */
   int32_t use_pdl;         /* 1: chain the kernels with programmatic dependent launch (prologue of kernel n+1 and
                               its first weight tiles overlap the tail of kernel n); 0: plain stream order */
+  int32_t use_chain;       /* 1 (bf16 engine, batches > 128): the depth transformer of a position
+                              (sampling_step_depth_parallel, hierarchical_ar.py:667-719) and the GEMM / LayerNorm runs of the
+                              spatial blocks execute as persistent multi-op kernels (one launch per run of dependent ops,
+                              grid barrier between ops); 0: one kernel per op.  Results are bit-identical either way. */
 } hq_config;
 
 /* Arguments of Sample(z; T, k, p) - hierarchical_ar.py:762-785 with utils/sampling.py:12-37.
@@ -155,6 +159,10 @@ int hq_run_host(hq_ctx* ctx, const hq_run_args* args);
 /* Number of kernel launches enqueued by the last hq_run / hq_run_host (graph nodes when replayed). */
 int64_t hq_last_launch_count(const hq_ctx* ctx);
 
+/* Launches of the persistent chain kernel (hq_config.use_chain) enqueued or captured since hq_create; 0 means every op
+ * ran as a kernel of its own (batch <= 128, fp32 engine, use_chain == 0). */
+int64_t hq_chain_launch_count(const hq_ctx* ctx);
+
 /* Bytes of device memory owned by the ctx (weights + KV cache + workspaces). */
 size_t hq_device_bytes(const hq_ctx* ctx);
 
@@ -190,6 +198,12 @@ int hq_bench_attention(hq_ctx* ctx, int B, int n_keys, int iters, float* usec, v
  * done, 5 softmax done, 6 first item written, 7 CTA end); *n_ctas = CTAs that reported. */
 int hq_debug_attention_phases(hq_ctx* ctx, int B, int n_keys, int warm, unsigned long long* out_ns, int max_ctas,
                               int* n_ctas, void* stream);
+
+/* One hq_run (device pointers, plain stream launches) in which op `op_idx` of the `launch_idx`-th persistent chain launch
+ * stamps %globaltimer per CTA: out_ns[8*c + p], p = 0 op begins, 1 grid barrier seen, 2 epilogue warps released, 3 work done,
+ * 4 proxy fence done, 5 all epilogue warps of the CTA done, 6 arrival posted; *n_ctas = CTAs that reported. */
+int hq_debug_chain_phases(hq_ctx* ctx, const hq_run_args* args, void* stream, int launch_idx, int op_idx,
+                          unsigned long long* out_ns, int max_ctas, int* n_ctas);
 
 /* Times one GEMM family of the loop alone on the ctx's own weights and buffers: kind 0 = fused qkv [3D, D],
  * 1 = attention proj [D, D], 2 = mlp fc1 [4D, D], 3 = mlp fc2 [D, 4D], 4 = head_top [V, D]; M rows.  L2 is evicted
