@@ -6,18 +6,22 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libhqgraft.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 HQ_OK = 0
 HQ_COND_CLS, HQ_COND_TXT, HQ_COND_UNCOND = 0, 1, 2
 HQ_PREC_BF16, HQ_PREC_FP32 = 0, 1
 HQ_F32, HQ_BF16, HQ_F16 = 0, 1, 2
+HQ_MODEL = {"parallel": 0, "top2bot": 1, "bidirectional": 2}
+HQ_EMB = {"transformer1": 0, "reduce": 1}
+HQ_POS = {"1d": 0, "2d": 1}
 
 
 class HQConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "embed_dim", "n_heads", "n_layers", "n_layers_depth", "vocab_top", "vocab_bot", "vocab_txt", "n_classes",
-        "ctx_len_img", "ctx_len_txt", "cond_kind", "precision", "max_seq_len", "use_cuda_graph", "use_pdl", "use_chain")]
+        "ctx_len_img", "ctx_len_txt", "cond_kind", "precision", "max_seq_len", "use_cuda_graph", "use_pdl", "use_chain", "model_type", "embedding_kind",
+        "position_kind")]
 
 
 class HQSamplingParams(C.Structure):

@@ -205,6 +205,7 @@ struct hq_ctx {
   std::vector<ChainOp> rec;
   std::vector<std::string> rec_tags;
   int rec_flags = 0;                   // flags of the next recorded GEMM op (CH_F_T0_RT)
+  const char* gemm_tag_override = nullptr;   // timeline tag of the next GEMM launch (split-K residual GEMMs: "gemm_resid")
   ChainRt chain_rt;                    // t0 / pos / S of the position being recorded
   std::vector<char> trace_chain_cont;  // tracing: entry i is op > 0 of a chain launch (its start is entry i-1's end)
   int64_t chain_launches = 0, chain_ops = 0;
@@ -958,7 +959,9 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
       return;
     }
     char buf[64];
-    snprintf(buf, sizeof(buf), "%s:%dx%dx%d:s%d", gemm_tag<EPI>(M), M, N, K, splits);
+    snprintf(buf, sizeof(buf), "%s:%dx%dx%d:s%d", ctx->gemm_tag_override ? ctx->gemm_tag_override : gemm_tag<EPI>(M), M, N, K,
+             splits);
+    ctx->gemm_tag_override = nullptr;
     ChainOp* op = chain_push(ctx, CH_OP_GEMM, buf);
     op->flags = ctx->rec_flags;
     op->map_a = ia;
@@ -973,12 +976,14 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
     snprintf(buf, sizeof(buf), ":%dx%dx%d:s%d", M, N, K, splits);
     ctx->tag_suffix = buf;
   }
+  const char* tag = ctx->gemm_tag_override ? ctx->gemm_tag_override : gemm_tag<EPI>(M);
+  ctx->gemm_tag_override = nullptr;
   if (bn > 0 && N % bn == 0) {
     const int tiles = (N / bn) * ((M + 255) / 256) * splits;
     dim3 grid(2 * (tiles < 74 ? tiles : 74));               // persistent: at most one CTA pair per SM pair
 #define HQ_LAUNCH2(BN)                                                                                             \
   case BN:                                                                                                         \
-    launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc2_kernel<BN, EPI, bf16>, grid, dim3(Tc2Cfg<BN>::THREADS), Tc2Cfg<BN>::SMEM_BYTES, mA, mWp.m[PairMaps::index(BN)], M, N, K,  \
+    launch_k(ctx, st, tag, gemm_tc2_kernel<BN, EPI, bf16>, grid, dim3(Tc2Cfg<BN>::THREADS), Tc2Cfg<BN>::SMEM_BYTES, mA, mWp.m[PairMaps::index(BN)], M, N, K,  \
              w_row_off, splits, ep);                                                                               \
     break;
     switch (bn) {
@@ -992,11 +997,11 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
   const bool wide = bn == -128 || (bn != -64 && (N % 128 == 0) && (mt * (N / 128) >= 120));
   if (wide) {
     dim3 grid(N / 128, mt, splits);
-    launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc_kernel<128, EPI, bf16>, grid, dim3(192), TcCfg<128>::SMEM_BYTES, mA, mW64, M, N, K,
+    launch_k(ctx, st, tag, gemm_tc_kernel<128, EPI, bf16>, grid, dim3(192), TcCfg<128>::SMEM_BYTES, mA, mW64, M, N, K,
              w_row_off, ep);
   } else {
     dim3 grid(N / 64, mt, splits);
-    launch_k(ctx, st, gemm_tag<EPI>(M), gemm_tc_kernel<64, EPI, bf16>, grid, dim3(192), TcCfg<64>::SMEM_BYTES, mA, mW64, M, N, K,
+    launch_k(ctx, st, tag, gemm_tc_kernel<64, EPI, bf16>, grid, dim3(192), TcCfg<64>::SMEM_BYTES, mA, mW64, M, N, K,
              w_row_off, ep);
   }
 }
@@ -1178,6 +1183,7 @@ static void gemm_fc2_split(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const We
   EpiParams<bf16> e;
   memset(&e, 0, sizeof(e));
   e.outf = ctx->splitk_ws; e.ldo = N; e.split_stride = static_cast<size_t>(ctx->ws_rows) * N;
+  ctx->gemm_tag_override = "gemm_resid";
   gemm_bf16<EPI_F32>(ctx, st, A.map, W.map, W.mapp, 0, M, N, K, e, splits, bn, A.map_idx, W.map_idx);
 }
 static void gemm_fc2_split(hq_ctx*, cudaStream_t, const ABuf&, const Weight&, int, int, int, int, int, float*) {}

@@ -22,6 +22,11 @@ struct EmbedArgs {
   const int64_t* codes_top; // [B, S]
   const int64_t* codes_bot; // [B, S, 4]
   int D, S, pos, cond_kind;
+  // variants
+  int emb_kind;             // 0: 'transformer1' (mean of the 5 stack tokens + pos_emb_emb); 1: 'reduce' (hierarchical_ar.py:522-526)
+  const float* P_top_h;     // position_embedding == '2d' (:508-514): P_top_h[p / Hpos] + P_top_w[p % Hpos]; else nullptr
+  const float* P_top_w;
+  int Hpos;
 };
 
 __global__ void __launch_bounds__(1024) embed_kernel(int trace_id, EmbedArgs a) {
@@ -44,13 +49,33 @@ __global__ void __launch_bounds__(1024) embed_kernel(int trace_id, EmbedArgs a) 
   const int64_t ct = a.codes_top[static_cast<size_t>(b) * a.S + p];
   const int64_t* cbp = a.codes_bot + (static_cast<size_t>(b) * a.S + p) * 4;
   const float4* et = reinterpret_cast<const float4*>(a.E_top + static_cast<size_t>(ct) * a.D);
-  const float4* pt = reinterpret_cast<const float4*>(a.P_top + static_cast<size_t>(p) * a.D);
+  const bool pos2d = a.P_top_h != nullptr;
+  // '2d': the reference splits the position with the number of ROWS OF THE TABLE (sqrt(ctx_len_img)), not the grid width
+  const float4* pt = reinterpret_cast<const float4*>(pos2d ? a.P_top_h + static_cast<size_t>(p / a.Hpos) * a.D
+                                                           : a.P_top + static_cast<size_t>(p) * a.D);
+  const float4* pw = pos2d ? reinterpret_cast<const float4*>(a.P_top_w + static_cast<size_t>(p % a.Hpos) * a.D) : nullptr;
+  if (a.emb_kind == 1) {
+    // 'reduce': x[d] = E_top[c_t][d] + pos[d] + E_bot[c_b[d % 4]][d / 4]   (rearrange 'B (U L) K -> B U (K L)': K outer)
+    const int Dq = a.D / 4;
+    const float* ebq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ebq[j] = a.E_bot + static_cast<size_t>(cbp[j]) * Dq;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 t = et[i];
+      float4 q = pt[i];
+      if (pos2d) { const float4 w = pw[i]; q.x += w.x; q.y += w.y; q.z += w.z; q.w += w.w; }
+      // elements 4i .. 4i+3 -> bottom code 0..3, element i of its narrow embedding
+      xo[i] = make_float4((t.x + q.x) + ebq[0][i], (t.y + q.y) + ebq[1][i], (t.z + q.z) + ebq[2][i], (t.w + q.w) + ebq[3][i]);
+    }
+    return;
+  }
   const float4* eb[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) eb[j] = reinterpret_cast<const float4*>(a.E_bot + static_cast<size_t>(cbp[j]) * a.D);
   const float4* pe = reinterpret_cast<const float4*>(a.P_emb);
   for (int i = threadIdx.x; i < n4; i += blockDim.x) {
     float4 t = et[i], q = pt[i], e0 = pe[i];
+    if (pos2d) { const float4 w = pw[i]; q.x += w.x; q.y += w.y; q.z += w.z; q.w += w.w; }
     float4 acc;
     acc.x = (t.x + q.x) + e0.x; acc.y = (t.y + q.y) + e0.y; acc.z = (t.z + q.z) + e0.z; acc.w = (t.w + q.w) + e0.w;
 #pragma unroll
@@ -110,9 +135,44 @@ embed_depth_kernel(int trace_id, float* y, const float* E_top_depth, const float
   }
 }
 
+// model_type 'top2bot' (hierarchical_ar.py:596-601): input of depth pass c >= 1:
+//   y[b] = E[code[b]] + P_depth[c - 1], E = tok_emb_top_depth with the top code (c == 1), tok_emb_bot_depth with bottom
+//   code c - 2 otherwise.  `codes` points at the first code (element stride `cstride` int64 between images).
+__global__ void __launch_bounds__(1024)
+embed_depth_seq_kernel(int trace_id, float* y, const float* E, const float* P_row, const int64_t* codes, int cstride, int D) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const int64_t c = codes[static_cast<size_t>(b) * cstride];
+  const float4* e = reinterpret_cast<const float4*>(E + static_cast<size_t>(c) * D);
+  const float4* p = reinterpret_cast<const float4*>(P_row);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    const float4 a = e[i], q = p[i];
+    reinterpret_cast<float4*>(y + static_cast<size_t>(b) * D)[i] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+  }
+}
+
+// model_type 'bidirectional' (hierarchical_ar.py:808-811): tokens 1..4 of the five-token depth input are the bare position
+// embeddings: y[b*5 + 1 + j] = P_depth[j]  (token 0 = hs + sos_depth is written by the ln_f launch).
+__global__ void __launch_bounds__(1024)
+depth_pos_rows_kernel(int trace_id, float* y, const float* P_depth, int D) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const float4* p = reinterpret_cast<const float4*>(P_depth);
+  const int n4 = D / 4;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(y + (static_cast<size_t>(b) * 5 + 1 + j) * D)[i] = p[j * n4 + i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2: LayerNorm (eps 1e-5, affine), one warp per row, fp32 statistics (two-pass).
-//   out[r] = LN(x[r * in_mul + in_off]) * gamma + beta (+ add)        OutT = float | bf16
+//   out[r * out_mul] = LN(x[(r / in_group) * in_mul + in_off + r % in_group]) * gamma + beta (+ add)    OutT = float | bf16
+// (in_group = out_mul = 1 everywhere except the 'bidirectional' depth pass, whose five-token stacks are normalised by
+//  ln_top (token 0) and ln_bot (tokens 1..4) and whose token 0 comes from ln_f of the spatial stream)
 // The (+ add) form produces the depth transformer's start token hs + sos_depth (hierarchical_ar.py:561, 685).
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_THREADS = 128;
@@ -149,14 +209,16 @@ template <typename OutT, int MAXFOLD>
 __global__ void __launch_bounds__(LN_THREADS)
 layernorm_kernel(int trace_id, float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* __restrict__ add, OutT* __restrict__ out, int rows, int D, int in_mul, int in_off,
-                 const float* __restrict__ fold, int n_fold, size_t fold_stride, const float* __restrict__ fold_bias) {
+                 const float* __restrict__ fold, int n_fold, size_t fold_stride, const float* __restrict__ fold_bias,
+                 int in_group, int out_mul) {
   TraceScope trace_scope(trace_id);
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[4];
   const int r = blockIdx.x;
-  float* xr = x + (static_cast<size_t>(r) * in_mul + in_off) * D;
-  OutT* o = out + static_cast<size_t>(r) * D;
+  const size_t in_row = static_cast<size_t>(r / in_group) * in_mul + in_off + (r % in_group);
+  float* xr = x + in_row * D;
+  OutT* o = out + static_cast<size_t>(r) * out_mul * D;
   const int tid = threadIdx.x;
   if (D <= LN_MAXV * LN_THREADS * 4) {
     float4 v[LN_MAXV], g[LN_MAXV], bt[LN_MAXV], ad[LN_MAXV], fb[LN_MAXV], f[MAXFOLD][LN_MAXV];
@@ -173,7 +235,7 @@ layernorm_kernel(int trace_id, float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
       for (int sidx = 0; sidx < MAXFOLD; ++sidx) f[sidx][j] = z4;
       if (fold != nullptr) {
-        const float* fr = fold + (static_cast<size_t>(r) * in_mul + in_off) * D + ic;
+        const float* fr = fold + in_row * D + ic;
         fb[j] = fold_bias != nullptr ? *reinterpret_cast<const float4*>(fold_bias + ic) : z4;
 #pragma unroll
         for (int sidx = 0; sidx < MAXFOLD; ++sidx)
@@ -224,7 +286,7 @@ layernorm_kernel(int trace_id, float* __restrict__ x, const float* __restrict__ 
   if (fold != nullptr) {
     for (int i = tid * 4; i < D; i += LN_THREADS * 4) {
       float4 v = *reinterpret_cast<const float4*>(xr + i);
-      const float* fr = fold + (static_cast<size_t>(r) * in_mul + in_off) * D + i;
+      const float* fr = fold + in_row * D + i;
       float4 acc = *reinterpret_cast<const float4*>(fr);
       for (int sidx = 1; sidx < n_fold; ++sidx) {
         const float4 f = *reinterpret_cast<const float4*>(fr + sidx * fold_stride);
@@ -975,6 +1037,9 @@ struct SampleArgs {
   int forced;           // 1: codes are given (teacher forcing): leave them untouched
   float* logits_out;    // optional [B, S, 5, Vmax]
   int Vmax;
+  int temp_sel;         // which softmax temperature: 0 = top, 1 = bottom
+  int filt_sel;         // which top-k / top-p pair:  0 = top, 1 = bottom
+  int bot_slot;         // rows_per_b == 1 only: >= 0 -> the code goes to codes_bot[b, pos, bot_slot] ('top2bot' passes 1..4)
   float* probs_out;     // optional [R, V] (debug)
   int64_t* flat_out;    // optional [R] (debug)
   // debug overrides (sp == nullptr)
@@ -1030,10 +1095,9 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 4 : 1) sample_kernel(int t
 
   float temperature, top_p; int top_k; uint64_t seed, row_offset;
   if (a.sp != nullptr) {
-    const bool top = (a.rows_per_b == 1);
-    temperature = top ? a.sp->temperature_top : a.sp->temperature_bot;
-    top_p = top ? a.sp->top_p_top : a.sp->top_p_bot;
-    top_k = top ? a.sp->top_k_top : a.sp->top_k_bot;
+    temperature = a.temp_sel == 0 ? a.sp->temperature_top : a.sp->temperature_bot;
+    top_p = a.filt_sel == 0 ? a.sp->top_p_top : a.sp->top_p_bot;
+    top_k = a.filt_sel == 0 ? a.sp->top_k_top : a.sp->top_k_bot;
     seed = a.sp->seed; row_offset = a.sp->row_offset;
   } else {
     temperature = a.temperature; top_p = a.top_p; top_k = a.top_k; seed = a.seed; row_offset = a.row_offset;
@@ -1061,8 +1125,9 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 4 : 1) sample_kernel(int t
 
   int64_t* dst = a.flat_out != nullptr
                      ? a.flat_out + r
-                     : (a.rows_per_b == 1 ? a.codes_top + static_cast<size_t>(b) * a.S + a.pos
-                                          : a.codes_bot + (static_cast<size_t>(b) * a.S + a.pos) * 4 + jj);
+                     : (a.rows_per_b == 1 && a.bot_slot < 0
+                            ? a.codes_top + static_cast<size_t>(b) * a.S + a.pos
+                            : a.codes_bot + (static_cast<size_t>(b) * a.S + a.pos) * 4 + (a.rows_per_b == 1 ? a.bot_slot : jj));
 
   // ---- greedy: lowest index among the maxima ----
   float mx = -INFINITY;

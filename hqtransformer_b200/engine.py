@@ -53,7 +53,8 @@ class Engine:
                  vocab_bot: int, vocab_txt: int = 16384, n_classes: int = 1000, ctx_len_img: int = 256,
                  ctx_len_txt: int = 64, cond: str = "cls", precision: str = "bf16", max_seq_len: int = 64,
                  max_batch: int = 16, device: Union[int, str, torch.device] = 0, use_cuda_graph: bool = True,
-                 use_pdl: bool = True, use_chain: bool = False):
+                 use_pdl: bool = True, use_chain: bool = False, model_type: str = "parallel",
+                 embedding_type: str = "transformer1", position_embedding: str = "1d"):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
@@ -70,7 +71,9 @@ class Engine:
                        cond_kind={"cls": _lib.HQ_COND_CLS, "txt": _lib.HQ_COND_TXT, "uncond": _lib.HQ_COND_UNCOND}[cond],
                        precision={"bf16": _lib.HQ_PREC_BF16, "fp32": _lib.HQ_PREC_FP32}[precision],
                        max_seq_len=max_seq_len, use_cuda_graph=1 if use_cuda_graph else 0,
-                       use_pdl=1 if use_pdl else 0, use_chain=1 if use_chain else 0)
+                       use_pdl=1 if use_pdl else 0, use_chain=1 if use_chain else 0,
+                       model_type=_lib.HQ_MODEL[model_type], embedding_kind=_lib.HQ_EMB[embedding_type],
+                       position_kind=_lib.HQ_POS[position_embedding])
         check(self._lib.hq_create(C.byref(cfg), self.device.index, int(max_batch), C.byref(self._ctx)), None, "hq_create")
 
     # ---- lifetime ----

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HQ_ABI_VERSION 3
+#define HQ_ABI_VERSION 4
 
 enum hq_status {
   HQ_OK = 0,
@@ -47,7 +47,24 @@ enum hq_precision { HQ_PREC_BF16 = 0, HQ_PREC_FP32 = 1 };
 
 enum hq_dtype { HQ_F32 = 0, HQ_BF16 = 1, HQ_F16 = 2 };
 
-/* Architecture of an iHQGPT(model_type='parallel', embedding_type='transformer1', position_embedding='1d')
+/* Depth-transformer schedule = the reference's `model_type` (hqvae/models/__init__.py:123-137):
+ *   HQ_MODEL_PARALLEL       'parallel'       top, then the four bottoms in one pass (hierarchical_ar.py:667-789)
+ *   HQ_MODEL_TOP2BOT        'top2bot'        five sequential single-token passes with a causal depth cache (:565-664)
+ *   HQ_MODEL_BIDIRECTIONAL  'bidirectional'  one pass over [hs + sos_depth, pos_emb_depth[0..3]], unmasked (:791-878);
+ *                                            as in the reference every token is drawn with the BOTTOM filters and
+ *                                            softmax_temperature[0] */
+enum hq_model_type { HQ_MODEL_PARALLEL = 0, HQ_MODEL_TOP2BOT = 1, HQ_MODEL_BIDIRECTIONAL = 2 };
+
+/* Input embedding of the spatial transformer = hparams.embedding_type (hierarchical_ar.py:83-113, 516-548):
+ *   HQ_EMB_TRANSFORMER1  mean over the five stack tokens of (embedding + pos_emb_emb) - ImageNet / CC-15M checkpoints
+ *   HQ_EMB_REDUCE        tok_emb_top + the four D/4-wide bottom embeddings interleaved ('B (U L) K -> B U (K L)') - FFHQ */
+enum hq_embedding_kind { HQ_EMB_TRANSFORMER1 = 0, HQ_EMB_REDUCE = 1 };
+
+/* hparams.position_embedding (hierarchical_ar.py:118-125, 506-514): one table, or pos_emb_top_h[p / H] + pos_emb_top_w[p % H]
+ * with H = sqrt(ctx_len_img) rows per table. */
+enum hq_position_kind { HQ_POS_1D = 0, HQ_POS_2D = 1 };
+
+/* Architecture of an iHQGPT (2-level HQ-Transformer; model_type / embedding_type / position_embedding variants below)
  * - constructor arguments at hqvae/models/stage2/hierarchical_ar.py:24-216, YAML fields at
  * hqvae/utils/config2.py:49-105. */
 typedef struct hq_config {
@@ -71,6 +88,9 @@ typedef struct hq_config {
                               (sampling_step_depth_parallel, hierarchical_ar.py:667-719) and the GEMM / LayerNorm runs of the
                               spatial blocks execute as persistent multi-op kernels (one launch per run of dependent ops,
                               grid barrier between ops); 0: one kernel per op.  Results are bit-identical either way. */
+  int32_t model_type;      /* hq_model_type */
+  int32_t embedding_kind;  /* hq_embedding_kind */
+  int32_t position_kind;   /* hq_position_kind */
 } hq_config;
 
 /* Arguments of Sample(z; T, k, p) - hierarchical_ar.py:762-785 with utils/sampling.py:12-37.

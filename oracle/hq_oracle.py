@@ -47,6 +47,10 @@ class HQConfig:
     ctx_len_img: int = 256           # rows of pos_emb_top; only 0..63 are used when sampling 8x8
     ctx_len_txt: int = 64
     cond: str = "cls"                # 'cls' | 'txt' | 'uncond'
+    # variants of the 2-level model; the defaults are the ImageNet / CC-15M checkpoints' settings
+    embedding_type: str = "transformer1"   # 'transformer1' | 'reduce' (FFHQ checkpoint; hierarchical_ar.py:85-88, 522-526)
+    position_embedding: str = "1d"         # '1d' | '2d' (hierarchical_ar.py:118-125, 506-514)
+    model_type: str = "parallel"           # 'parallel' | 'top2bot' (:565-664) | 'bidirectional' (:791-878)
 
     @property
     def head_dim(self) -> int:
@@ -108,9 +112,17 @@ def param_shapes(cfg: HQConfig) -> "OrderedDict[str, Tuple[int, ...]]":
         s["sos"] = (1, 1, D)                              # :77
     s["sos_depth"] = (1, 1, D)                            # :156
     s["tok_emb_top.weight"] = (cfg.vocab_top, D)          # :101-103
-    s["tok_emb_bot.weight"] = (cfg.vocab_bot, D)
-    s["pos_emb_emb.weight"] = (5, D)
-    s["pos_emb_top.weight"] = (cfg.ctx_len_img, D)        # :120
+    if cfg.embedding_type == "reduce":                    # :85-88: bottom embeddings are D/4 wide, no pos_emb_emb
+        s["tok_emb_bot.weight"] = (cfg.vocab_bot, D // 4)
+    else:
+        s["tok_emb_bot.weight"] = (cfg.vocab_bot, D)
+        s["pos_emb_emb.weight"] = (5, D)
+    if cfg.position_embedding == "2d":                    # :121-125
+        H = int(math.sqrt(cfg.ctx_len_img))
+        s["pos_emb_top_h.weight"] = (H, D)
+        s["pos_emb_top_w.weight"] = (H, D)
+    else:
+        s["pos_emb_top.weight"] = (cfg.ctx_len_img, D)    # :120
     for i in range(cfg.n_layers):                         # :134-142
         s.update(_block_shapes(f"blocks.{i}", D))
     s["ln_f.weight"] = (D,)                               # :144
@@ -296,11 +308,26 @@ def build_sos(P: Dict[str, Tensor], cfg: HQConfig, cond, num_candidates: int) ->
     return P["sos"].repeat(num_candidates, 1, 1)
 
 
-def embed_stack(P: Dict[str, Tensor], code_top: Tensor, code_bot: Tensor, pos: int) -> Tensor:
+def embed_stack(P: Dict[str, Tensor], code_top: Tensor, code_bot: Tensor, pos: int,
+                cfg: Optional[HQConfig] = None) -> Tensor:
     """hierarchical_ar.py:506-507, 534-544 with `emb_blocks` empty (:100-113, n_layers_emb=1):
     mean over the 5 stack tokens of (embedding + pos_emb_emb[j]); the top token also gets
-    pos_emb_top[pos].  code_top [B], code_bot [B,4] -> [B,1,D]."""
-    e_top = P["tok_emb_top.weight"][code_top] + P["pos_emb_top.weight"][pos]                     # [B,D]
+    pos_emb_top[pos].  code_top [B], code_bot [B,4] -> [B,1,D].
+    position_embedding='2d' (:508-514): pos_emb_top_h[pos // H] + pos_emb_top_w[pos % H] with H = rows of the table
+    (sqrt(ctx_len_img), NOT the 8 of the 8x8 grid - kept as the reference computes it).
+    embedding_type='reduce' (:522-526): x = E_top[c_t] + pos + rearrange(E_bot[c_b], 'B (U L) K -> B U (K L)', U=1),
+    i.e. element d of the bottom part is E_bot[c_b[d % 4]][d // 4] (K outer, L inner)."""
+    if cfg is not None and cfg.position_embedding == "2d":
+        H = P["pos_emb_top_h.weight"].shape[0]
+        pos_emb = P["pos_emb_top_h.weight"][pos // H] + P["pos_emb_top_w.weight"][pos % H]
+    else:
+        pos_emb = P["pos_emb_top.weight"][pos]
+    if cfg is not None and cfg.embedding_type == "reduce":
+        e_top = P["tok_emb_top.weight"][code_top] + pos_emb                                      # [B,D]
+        e_bot = P["tok_emb_bot.weight"][code_bot]                                                # [B,4,D/4]
+        B = e_bot.shape[0]
+        return (e_top + e_bot.permute(0, 2, 1).reshape(B, -1)).unsqueeze(1)                      # (K L) flattening
+    e_top = P["tok_emb_top.weight"][code_top] + pos_emb                                          # [B,D]
     e_bot = P["tok_emb_bot.weight"][code_bot]                                                    # [B,4,D]
     h = torch.cat([e_top.unsqueeze(1), e_bot], dim=1) + P["pos_emb_emb.weight"].unsqueeze(0)     # [B,5,D]
     return h.mean(dim=1, keepdim=True)
@@ -357,6 +384,54 @@ def depth_pass1(P, cfg: HQConfig, code_top: Tensor, kv0, rnd=_identity) -> Tenso
     return F.linear(y, P["head_bot.weight"])
 
 
+def depth_top2bot(P, cfg: HQConfig, hs_last: Tensor, draw, rnd=_identity):
+    """`sampling_depth_baseline` / `sampling_step_depth_baseline` (hierarchical_ar.py:565-664), model_type='top2bot':
+    five sequential single-token passes over the depth blocks with a growing cache.  Inputs: hs + sos_depth, then
+    tok_emb_top_depth[c_top] + pos_emb_depth[0], then tok_emb_bot_depth[c_b(j-1)] + pos_emb_depth[j] (the position is the
+    index of the code fed in, :630-637); outputs head_top(ln_top) for pass 0, head_bot(ln_bot) after.
+    `draw(logits [B,V], slot)` returns the code [B] emitted for stack slot 0..4.  Returns (codes [B,5], logits list)."""
+    D = cfg.embed_dim
+    B = hs_last.shape[0]
+    past = [(None, None)] * cfg.n_layers_depth
+    codes, all_logits = [], []
+    for c in range(5):
+        if c == 0:
+            y = hs_last + P["sos_depth"]
+        elif c == 1:
+            y = (P["tok_emb_top_depth.weight"][codes[0]] + P["pos_emb_depth.weight"][0]).unsqueeze(1)
+        else:
+            y = (P["tok_emb_bot_depth.weight"][codes[c - 1]] + P["pos_emb_depth.weight"][c - 1]).unsqueeze(1)
+        new_past = []
+        for l in range(cfg.n_layers_depth):
+            y, k, v = block_sample(y, P, f"depths.{l}", cfg.n_heads, past[l][0], past[l][1], causal=True, rnd=rnd)
+            pk, pv = past[l]
+            new_past.append((k if pk is None else torch.cat([pk, k], 2), v if pv is None else torch.cat([pv, v], 2)))
+        past = new_past
+        if c == 0:
+            y = rnd(F.layer_norm(y, (D,), P["ln_top.weight"], P["ln_top.bias"], 1e-5))
+            logits = F.linear(y, P["head_top.weight"])[:, 0]
+        else:
+            y = rnd(F.layer_norm(y, (D,), P["ln_bot.weight"], P["ln_bot.bias"], 1e-5))
+            logits = F.linear(y, P["head_bot.weight"])[:, 0]
+        all_logits.append(logits)
+        codes.append(draw(logits, c))
+    return torch.stack(codes, 1), all_logits
+
+
+def depth_bidirectional(P, cfg: HQConfig, hs_last: Tensor, rnd=_identity):
+    """`sampling_step_depth_bidirectional` (hierarchical_ar.py:791-826), model_type='bidirectional': ONE pass over the five
+    tokens [hs + sos_depth, pos_emb_depth[0..3]] with unmasked attention among them (Block(causal_attn=False));
+    logits_top = head_top(ln_top(y[:, 0])), logits_bot = head_bot(ln_bot(y[:, 1:])).  Returns (top [B,V], bot [B,4,V])."""
+    D = cfg.embed_dim
+    B = hs_last.shape[0]
+    y = torch.cat([hs_last + P["sos_depth"], P["pos_emb_depth.weight"][:4].unsqueeze(0).repeat(B, 1, 1)], dim=1)
+    for l in range(cfg.n_layers_depth):
+        y, _, _ = block_sample(y, P, f"depths.{l}", cfg.n_heads, None, None, causal=False, rnd=rnd)
+    yt = rnd(F.layer_norm(y[:, 0:1], (D,), P["ln_top.weight"], P["ln_top.bias"], 1e-5))
+    yb = rnd(F.layer_norm(y[:, 1:], (D,), P["ln_bot.weight"], P["ln_bot.bias"], 1e-5))
+    return F.linear(yt, P["head_top.weight"])[:, 0], F.linear(yb, P["head_bot.weight"])
+
+
 def _as_pair(softmax_temperature) -> Tuple[float, float]:
     """The reference indexes `softmax_temperatures[0/1]` (hierarchical_ar.py:763, 779); the shipped
     measure_throughput_txt passes a bare float - accept both."""
@@ -397,9 +472,41 @@ def sample(params: Dict[str, Tensor], cfg: HQConfig, cond, num_candidates: int,
         if cnt == 0:
             x = sos                                                                              # :493-499
         else:
-            x = embed_stack(P, codes_top[:, cnt - 1], codes_bot[:, cnt - 1], cnt - 1)            # :506-544
+            x = embed_stack(P, codes_top[:, cnt - 1], codes_bot[:, cnt - 1], cnt - 1, cfg)       # :506-544
         hs = spatial_step(P, cfg, x, cache, rnd)
         hs_last = hs[:, -1:, :]                                                                  # :684-685
+        if cfg.model_type == "top2bot":
+            def draw(logits, slot):                                                              # :639-661
+                if slot == 0 and given_top_code is not None:
+                    return given_top_code[:, cnt]
+                if slot > 0 and given_bot_code is not None:
+                    return given_bot_code[:, cnt, slot - 1]
+                T, k, p = (T_top, top_k_top, top_p_top) if slot == 0 else (T_bot, top_k_bot, top_p_bot)
+                return draw_token(logits, T, k, p, generator)[0][:, 0]
+            codes, lgs = depth_top2bot(P, cfg, hs_last, draw, rnd)
+            codes_top[:, cnt] = codes[:, 0]
+            codes_bot[:, cnt] = codes[:, 1:]
+            if return_logits:
+                all_logits[:, cnt, 0, : cfg.vocab_top] = lgs[0]
+                for j in range(4):
+                    all_logits[:, cnt, 1 + j, : cfg.vocab_bot] = lgs[1 + j]
+            continue
+        if cfg.model_type == "bidirectional":
+            # :846-871: every one of the five tokens is drawn with the BOTTOM filters and softmax_temperatures[0]
+            lt, lb = depth_bidirectional(P, cfg, hs_last, rnd)
+            if return_logits:
+                all_logits[:, cnt, 0, : cfg.vocab_top] = lt
+                all_logits[:, cnt, 1:, : cfg.vocab_bot] = lb
+            if given_top_code is not None:
+                codes_top[:, cnt] = given_top_code[:, cnt]
+            else:
+                codes_top[:, cnt] = draw_token(lt, T_top, top_k_bot, top_p_bot, generator)[0][:, 0]
+            for j in range(4):
+                if given_bot_code is not None:
+                    codes_bot[:, cnt, j] = given_bot_code[:, cnt, j]
+                else:
+                    codes_bot[:, cnt, j] = draw_token(lb[:, j], T_top, top_k_bot, top_p_bot, generator)[0][:, 0]
+            continue
         logits_top, kv0 = depth_pass0(P, cfg, hs_last, rnd)
         if given_top_code is None:
             c_top, _ = draw_token(logits_top, T_top, top_k_top, top_p_top, generator)            # :763-769

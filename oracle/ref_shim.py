@@ -64,14 +64,14 @@ def import_reference():
 
 
 def make_hparams(embed_dim, n_layers, n_heads, n_classes=None, ctx_len_img=64, ctx_len_txt=64,
-                 embedding_type="transformer1"):
+                 embedding_type="transformer1", position_embedding="1d"):
     """Field set of hqvae/utils/config2.py:49-71 (Stage2Hparams) as a SimpleNamespace."""
     return types.SimpleNamespace(
         embed_dim=embed_dim, n_layers=n_layers, n_heads=n_heads, n_dense_layers=n_layers,
         ctx_len=None, ctx_len_img=ctx_len_img, ctx_len_txt=ctx_len_txt,
         embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0, mlp_bias=True, attn_bias=True,
         gelu_use_approx=False, use_head_txt=True, n_classes=n_classes, causal_attn=None,
-        embedding_type=embedding_type, position_embedding="1d", bottom_head_type="linear",
+        embedding_type=embedding_type, position_embedding=position_embedding, bottom_head_type="linear",
         use_random_order=False, rate_random_order=1.0)
 
 
@@ -80,15 +80,18 @@ def build_reference_model(cfg, state_dict):
     import contextlib
     import io
     iHQGPT, _ = import_reference()
+    emb = getattr(cfg, "embedding_type", "transformer1")
+    pe = getattr(cfg, "position_embedding", "1d")
     hp = make_hparams(cfg.embed_dim, cfg.n_layers, cfg.n_heads, n_classes=cfg.n_classes,
-                      ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt)
+                      ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt, embedding_type=emb, position_embedding=pe)
     hp_dec = make_hparams(cfg.embed_dim, cfg.n_layers_depth, cfg.n_heads, n_classes=cfg.n_classes,
-                          ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt)
+                          ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt, embedding_type=emb,
+                          position_embedding=pe)
     with contextlib.redirect_stdout(io.StringIO()):
         model = iHQGPT(vocab_size_top=cfg.vocab_top, vocab_size_bot=cfg.vocab_bot,
                        vocab_size_txt=cfg.vocab_txt, ratio_bot2top=4,
                        use_cls_cond=(cfg.cond == "cls"), use_txt_cond=(cfg.cond == "txt"),
-                       model_type="parallel", hparams=hp, hparams_dec=hp_dec)
+                       model_type=getattr(cfg, "model_type", "parallel"), hparams=hp, hparams_dec=hp_dec)
     missing = model.load_state_dict(state_dict, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
     return model.eval()
@@ -121,12 +124,15 @@ def build_reference_model_random(cfg):
     import contextlib
     import io
     iHQGPT, _ = import_reference()
+    emb = getattr(cfg, "embedding_type", "transformer1")
+    pe = getattr(cfg, "position_embedding", "1d")
     hp = make_hparams(cfg.embed_dim, cfg.n_layers, cfg.n_heads, n_classes=cfg.n_classes,
-                      ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt)
+                      ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt, embedding_type=emb, position_embedding=pe)
     hp_dec = make_hparams(cfg.embed_dim, cfg.n_layers_depth, cfg.n_heads, n_classes=cfg.n_classes,
-                          ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt)
+                          ctx_len_img=cfg.ctx_len_img, ctx_len_txt=cfg.ctx_len_txt, embedding_type=emb,
+                          position_embedding=pe)
     with contextlib.redirect_stdout(io.StringIO()):
         model = iHQGPT(vocab_size_top=cfg.vocab_top, vocab_size_bot=cfg.vocab_bot, vocab_size_txt=cfg.vocab_txt,
                        ratio_bot2top=4, use_cls_cond=(cfg.cond == "cls"), use_txt_cond=(cfg.cond == "txt"),
-                       model_type="parallel", hparams=hp, hparams_dec=hp_dec)
+                       model_type=getattr(cfg, "model_type", "parallel"), hparams=hp, hparams_dec=hp_dec)
     return model.eval()
