@@ -27,7 +27,7 @@ if ROOT not in sys.path:
 METRIC = "images_per_sec_sampled_256x256"
 UNIT = "images/s"
 CONFIGS = {"imagenet_l12": "imagenet_l12.yaml", "imagenet_l24": "imagenet_l24.yaml", "imagenet_l42": "imagenet_l42.yaml",
-           "cc15m_l12": "cc15m_l12.yaml"}
+           "cc15m_l12": "cc15m_l12.yaml", "ffhq_l24": "ffhq_l24.yaml"}
 
 
 def parse_args():

@@ -157,6 +157,10 @@ struct hq_ctx {
   float *E_top = nullptr, *E_bot = nullptr, *P_emb = nullptr, *P_top = nullptr;
   float *E_txt = nullptr, *P_txt = nullptr;
   float *E_top_depth = nullptr, *P_depth = nullptr;
+  float *E_bot_depth = nullptr;                       // 'top2bot' only (tok_emb_bot_depth is unused by 'parallel' sampling)
+  float *P_top_h = nullptr, *P_top_w = nullptr;       // position_embedding == '2d'
+  int Hpos = 0;                                       // rows of pos_emb_top_h / _w = sqrt(ctx_len_img)
+  int depth_rows = 4;                                 // rows per image of the widest depth pass (5: 'bidirectional')
   float *lnf_g = nullptr, *lnf_b = nullptr, *lnt_g = nullptr, *lnt_b = nullptr, *lnb_g = nullptr, *lnb_b = nullptr;
 
   // activations / state
@@ -478,13 +482,13 @@ static int reserve_alloc(hq_ctx* ctx, int max_batch) {
   const int D = ctx->D;
   const int B = max_batch;
   const int Mx = B * ctx->T0;                       // rows of the spatial residual stream (prefill for text)
-  const int Mmax = (4 * B > Mx) ? 4 * B : Mx;
+  const int Mmax = (ctx->depth_rows * B > Mx) ? ctx->depth_rows * B : Mx;
   if ((rc = alloc_abuf(ctx, &ctx->h, Mmax, D))) return rc;
   if ((rc = alloc_abuf(ctx, &ctx->att, Mmax, D))) return rc;
   if ((rc = alloc_abuf(ctx, &ctx->mlp, Mmax, 4 * D))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->q, static_cast<size_t>(Mmax) * D * ctx->wsize))) return rc;
   if ((rc = alloc_f32(ctx, &ctx->x, static_cast<size_t>(Mx) * D))) return rc;
-  if ((rc = alloc_f32(ctx, &ctx->yd, static_cast<size_t>(4) * B * D))) return rc;
+  if ((rc = alloc_f32(ctx, &ctx->yd, static_cast<size_t>(ctx->depth_rows) * B * D))) return rc;
   if ((rc = alloc_f32(ctx, &ctx->logits, static_cast<size_t>(4) * B * ctx->Vmax))) return rc;
   ctx->ws_rows = Mmax;
   if (ctx->bf16 && (rc = alloc_f32(ctx, &ctx->splitk_ws, static_cast<size_t>(LN_MAXFOLD) * Mmax * D))) return rc;
@@ -569,6 +573,21 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
     set_err(ctx, "bad cond_kind / precision");
     return HQ_ERR_INVALID;
   }
+  if (cfg->model_type < 0 || cfg->model_type > 2 || cfg->embedding_kind < 0 || cfg->embedding_kind > 1 ||
+      cfg->position_kind < 0 || cfg->position_kind > 1) {
+    set_err(ctx, "bad model_type / embedding_kind / position_kind");
+    return HQ_ERR_INVALID;
+  }
+  if (cfg->embedding_kind == HQ_EMB_REDUCE && D % 16 != 0) {
+    set_err(ctx, "embedding_type 'reduce' needs embed_dim %% 16 == 0 (four D/4-wide bottom embeddings)");
+    return HQ_ERR_UNSUPPORTED;
+  }
+  ctx->depth_rows = cfg->model_type == HQ_MODEL_BIDIRECTIONAL ? 5 : 4;
+  if (cfg->position_kind == HQ_POS_2D) {
+    int H = 1;
+    while ((H + 1) * (H + 1) <= cfg->ctx_len_img) ++H;        // int(math.sqrt(ctx_len_img)), hierarchical_ar.py:122
+    ctx->Hpos = H;
+  }
   if (ctx->bf16) {
     if ((rc = get_encode_fn(ctx, &ctx->encode))) return rc;
     if ((rc = set_gemm_attrs(ctx))) return rc;
@@ -616,15 +635,25 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
   std::vector<F32P> f32s = {
       {"sos_depth", &ctx->sos_depth, {1, 1, D}},
       {"tok_emb_top.weight", &ctx->E_top, {ctx->Vt, D}},
-      {"tok_emb_bot.weight", &ctx->E_bot, {ctx->Vb, D}},
-      {"pos_emb_emb.weight", &ctx->P_emb, {5, D}},
-      {"pos_emb_top.weight", &ctx->P_top, {cfg->ctx_len_img, D}},
       {"tok_emb_top_depth.weight", &ctx->E_top_depth, {ctx->Vt, D}},
       {"pos_emb_depth.weight", &ctx->P_depth, {5, D}},
       {"ln_f.weight", &ctx->lnf_g, {D}}, {"ln_f.bias", &ctx->lnf_b, {D}},
       {"ln_top.weight", &ctx->lnt_g, {D}}, {"ln_top.bias", &ctx->lnt_b, {D}},
       {"ln_bot.weight", &ctx->lnb_g, {D}}, {"ln_bot.bias", &ctx->lnb_b, {D}},
   };
+  if (cfg->embedding_kind == HQ_EMB_REDUCE) {               // hierarchical_ar.py:85-88
+    f32s.push_back({"tok_emb_bot.weight", &ctx->E_bot, {ctx->Vb, D / 4}});
+  } else {                                                   // :97-103
+    f32s.push_back({"tok_emb_bot.weight", &ctx->E_bot, {ctx->Vb, D}});
+    f32s.push_back({"pos_emb_emb.weight", &ctx->P_emb, {5, D}});
+  }
+  if (cfg->position_kind == HQ_POS_2D) {                     // :121-125
+    f32s.push_back({"pos_emb_top_h.weight", &ctx->P_top_h, {ctx->Hpos, D}});
+    f32s.push_back({"pos_emb_top_w.weight", &ctx->P_top_w, {ctx->Hpos, D}});
+  } else {
+    f32s.push_back({"pos_emb_top.weight", &ctx->P_top, {cfg->ctx_len_img, D}});
+  }
+  if (cfg->model_type == HQ_MODEL_TOP2BOT) f32s.push_back({"tok_emb_bot_depth.weight", &ctx->E_bot_depth, {ctx->Vb, D}});
   if (cfg->cond_kind == HQ_COND_CLS) f32s.push_back({"sos.weight", &ctx->sos_table, {cfg->n_classes, D}});
   if (cfg->cond_kind == HQ_COND_UNCOND) f32s.push_back({"sos", &ctx->sos_table, {1, 1, D}});
   if (txt) {
@@ -638,7 +667,7 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
     reg(ctx, f.name, *f.p, 0, f.shape);
   }
   // present in the reference state_dict, never read when sampling model_type='parallel' 
-  reg(ctx, "tok_emb_bot_depth.weight", nullptr, 0, {ctx->Vb, D}, true);
+  if (cfg->model_type != HQ_MODEL_TOP2BOT) reg(ctx, "tok_emb_bot_depth.weight", nullptr, 0, {ctx->Vb, D}, true);
   if (txt) {
     reg(ctx, "head_txt.weight", nullptr, 0, {cfg->vocab_txt, D}, true);
     reg(ctx, "ln_txt.weight", nullptr, 0, {D}, true);
@@ -833,7 +862,7 @@ static void launch_k(hq_ctx* ctx, cudaStream_t st, const char* tag, void (*kerne
 // ------------------------------------------------------------------------------------------------
 static bool chain_enabled(const hq_ctx* ctx, int B) {
   const int min_b = ctx->dbg.chain_min_batch > 0 ? ctx->dbg.chain_min_batch : 129;   // every GEMM on CTA-pair tiles
-  return ctx->chain_ok && ctx->d_maps != nullptr && B >= min_b && ctx->D <= LN_MAXV * LN_THREADS * 4 &&
+  return ctx->chain_ok && ctx->cfg.model_type == HQ_MODEL_PARALLEL && ctx->d_maps != nullptr && B >= min_b && ctx->D <= LN_MAXV * LN_THREADS * 4 &&
          ctx->chain_mode != hq_ctx::CHAIN_OFF;
 }
 
@@ -1049,8 +1078,19 @@ static void layernorm_act(hq_ctx* ctx, cudaStream_t st, float* x, const float* g
   // the lean instantiation (<= 3 partial sums in registers) unless the pending split is wider
   auto kern = f.n > 3 ? layernorm_kernel<AT, LN_MAXFOLD> : layernorm_kernel<AT, 3>;
   launch_k(ctx, st, "layernorm", kern, dim3(rows), dim3(LN_THREADS), 0, x, g, b, nullptr, out, rows,
-           ctx->D, 1, 0, f.partial, f.n, f.stride, f.bias);
+           ctx->D, 1, 0, f.partial, f.n, f.stride, f.bias, 1, 1);
   if (fold) *fold = Fold();
+}
+
+// LayerNorm with a row mapping (layernorm_kernel: input row (r / in_group) * in_mul + in_off + r % in_group, output row
+// r * out_mul); `fold` is NOT cleared: the 'bidirectional' depth pass normalises disjoint row sets with two launches.
+template <typename OutT>
+static void layernorm_rows(hq_ctx* ctx, cudaStream_t st, const char* tag, float* x, const float* g, const float* b,
+                           const float* add, OutT* out, int rows, int in_group, int in_mul, int in_off, int out_mul,
+                           const Fold& f) {
+  auto kern = f.n > 3 ? layernorm_kernel<OutT, LN_MAXFOLD> : layernorm_kernel<OutT, 3>;
+  launch_k(ctx, st, tag, kern, dim3(rows), dim3(LN_THREADS), 0, x, g, b, add, out, rows, ctx->D, in_mul, in_off, f.partial,
+           f.n, f.stride, f.bias, in_group, out_mul);
 }
 
 // May the decode attention request cached keys BEFORE griddepcontrol.wait?  Yes: run_position orders positions with a
@@ -1142,8 +1182,10 @@ static void attention(hq_ctx* ctx, cudaStream_t st, const AT* q, const AT* K, co
     int stages = 0, grid = 0;
     size_t smem2 = 0;
     // the tensor maps describe ctx->kc / ctx->vc: the TMA kernel needs K and V at the same offset inside them
-    const bool in_cache = reinterpret_cast<const char*>(K) - static_cast<const char*>(ctx->kc) ==
-                          reinterpret_cast<const char*>(V) - static_cast<const char*>(ctx->vc);
+    const ptrdiff_t koff = reinterpret_cast<const char*>(K) - static_cast<const char*>(ctx->kc);
+    const ptrdiff_t kv_bytes = static_cast<ptrdiff_t>(ctx->L) * ctx->max_batch * ctx->Tc * ctx->D * static_cast<ptrdiff_t>(ctx->wsize);
+    const bool in_cache = ctx->kc != nullptr && koff >= 0 && (koff < kv_bytes || ctx->L == 0) &&
+                          koff == reinterpret_cast<const char*>(V) - static_cast<const char*>(ctx->vc);
     if (sizeof(AT) == 2 && in_cache && attn_mma_plan(ctx, groups, hpc, M * groups, &stages, &smem2, &grid)) {
       launch_attn_mma<AT>(ctx, st, q, K, out, t_stride, kbase, hpc, groups, M * groups, stages, grid, smem2);
       return;
@@ -1334,6 +1376,7 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
     ea.cond = ctx->cond; ea.E_top = ctx->E_top; ea.E_bot = ctx->E_bot; ea.P_top = ctx->P_top; ea.P_emb = ctx->P_emb;
     ea.codes_top = ctx->codes_top; ea.codes_bot = ctx->codes_bot; ea.D = D; ea.S = S; ea.pos = pos;
     ea.cond_kind = ctx->cfg.cond_kind;
+    ea.emb_kind = ctx->cfg.embedding_kind; ea.P_top_h = ctx->P_top_h; ea.P_top_w = ctx->P_top_w; ea.Hpos = ctx->Hpos;
     launch_k(ctx, st, "embed", embed_kernel, dim3(B), dim3(eb), 0, ea);
   }
 
@@ -1357,9 +1400,62 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
     launch_k(ctx, st, "layernorm_f", fold_x.n > 3 ? layernorm_kernel<float, LN_MAXFOLD> : layernorm_kernel<float, 3>, dim3(B),
              dim3(LN_THREADS), 0, ctx->x, ctx->lnf_g, ctx->lnf_b,
              ctx->sos_depth, ctx->yd, B, D, prefill ? T0 : 1, prefill ? T0 - 1 : 0, fold_x.partial, fold_x.n, fold_x.stride,
-             fold_x.bias);
+             fold_x.bias, 1, ctx->cfg.model_type == HQ_MODEL_BIDIRECTIONAL ? 5 : 1);
   }
   fold_x = Fold();
+
+  SampleArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.logits = ctx->logits; sa.ldl = ctx->Vmax; sa.V = ctx->Vt; sa.R = B; sa.rows_per_b = 1; sa.slot0 = 0;
+  sa.sp = ctx->d_sp; sa.pos = pos; sa.S = S; sa.codes_top = ctx->codes_top; sa.codes_bot = ctx->codes_bot;
+  sa.forced = f.forced_top; sa.logits_out = f.logits_out; sa.Vmax = ctx->Vmax;
+  sa.temp_sel = 0; sa.filt_sel = 0; sa.bot_slot = -1;
+  auto head = [&](const Weight& w, int rows, int V) {
+    EpiParams<AT> e;
+    memset(&e, 0, sizeof(e));
+    e.outf = ctx->logits; e.ldo = ctx->Vmax;
+    gemm_any<EPI_F32>(ctx, st, ctx->h, w, 0, rows, V, D, e);
+  };
+
+  if (ctx->cfg.model_type == HQ_MODEL_TOP2BOT) {
+    // ---- 'top2bot' (sampling_depth_baseline, hierarchical_ar.py:565-664): five sequential single-token passes over the
+    //      depth blocks with a growing cache [Ld][B][5][D]; pass c writes slot c and attends over slots 0..c ----
+    for (int c = 0; c < 5; ++c) {
+      if (c >= 1) {
+        const float* E = c == 1 ? ctx->E_top_depth : ctx->E_bot_depth;
+        const int64_t* codes = c == 1 ? ctx->codes_top + pos : ctx->codes_bot + static_cast<size_t>(pos) * 4 + (c - 2);
+        launch_k(ctx, st, "embed_depth_seq", embed_depth_seq_kernel, dim3(B), dim3(eb), 0, ctx->yd, E,
+                 static_cast<const float*>(ctx->P_depth + static_cast<size_t>(c - 1) * D), codes, c == 1 ? S : 4 * S, D);
+      }
+      for (int l = 0; l < ctx->Ld; ++l)
+        run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, B, 0, kd + l * dstride, vd + l * dstride, 1, 5, c, c + 1, 0, &fold_y);
+      layernorm_act<AT>(ctx, st, ctx->yd, c == 0 ? ctx->lnt_g : ctx->lnb_g, c == 0 ? ctx->lnt_b : ctx->lnb_b, h, B, &fold_y);
+      head(c == 0 ? ctx->head_top : ctx->head_bot, B, c == 0 ? ctx->Vt : ctx->Vb);
+      sa.V = c == 0 ? ctx->Vt : ctx->Vb; sa.slot0 = c; sa.bot_slot = c - 1;
+      sa.temp_sel = sa.filt_sel = c == 0 ? 0 : 1;
+      sa.forced = c == 0 ? f.forced_top : f.forced_bot;
+      if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+    }
+    return;
+  }
+  if (ctx->cfg.model_type == HQ_MODEL_BIDIRECTIONAL) {
+    // ---- 'bidirectional' (hierarchical_ar.py:791-878): ONE pass over five tokens per image, [hs + sos_depth (written above
+    //      at rows 5b), pos_emb_depth[0..3]], unmasked attention among them; ln_top / head_top on token 0, ln_bot / head_bot on
+    //      tokens 1..4.  As in the reference every token is drawn with the bottom filters and softmax_temperature[0]. ----
+    launch_k(ctx, st, "depth_pos_rows", depth_pos_rows_kernel, dim3(B), dim3(eb), 0, ctx->yd, static_cast<const float*>(ctx->P_depth), D);
+    for (int l = 0; l < ctx->Ld; ++l)
+      run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, 5 * B, 2, kd + l * dstride, vd + l * dstride, 5, 5, 0, 5, 0, &fold_y);
+    layernorm_rows<AT>(ctx, st, "layernorm", ctx->yd, ctx->lnt_g, ctx->lnt_b, nullptr, h, B, 1, 5, 0, 1, fold_y);
+    head(ctx->head_top, B, ctx->Vt);
+    sa.temp_sel = 0; sa.filt_sel = 1;
+    if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+    layernorm_rows<AT>(ctx, st, "layernorm", ctx->yd, ctx->lnb_g, ctx->lnb_b, nullptr, h, 4 * B, 4, 5, 1, 1, fold_y);
+    fold_y = Fold();
+    head(ctx->head_bot, 4 * B, ctx->Vb);
+    sa.V = ctx->Vb; sa.R = 4 * B; sa.rows_per_b = 4; sa.slot0 = 1; sa.forced = f.forced_bot;
+    if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+    return;
+  }
 
   // ---- depth pass 0 -> top logits ----
   for (int l = 0; l < ctx->Ld; ++l)
@@ -1371,11 +1467,6 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
     e.outf = ctx->logits; e.ldo = ctx->Vmax;
     gemm_any<EPI_F32>(ctx, st, ctx->h, ctx->head_top, 0, B, ctx->Vt, D, e);
   }
-  SampleArgs sa;
-  memset(&sa, 0, sizeof(sa));
-  sa.logits = ctx->logits; sa.ldl = ctx->Vmax; sa.V = ctx->Vt; sa.R = B; sa.rows_per_b = 1; sa.slot0 = 0;
-  sa.sp = ctx->d_sp; sa.pos = pos; sa.S = S; sa.codes_top = ctx->codes_top; sa.codes_bot = ctx->codes_bot;
-  sa.forced = f.forced_top; sa.logits_out = f.logits_out; sa.Vmax = ctx->Vmax;
   if (chain) chain_end(ctx, st);
   if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
 
@@ -1398,6 +1489,7 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
     gemm_any<EPI_F32>(ctx, st, ctx->h, ctx->head_bot, 0, 4 * B, ctx->Vb, D, e);
   }
   sa.V = ctx->Vb; sa.R = 4 * B; sa.rows_per_b = 4; sa.slot0 = 1; sa.forced = f.forced_bot;
+  sa.temp_sel = 1; sa.filt_sel = 1;
   if (chain) chain_end(ctx, st);
   if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
 }
@@ -1724,6 +1816,7 @@ extern "C" int hq_debug_sample(const float* logits, int R, int V, float temperat
   sa.logits = logits; sa.ldl = V; sa.V = V; sa.R = R; sa.rows_per_b = 1; sa.slot0 = slot; sa.sp = nullptr;
   sa.pos = position; sa.S = 1; sa.flat_out = out_codes; sa.probs_out = out_probs; sa.Vmax = V;
   sa.temperature = temperature; sa.top_p = top_p; sa.top_k = top_k; sa.seed = seed; sa.row_offset = row_offset;
+  sa.bot_slot = -1;
   launch_sample(&tmp, static_cast<cudaStream_t>(stream), sa);
   if (tmp.launch_err != cudaSuccess) {
     set_err(nullptr, "hq_debug_sample launch failed: %s", cudaGetErrorString(tmp.launch_err));

@@ -57,15 +57,21 @@ class iHQGPT:
                  device: Union[int, str, torch.device] = 0, precision: str = "bf16", max_batch: int = 16,
                  max_seq_len: int = 64, use_cuda_graph: bool = True, use_pdl: bool = True,
                  use_chain: bool = False) -> None:
-        if model_type != "parallel":
+        if model_type not in ("parallel", "top2bot", "bidirectional"):
             raise NotImplementedError(
-                f"model_type={model_type!r}: only 'parallel' (1 top + 4 bottom codes in two depth passes) is implemented; "
-                "'top2bot' / 'bidirectional' are listed as next in SURVEY.md 8f")
+                f"model_type={model_type!r}: 'parallel', 'top2bot' and 'bidirectional' with a 2x2 bottom window are "
+                "implemented (hierarchical_ar.py:40-57 also parses 'parallel<N>' / 'bidirectional<N>' window sizes)")
         if ratio_bot2top != 4:
             raise NotImplementedError("ratio_bot2top must be 4 (8x8 top + 16x16 bottom codes)")
         emb = getattr(hparams, "embedding_type", "transformer1")
-        if emb != "transformer1" or getattr(hparams, "position_embedding", "1d") != "1d":
-            raise NotImplementedError(f"embedding_type={emb!r} / position_embedding: only 'transformer1' + '1d' are implemented")
+        pos_emb = getattr(hparams, "position_embedding", "1d")
+        if emb not in ("transformer1", "reduce") or pos_emb not in ("1d", "2d"):
+            raise NotImplementedError(
+                f"embedding_type={emb!r} / position_embedding={pos_emb!r}: 'transformer1' | 'reduce' with '1d' | '2d' are "
+                "implemented ('baseline', 'multiple' and 'transformer<N>' with N > 1 embedding blocks are not)")
+        if getattr(hparams, "use_random_order", False):
+            raise NotImplementedError("use_random_order=True is not implemented")
+        self.embedding_type, self.position_embedding = emb, pos_emb
         if getattr(hparams, "gelu_use_approx", False):
             raise NotImplementedError("gelu_use_approx=True is not implemented (shipped configs use exact erf GELU)")
         if hparams_dec is None:                                   # hierarchical_ar.py:150-153
@@ -75,7 +81,8 @@ class iHQGPT:
             raise NotImplementedError("depth transformer must share embed_dim / n_heads with the spatial transformer")
         self.use_cls_cond, self.use_txt_cond = bool(use_cls_cond), bool(use_txt_cond)
         self.model_type = model_type
-        self.bot_win, self.num_bottom_pred, self.ratio_bot2top = 2, 4, ratio_bot2top
+        self.bot_win = 1 if model_type == "top2bot" else 2          # hierarchical_ar.py:40-59
+        self.num_bottom_pred, self.ratio_bot2top = self.bot_win * self.bot_win, ratio_bot2top
         self.len_seq_depth = 1 + ratio_bot2top // self.num_bottom_pred
         self.top_win = int(math.sqrt(ratio_bot2top)) // self.bot_win
         self.idx_pred = hparams.ctx_len_txt if (self.use_txt_cond and not self.use_cls_cond) else 0
@@ -94,7 +101,7 @@ class iHQGPT:
                                vocab_txt=vocab_size_txt, n_classes=self.n_classes or 0, ctx_len_img=self.ctx_len_img,
                                ctx_len_txt=self.ctx_len_txt, cond=self.cond, max_seq_len=self.max_seq_len,
                                device=self.device, use_cuda_graph=use_cuda_graph, use_pdl=use_pdl,
-                               use_chain=use_chain)
+                               use_chain=use_chain, model_type=model_type, embedding_type=emb, position_embedding=pos_emb)
         self._max_batch = max_batch
         self._engines: Dict[str, Engine] = {}
         self._source: Optional[Dict[str, torch.Tensor]] = None    # retained only when asked (other-precision engine)
@@ -151,9 +158,17 @@ class iHQGPT:
             s["sos"] = (1, 1, D)
         s["sos_depth"] = (1, 1, D)
         s["tok_emb_top.weight"] = (self.vocab_size_top, D)
-        s["tok_emb_bot.weight"] = (self.vocab_size_bot, D)
-        s["pos_emb_emb.weight"] = (5, D)
-        s["pos_emb_top.weight"] = (self.ctx_len_img, D)
+        if self.embedding_type == "reduce":                       # hierarchical_ar.py:85-88
+            s["tok_emb_bot.weight"] = (self.vocab_size_bot, D // 4)
+        else:
+            s["tok_emb_bot.weight"] = (self.vocab_size_bot, D)
+            s["pos_emb_emb.weight"] = (5, D)
+        if self.position_embedding == "2d":                       # :121-125
+            H = int(math.sqrt(self.ctx_len_img))
+            s["pos_emb_top_h.weight"] = (H, D)
+            s["pos_emb_top_w.weight"] = (H, D)
+        else:
+            s["pos_emb_top.weight"] = (self.ctx_len_img, D)
         for i in range(self.n_layers):
             s.update(_block_shapes(f"blocks.{i}", D))
         s["ln_f.weight"] = (D,)

@@ -4,6 +4,7 @@ Run in the build container (where /root/reference exists):
 
     python -m oracle.make_golden            # writes tests/golden/ (small models + filters)
     python -m oracle.make_golden --full-size    # only the ImageNet-L12-size golden (BASELINE config 1 at real scale)
+    python -m oracle.make_golden --variants     # only the 8f-3 model variants (reduce / 2d / top2bot / bidirectional)
     python -m oracle.make_golden --all
 
 The reference has no tests or golden vectors of its own, so these files are the
@@ -160,6 +161,27 @@ def golden_uncond(cfg, name, seed, init, B):
     print(name, "done")
 
 
+def golden_variant(cfg, name, seed, init, labels=None, B=3):
+    """SURVEY.md 8f-3 variants of the 2-level model (embedding_type 'reduce', position_embedding '2d', model_type 'top2bot' /
+    'bidirectional', unconditional sos): greedy code grids of the reference's own sampler; class-conditional models are
+    driven row by row with per-row classes (`iHQGPT.sampling_step` unchanged), unconditional ones through `sampling_ihqgpt`."""
+    P = O.make_params(cfg, seed=seed, init=init)
+    model = R.build_reference_model(cfg, P)
+    if cfg.cond == "cls":
+        labels_t = torch.tensor(labels, dtype=torch.long)
+        ct, cb = reference_sample_rows(model, model.sos(labels_t).unsqueeze(1), 64, **GREEDY)
+        cond, n = labels_t, len(labels)
+        extra = dict(labels=np.asarray(labels, dtype=np.int64))
+    else:
+        ct, cb = R.reference_sample(model, B, None, max_seq_len=64, **GREEDY)
+        cond, n = None, B
+        extra = {}
+    margin = full_run_margin(cfg, P, cond, n)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name), meta=meta(cfg, seed, init, min_logit_margin=margin),
+                        codes_top=ct.numpy(), codes_bot=cb.numpy(), **extra)
+    print(name, "min greedy margin over the run", margin)
+
+
 def golden_filters(name):
     """Known answers of cutoff_topk_logits / cutoff_topp_probs (sampling.py:12-37) incl. ties."""
     _, S = R.import_reference()
@@ -190,6 +212,18 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if "--variants" in sys.argv or "--all" in sys.argv:
+        # seeds searched (oracle) for a greedy margin >= 2e-4 over the whole run, as for the other goldens
+        V = lambda **kw: O.HQConfig(**{**O.TINY.to_dict(), **kw})
+        golden_variant(V(embedding_type="reduce", cond="uncond"), "tiny_reduce_uncond_greedy.npz", seed=21, init="rich", B=2)
+        golden_variant(V(position_embedding="2d"), "tiny_pos2d_cls_greedy.npz", seed=31, init="rich", labels=[1, 8, 3])
+        golden_variant(V(model_type="top2bot"), "tiny_top2bot_cls_greedy.npz", seed=31, init="rich", labels=[5, 0, 9])
+        golden_variant(V(model_type="bidirectional"), "tiny_bidir_cls_greedy.npz", seed=24, init="rich", labels=[2, 7, 4])
+        golden_variant(O.HQConfig(**{**O.ASYM.to_dict(), "model_type": "top2bot", "embedding_type": "reduce",
+                                     "position_embedding": "2d"}), "asym_top2bot_reduce_pos2d_greedy.npz", seed=62,
+                       init="rich", labels=[6, 1, 4, 0])
+        if "--all" not in sys.argv:
+            return 0
     if "--full-size" in sys.argv or "--all" in sys.argv:       # ~1 min of CPU: the reference at ImageNet-L12 size
         golden_cls_full_size(O.IMAGENET_L12, "l12_cls_greedy_b4.npz", seed=0, labels=[166, 721, 312, 49])   # margin 1.6e-4 (label sets searched for >= 1e-4)
         if "--all" not in sys.argv:

@@ -26,7 +26,8 @@ def hparams_of(cfg: O.HQConfig, n_layers=None):
                            n_dense_layers=cfg.n_layers, ctx_len=None, ctx_len_img=cfg.ctx_len_img,
                            ctx_len_txt=cfg.ctx_len_txt, embd_pdrop=0.0, resid_pdrop=0.0, attn_pdrop=0.0, mlp_bias=True,
                            attn_bias=True, gelu_use_approx=False, use_head_txt=True, n_classes=cfg.n_classes,
-                           causal_attn=None, embedding_type="transformer1", position_embedding="1d",
+                           causal_attn=None, embedding_type=getattr(cfg, "embedding_type", "transformer1"),
+                           position_embedding=getattr(cfg, "position_embedding", "1d"),
                            bottom_head_type="linear", use_random_order=False, rate_random_order=1.0)
 
 
@@ -36,7 +37,7 @@ def build_model(cfg: O.HQConfig, params, precision="fp32", max_batch=8, use_cuda
     import hqtransformer_b200 as H
     model = H.iHQGPT(vocab_size_top=cfg.vocab_top, vocab_size_bot=cfg.vocab_bot, vocab_size_txt=cfg.vocab_txt,
                      ratio_bot2top=4, use_cls_cond=(cfg.cond == "cls"), use_txt_cond=(cfg.cond == "txt"),
-                     model_type="parallel", hparams=hparams_of(cfg), hparams_dec=hparams_of(cfg, cfg.n_layers_depth),
+                     model_type=getattr(cfg, "model_type", "parallel"), hparams=hparams_of(cfg), hparams_dec=hparams_of(cfg, cfg.n_layers_depth),
                      device=0, precision=precision, max_batch=max_batch, use_cuda_graph=use_cuda_graph,
                      max_seq_len=max_seq_len, use_pdl=use_pdl, use_chain=use_chain)
     model.load_state_dict(params, strict=True)

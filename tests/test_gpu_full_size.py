@@ -90,7 +90,8 @@ def test_l12_b4_greedy_grid_bit_exact_vs_reference_golden(l12_params, l12_bf16):
     import hqtransformer_b200 as H
     from tests.helpers import load_golden
     g, meta = load_golden("l12_cls_greedy_b4.npz")
-    assert meta["config"] == CFG.to_dict() and meta["seed"] == 0 and meta["min_logit_margin"] >= 1e-4
+    from tests.helpers import cfg_from_meta
+    assert cfg_from_meta(meta) == CFG and meta["seed"] == 0 and meta["min_logit_margin"] >= 1e-4
     labels = torch.from_numpy(g["labels"])
     m32 = build_model(CFG, l12_params, precision="fp32", max_batch=4)
     ct, cb = H.sampling_ihqgpt(m32, 4, labels, top_k_top=1, top_p_top=1.0, top_k_bot=1, top_p_bot=1.0, use_fp16=False,

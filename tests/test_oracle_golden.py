@@ -135,3 +135,40 @@ def test_teacher_forced_forward_matches_incremental_sampling():
         out = model((ct, bot_grid.reshape(ct.shape[0], -1)), torch.from_numpy(g["labels"]))
     logits_top, logits_bot = out[0], out[1]
     assert torch.equal(logits_top.argmax(-1), ct)
+
+
+VARIANT_GOLDENS = ["tiny_reduce_uncond_greedy.npz", "tiny_pos2d_cls_greedy.npz", "tiny_top2bot_cls_greedy.npz",
+                   "tiny_bidir_cls_greedy.npz", "asym_top2bot_reduce_pos2d_greedy.npz"]
+
+
+@pytest.mark.parametrize("name", VARIANT_GOLDENS)
+def test_oracle_model_variants_equal_reference(name):
+    """embedding_type 'reduce', position_embedding '2d', model_type 'top2bot' / 'bidirectional',
+    unconditional sos - greedy grids of the unmodified reference (oracle/make_golden.py --variants)."""
+    g, meta = load_golden(name)
+    cfg = cfg_from_meta(meta)
+    assert meta["min_logit_margin"] >= 1e-4
+    P = O.make_params(cfg, seed=meta["seed"], init=meta["init"])
+    B = g["codes_top"].shape[0]
+    cond = torch.from_numpy(g["labels"]) if cfg.cond == "cls" else None
+    ct, cb = O.sample(P, cfg, cond, B, **GREEDY)
+    assert np.array_equal(ct.numpy(), g["codes_top"]) and np.array_equal(cb.numpy(), g["codes_bot"])
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="reference tree absent")
+@pytest.mark.parametrize("kw", [dict(model_type="top2bot"), dict(model_type="bidirectional"),
+                                dict(embedding_type="reduce", position_embedding="2d", cond="uncond")])
+def test_oracle_variants_stochastic_equal_live_reference(kw):
+    """Same torch seed, same draw order -> identical stochastic sequences ('bidirectional' draws every token with the
+    bottom filters and softmax_temperature[0], hierarchical_ar.py:860-866)."""
+    from dataclasses import replace
+    cfg = replace(O.TINY, **kw)
+    P = O.make_params(cfg, seed=3, init="rich")
+    model = R.build_reference_model(cfg, P)
+    cond = 4 if cfg.cond == "cls" else None
+    skw = dict(top_k_top=8, top_p_top=0.9, top_k_bot=16, top_p_bot=0.95, softmax_temperature=[0.9, 1.1])
+    torch.manual_seed(5)
+    ct, cb = R.reference_sample(model, 3, cond, max_seq_len=6, **skw)
+    torch.manual_seed(5)
+    ot, ob = O.sample(P, cfg, cond, 3, max_seq_len=6, **skw)
+    assert torch.equal(ct, ot) and torch.equal(cb, ob)
