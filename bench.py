@@ -201,7 +201,7 @@ def run_reference_arm(args, rank: int):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
             "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.model}: class-conditional HQ-Transformer sampling, 64 top positions x (1 top + 4 "
+            "config": {"workload": f"{args.model}: {s2.cond}-conditional HQ-Transformer sampling, 64 top positions x (1 top + 4 "
                                    f"bottom codes), random-init weights, top_k=None top_p=None T=1.0; CPU sample: batch {B}, "
                                    f"{positions} positions per step",
                        "model": args.model, "batch": B, "positions": positions, "same_config_as_gpu_arm": False,
@@ -417,7 +417,7 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
     line = {"metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.model}: class-conditional HQ-Transformer sampling, 64 top positions x (1 top + 4 bottom "
+            "config": {"workload": f"{args.model}: {s2.cond}-conditional HQ-Transformer sampling, 64 top positions x (1 top + 4 bottom "
                                    f"codes), batch {B} per GPU, random-init weights, top_k={args.top_k or None} "
                                    f"top_p={args.top_p or None} T={args.temperature}",
                        "model": args.model, "batch_per_gpu": B, "global_batch": world * B, "positions": S,
@@ -439,9 +439,10 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
         if not args.no_kernel_table:
             rows, span_us = kernel_table(eng, sp, B, cond_dev, local_ct, local_cb, D, peaks)
             traffic = {}
-            tp = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+            tp = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
             if os.path.isfile(tp):
                 traffic = json.load(open(tp))
+            traffic.pop("_source", None)
             gemm_rows = [r for r in rows if r["kernel"].startswith("gemm")]
             gemm_us = sum(r["us_per_position"] for r in gemm_rows)
             gemm_flops = sum(r["flops"] * r["launches_per_position"] for r in gemm_rows)
@@ -457,7 +458,8 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
                 "hbm_view": {"achieved_gbs": dom["weight_gbs"], "peak_gbs": peaks["hbm_gbs"], "frac": dom["frac_hbm"]},
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 "how": "device %globaltimer per launch inside the replayed loop (hq_trace_run), top positions 30-33; "
-                       "traffic from profiles/r1_ncu_traffic.json (ncu --set full of the same command)"}
+                       "traffic IMPORTED from profiles/r2_ncu_traffic.json (ncu --set full capture of the same command, "
+                       "committed; not measured in this run)"}
             line["roofline_gemm_all"] = {
                 "bound": "tensor", "kernel": "all tcgen05 GEMM launches of a top position", "achieved": gemm_flops / gemm_us * 1e-6,
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",

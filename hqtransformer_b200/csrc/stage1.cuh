@@ -1,0 +1,435 @@
+// Stage-1 decode of sampled code grids: `SimRQGAN2Generator.decode_code`
+// (hqvae/models/stage1/generator.py:312-367) for the shipped HQ-VAE configuration (decoding_type 'concat', upsample
+// 'pixelshuffle'): codebook gather + PixelShuffle + concat -> post_quant_conv_b (1x1) -> VQGAN Decoder
+// (stage1/modules/layers.py:300-410: conv_in, mid {ResnetBlock, AttnBlock, ResnetBlock}, per level {ResnetBlock (+ AttnBlock
+// at the attention resolution)} x (num_res_blocks + 1) + nearest-2x Upsample conv, GroupNorm + swish + conv_out).
+//
+// Layout.  Activations are NHWC with a one-pixel ZERO border: a [B, H+2, W+2, C] tensor viewed as a matrix [B (H+2)(W+2), C].
+// A 3x3 convolution is then nine SHIFTED GEMMs accumulated in TMEM: tap (ky, kx) reads the same matrix (ky-1)(W+2) + (kx-1)
+// rows further down - one plain 2-D TMA tile load per k-block with a row offset, no im2col buffer, out-of-range rows are
+// zero-filled by TMA - against the weight stored [Cout, 9 Cin] tap-major.  Outputs are computed for every padded position
+// and the epilogue keeps only interior pixels, so borders stay zero.  The residual stream is fp32 (as in the sampler);
+// GroupNorm (fp32 statistics, deterministic two-level reduction) writes the bf16 GEMM input.
+#pragma once
+
+#include "chain.cuh"
+
+namespace hq {
+
+// ------------------------------------------------------------------------------------------------
+// implicit-GEMM convolution on CTA pairs (tcgen05, cta_group::2): 256 padded positions x bn output channels per tile
+// ------------------------------------------------------------------------------------------------
+enum { S1_OUT_F32 = 0, S1_OUT_BF16 = 1, S1_OUT_IMAGE = 2 };
+
+struct ConvParams {
+  int R;            // padded positions in total (B * Hp * Wp) = rows of the A matrix
+  int Cin, CoutPad, cout;   // CoutPad: weight rows (multiple of bn, zero-padded); cout: real output channels
+  int taps;         // 1 (1x1) | 9 (3x3, padding 1)
+  int Hp, Wp;       // padded height / width (H + 2, W + 2)
+  int bn;           // tile width
+  int mode;         // S1_OUT_*
+  int ldo;          // row stride (elements) of the output matrix (modes 0 / 1)
+  const float* bias;    // [CoutPad]
+  const float* res;     // optional fp32 residual [R, ldo] (mode 0), may alias outf
+  float* outf;          // mode 0: fp32 [R, ldo]; mode 2: image [B, cout, H, W] fp32
+  bf16* outb;           // mode 1: bf16 [R, ldo]
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CH_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, ConvParams p) {
+#if defined(__CUDA_ARCH__)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* slab = smem + CH_STAGES * CH_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slab + CH_SLAB_BYTES);
+  uint64_t* empty_bar = full_bar + CH_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + CH_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int bn = p.bn;
+  const int nt = p.CoutPad / bn, mt = (p.R + 255) / 256;
+  const int total_tiles = nt * mt;
+  const int kpt = p.Cin / 64;                       // k-blocks per tap
+  const int num_kb = p.taps * kpt;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < CH_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 2 * CH_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, 2 * CH_ACC_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: tap (ky, kx) of a 3x3 kernel reads the activation matrix (ky-1) Wp + (kx-1) rows below the
+      //      output row; rows outside [0, R) are zero-filled by TMA.  Column tile fastest: the pairs working on the same
+      //      row block at the same time share its A tiles through L2. ----
+      const uint32_t stage_tx = 2u * static_cast<uint32_t>(CH_A_BYTES + bn * 64);
+      uint32_t g = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const int m0 = (tile / nt) * 256 + static_cast<int>(rank) * 128;
+        const int wrow = (tile % nt) * bn + static_cast<int>(rank) * (bn / 2);
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int tap = kb / kpt, kc = kb - tap * kpt;
+          const int off = p.taps == 9 ? (tap / 3 - 1) * p.Wp + (tap % 3 - 1) : 0;
+          const int s = static_cast<int>(g % CH_STAGES);
+          mbar_wait(&empty_bar[s], ((g / CH_STAGES) & 1) ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+          tma_load_2d_2sm(smem + s * CH_STAGE_BYTES, &tmA, &full_bar[s], kc * 64, m0 + off);
+          tma_load_2d_2sm(smem + s * CH_STAGE_BYTES + CH_A_BYTES, &tmW, &full_bar[s], kb * 64, wrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, bn);
+      uint32_t g = 0, it = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+        const uint32_t buf = it & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * CH_ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = static_cast<int>(g % CH_STAGES);
+          mbar_wait(&full_bar[s], (g / CH_STAGES) & 1);
+          tc_fence_after();
+          const uint64_t da = umma_smem_desc_sw128(smem_u32(smem + s * CH_STAGE_BYTES));
+          const uint64_t db = umma_smem_desc_sw128(smem_u32(smem + s * CH_STAGE_BYTES + CH_A_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_2sm(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[s], 0x3);
+        }
+        umma_commit_2sm(&tmem_full_bar[buf], 0x3);
+      }
+    }
+  } else {
+    // ---- epilogue: bias (+ fp32 residual), interior pixels only ----
+    const int ew = (warp & 3) + ((warp - 2) >> 2) * 4;
+    const int quarter = warp & 3, half = ew >> 2;
+    const int etid = ew * 32 + lane;
+    const int piece = lane & 7;
+    const int HpWp = p.Hp * p.Wp, H = p.Hp - 2, W = p.Wp - 2;
+    uint8_t* myslab = slab + ew * 4096;
+    const uint32_t slab_u32 = smem_u32(myslab);
+    uint32_t it = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+      const uint32_t buf = it & 1;
+      const int m0 = (tile / nt) * 256 + static_cast<int>(rank) * 128;
+      const int n0 = (tile % nt) * bn;
+      named_bar(1, 256);
+      for (int i = etid; i < bn; i += 256) sbias[i] = p.bias[n0 + i];
+      // rows this lane writes: it8*4 + (lane >> 3) of the warp's 32
+      bool row_ok[8];
+      size_t row_off[8];
+#pragma unroll
+      for (int r8 = 0; r8 < 8; ++r8) {
+        const int m = m0 + quarter * 32 + r8 * 4 + (lane >> 3);
+        const int b = m / HpWp, q = m - b * HpWp;
+        const int y = q / p.Wp, x = q - y * p.Wp;
+        row_ok[r8] = m < p.R && y >= 1 && y <= H && x >= 1 && x <= W;
+        row_off[r8] = p.mode == S1_OUT_IMAGE ? (static_cast<size_t>(b) * p.cout * H + (y - 1)) * W + (x - 1)
+                                             : static_cast<size_t>(m) * p.ldo;
+      }
+      named_bar(1, 256);
+      mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + buf * CH_ACC_COLS;
+#pragma unroll 1
+      for (int c = half; c < bn / 32; c += 2) {
+        uint32_t r[32];
+        tmem_ld_32x32(acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = slab_u32 + lane * 128 + ((j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                       "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
+        }
+        __syncwarp();
+        const int col = n0 + c * 32 + piece * 4;
+        const float4 b4 = *reinterpret_cast<const float4*>(sbias + c * 32 + piece * 4);
+        if (col < p.cout) {
+#pragma unroll
+          for (int r8 = 0; r8 < 8; ++r8) {
+            const int row = r8 * 4 + (lane >> 3);
+            float4 v;
+            const uint32_t addr = slab_u32 + row * 128 + ((piece ^ (row & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+            if (!row_ok[r8]) continue;
+            if (p.mode == S1_OUT_F32) {
+              float4* dst = reinterpret_cast<float4*>(p.outf + row_off[r8] + col);
+              if (p.res != nullptr) {
+                const float4 a = *reinterpret_cast<const float4*>(p.res + row_off[r8] + col);
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+              }
+              *dst = v;
+            } else if (p.mode == S1_OUT_BF16) {
+              uint2 u;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+              u.x = *reinterpret_cast<uint32_t*>(&h0);
+              u.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(p.outb + row_off[r8] + col) = u;
+            } else {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+              const size_t plane = static_cast<size_t>(H) * W;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (col + e < p.cout) p.outf[row_off[r8] + static_cast<size_t>(col + e) * plane] = vv[e];
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[buf], 0);
+    }
+  }
+  __syncwarp();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * CH_ACC_COLS);
+  }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise / reduction kernels of the decoder
+// ------------------------------------------------------------------------------------------------
+// codes -> input of post_quant_conv_b (generator.py:316-319): channels [0, E) = PixelShuffle(2) of the top entry (E*4 wide:
+// out[c, y, x] = in[4c + 2 (y % 2) + (x % 2), y / 2, x / 2]), channels [E, 2E) = the bottom entry.  One CTA per bottom pixel.
+__global__ void __launch_bounds__(256)
+s1_quant_kernel(const int64_t* __restrict__ code_t, const int64_t* __restrict__ code_b, const float* __restrict__ E_t,
+                const float* __restrict__ E_b, bf16* __restrict__ out, int E, int hb /*bottom grid side*/, int n_embed, int* err) {
+  const int pix = blockIdx.x;                  // b * hb * hb + y * hb + x
+  const int b = pix / (hb * hb), q = pix % (hb * hb), y = q / hb, x = q % hb;
+  const int ht = hb / 2;
+  const int64_t ct = code_t[(static_cast<size_t>(b) * ht + y / 2) * ht + x / 2];
+  const int64_t cb = code_b[pix];
+  if (ct < 0 || ct >= n_embed || cb < 0 || cb >= n_embed) {
+    if (threadIdx.x == 0) atomicExch(err, 1);
+    return;
+  }
+  const float* et = E_t + static_cast<size_t>(ct) * 4 * E + 2 * (y & 1) + (x & 1);
+  const float* eb = E_b + static_cast<size_t>(cb) * E;
+  bf16* o = out + (static_cast<size_t>(b) * (hb + 2) * (hb + 2) + static_cast<size_t>(y + 1) * (hb + 2) + (x + 1)) * 2 * E;
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    o[c] = __float2bfloat16_rn(et[4 * c]);
+    o[E + c] = __float2bfloat16_rn(eb[c]);
+  }
+}
+
+// GroupNorm(32 groups, eps 1e-6; layers.py:17-21) statistics over the interior of a padded fp32 NHWC tensor: partial (sum,
+// sum of squares) in double per (image, group, slice of rows); grid (S slices, 32 groups, B).  Deterministic: the apply
+// kernel adds the S partials in a fixed order.
+__global__ void __launch_bounds__(256)
+s1_gn_stats_kernel(const float* __restrict__ x, double* __restrict__ part, int Hp, int Wp, int C, int S) {
+  const int s = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+  const int H = Hp - 2, W = Wp - 2, cg = C / 32;
+  const int rows_per = (H + S - 1) / S;
+  const int y0 = s * rows_per, y1 = min(H, y0 + rows_per);
+  double sum = 0.0, sq = 0.0;
+  const int n = (y1 - y0) * W * cg;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i % cg, px = i / cg, yy = y0 + px / W, xx = px % W;
+    const float v = x[((static_cast<size_t>(b) * Hp + yy + 1) * Wp + xx + 1) * C + g * cg + c];
+    sum += v;
+    sq += static_cast<double>(v) * v;
+  }
+  __shared__ double ssum[8], ssq[8];
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = sum; ssq[threadIdx.x >> 5] = sq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, q = 0.0;
+    for (int w = 0; w < 8; ++w) { a += ssum[w]; q += ssq[w]; }
+    double* o = part + ((static_cast<size_t>(b) * 32 + g) * S + s) * 2;
+    o[0] = a;
+    o[1] = q;
+  }
+}
+
+__device__ __forceinline__ float swish_f(float v) { return v / (1.0f + expf(-v)); }
+
+// y = GroupNorm(x) (optionally * sigmoid) as bf16, interior pixels only (the border of `out` stays zero).  One CTA per
+// padded row (b, y); thread = 4 channels of a pixel.
+__global__ void __launch_bounds__(256)
+s1_gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ part, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, bf16* __restrict__ out, int Hp, int Wp, int C, int S, int swish) {
+  const int b = blockIdx.y, y = blockIdx.x + 1;
+  const int H = Hp - 2, W = Wp - 2, cg = C / 32;
+  __shared__ float s_mean[32], s_rstd[32];
+  if (threadIdx.x < 32) {
+    const double* pp = part + (static_cast<size_t>(b) * 32 + threadIdx.x) * S * 2;
+    double a = 0.0, q = 0.0;
+    for (int s = 0; s < S; ++s) { a += pp[2 * s]; q += pp[2 * s + 1]; }
+    const double n = static_cast<double>(H) * W * cg;
+    const double mean = a / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-6));
+  }
+  __syncthreads();
+  const int c4 = C / 4;
+  const size_t base = (static_cast<size_t>(b) * Hp + y) * Wp * C;
+  for (int i = threadIdx.x; i < W * c4; i += blockDim.x) {
+    const int xx = i / c4 + 1, c = (i % c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + base + static_cast<size_t>(xx) * C + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    const int g = c / cg;                       // cg % 4 == 0: the four channels share a group
+    const float m = s_mean[g], r = s_rstd[g];
+    float o0 = (v.x - m) * r * ga.x + be.x, o1 = (v.y - m) * r * ga.y + be.y;
+    float o2 = (v.z - m) * r * ga.z + be.z, o3 = (v.w - m) * r * ga.w + be.w;
+    if (swish) { o0 = swish_f(o0); o1 = swish_f(o1); o2 = swish_f(o2); o3 = swish_f(o3); }
+    uint2 u;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(out + base + static_cast<size_t>(xx) * C + c) = u;
+  }
+}
+
+// nearest-neighbour 2x upsampling (Upsample, layers.py:49-52) fp32 [B, H+2, W+2, C] -> bf16 [B, 2H+2, 2W+2, C]: the input
+// of the level's upsample convolution.  up = 1: plain fp32 -> bf16 copy of the interior (input of a nin_shortcut 1x1 conv).
+__global__ void __launch_bounds__(256)
+s1_resample_kernel(const float* __restrict__ x, bf16* __restrict__ out, int H, int W, int C, int up) {
+  const int b = blockIdx.y, yo = blockIdx.x;           // output interior row 0 .. up*H-1
+  const int Wo = up * W, c4 = C / 4;
+  const float* src = x + ((static_cast<size_t>(b) * (H + 2) + yo / up + 1) * (W + 2)) * C;
+  bf16* dst = out + ((static_cast<size_t>(b) * (up * H + 2) + yo + 1) * (Wo + 2)) * C;
+  for (int i = threadIdx.x; i < Wo * c4; i += blockDim.x) {
+    const int xo = i / c4, c = (i % c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + static_cast<size_t>(xo / up + 1) * C + c);
+    uint2 u;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(dst + static_cast<size_t>(xo + 1) * C + c) = u;
+  }
+}
+
+// AttnBlock core (layers.py:170-183): single-head attention over the N = H W pixels of an image, C channels, scale C^-1/2.
+// qkv: bf16 padded [B, Hp, Wp, 3C] (q | k | v along channels); out: bf16 padded [B, Hp, Wp, C] (interior only).
+// One CTA (256 threads) per (image, tile of S1_ATT_Q queries): scores in shared memory, full softmax, then P V.
+constexpr int S1_ATT_Q = 8;
+__global__ void __launch_bounds__(256)
+s1_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int H, int W, int C) {
+  extern __shared__ float s1_att_smem[];
+  const int N = H * W, Wp = W + 2;
+  float* sq = s1_att_smem;                     // [S1_ATT_Q][C]
+  float* sp = sq + S1_ATT_Q * C;               // [S1_ATT_Q][N]
+  __shared__ float red[S1_ATT_Q][8];
+  const int b = blockIdx.y, q0 = blockIdx.x * S1_ATT_Q;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const size_t img = static_cast<size_t>(b) * (H + 2) * Wp;
+  auto prow = [&](int n) { return img + static_cast<size_t>(n / W + 1) * Wp + (n % W + 1); };
+  for (int i = tid; i < S1_ATT_Q * C; i += blockDim.x) {
+    const int qi = i / C, c = i % C, n = q0 + qi;
+    sq[i] = n < N ? __bfloat162float(qkv[prow(n) * 3 * C + c]) : 0.f;
+  }
+  __syncthreads();
+  const float scale = rsqrtf(static_cast<float>(C));
+  for (int j = tid; j < N; j += blockDim.x) {
+    const bf16* kr = qkv + prow(j) * 3 * C + C;
+    float acc[S1_ATT_Q];
+#pragma unroll
+    for (int qi = 0; qi < S1_ATT_Q; ++qi) acc[qi] = 0.f;
+    for (int c = 0; c < C; c += 8) {
+      float kv[8];
+      load8(kr + c, kv);
+#pragma unroll
+      for (int qi = 0; qi < S1_ATT_Q; ++qi)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[qi] = fmaf(sq[qi * C + c + e], kv[e], acc[qi]);
+    }
+#pragma unroll
+    for (int qi = 0; qi < S1_ATT_Q; ++qi) sp[qi * N + j] = acc[qi] * scale;
+  }
+  __syncthreads();
+  // softmax over the keys of each query: warp `wid` owns query `wid`
+  if (wid < S1_ATT_Q) {
+    float mx = -INFINITY;
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, sp[wid * N + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      const float e = expf(sp[wid * N + j] - mx);
+      sp[wid * N + j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[wid][0] = 1.0f / sum;
+  }
+  __syncthreads();
+  for (int c = tid * 2; c < C; c += blockDim.x * 2) {
+    float a0[S1_ATT_Q], a1[S1_ATT_Q];
+#pragma unroll
+    for (int qi = 0; qi < S1_ATT_Q; ++qi) a0[qi] = a1[qi] = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(qkv + prow(j) * 3 * C + 2 * C + c);
+      const float2 vf = __bfloat1622float2(v2);
+#pragma unroll
+      for (int qi = 0; qi < S1_ATT_Q; ++qi) {
+        const float w = sp[qi * N + j];
+        a0[qi] = fmaf(w, vf.x, a0[qi]);
+        a1[qi] = fmaf(w, vf.y, a1[qi]);
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < S1_ATT_Q; ++qi) {
+      const int n = q0 + qi;
+      if (n < N) {
+        const float inv = red[qi][0];
+        *reinterpret_cast<__nv_bfloat162*>(out + prow(n) * C + c) = __floats2bfloat162_rn(a0[qi] * inv, a1[qi] * inv);
+      }
+    }
+  }
+}
+
+// conv weight [Cout, Cin, k, k] (fp32 / bf16 / fp16 source already converted to fp32) -> bf16 [CoutPad, k*k*Cin] tap-major
+__global__ void s1_pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int taps) {
+  const size_t n = static_cast<size_t>(Cout) * Cin * taps;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i % taps);
+    const int ci = static_cast<int>((i / taps) % Cin);
+    const int co = static_cast<int>(i / (static_cast<size_t>(taps) * Cin));
+    out[(static_cast<size_t>(co) * taps + t) * Cin + ci] = __float2bfloat16_rn(w[i]);
+  }
+}
+
+}  // namespace hq

@@ -136,3 +136,36 @@ def build_reference_model_random(cfg):
                        ratio_bot2top=4, use_cls_cond=(cfg.cond == "cls"), use_txt_cond=(cfg.cond == "txt"),
                        model_type=getattr(cfg, "model_type", "parallel"), hparams=hp, hparams_dec=hp_dec)
     return model.eval()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# stage 1: the unmodified `SimRQGAN2Generator` for the decode_code oracle pin
+# ---------------------------------------------------------------------------------------------------------------------
+class _AttrDict(dict):
+    """Stands in for the OmegaConf node: `Encoder(**hparams)` needs a mapping, the generator reads attributes."""
+    __getattr__ = dict.__getitem__
+
+
+def build_reference_stage1(cfg, state_dict):
+    """Reference `SimRQGAN2Generator` (hqvae/models/stage1/generator.py:176-260) for an `oracle.s1_oracle.S1Config`, with the
+    decode-side parameters of `state_dict` loaded (the encoder keeps its own random init: decode_code never touches it)."""
+    import_reference()
+    for name, rel in (("hqvae.models.stage1", "hqvae/models/stage1"),
+                      ("hqvae.models.stage1.modules", "hqvae/models/stage1/modules")):
+        if name not in sys.modules:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [os.path.join(REFERENCE_ROOT, rel)]
+            sys.modules[name] = pkg
+    from hqvae.models.stage1.generator import SimRQGAN2Generator  # noqa: E402
+    hp = _AttrDict(double_z=False, z_channels=cfg.z_channels, resolution=cfg.resolution, in_channels=3, out_ch=cfg.out_ch,
+                   ch=cfg.ch, ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks,
+                   attn_resolutions=list(cfg.attn_resolutions), pdrop=0.0, use_init_downsample=True, use_mid_block=True,
+                   use_attn=True)
+    aux = types.SimpleNamespace(shared_codebook=False, decoding_type="concat", upsample="pixelshuffle", bottom_start=0,
+                                bottom_window=2)
+    model = SimRQGAN2Generator(n_embed=cfg.n_embed, embed_dim=cfg.embed_dim, ema_update=True, hparams=hp, hparams_aux=aux)
+    res = model.load_state_dict(state_dict, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.startswith(("encoder.", "quant_conv_b.", "quantize_t.cluster", "quantize_t.embedding_avg",
+                             "quantize_b.cluster", "quantize_b.embedding_avg")) for k in res.missing_keys), res.missing_keys
+    return model.eval()
