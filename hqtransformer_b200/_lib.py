@@ -6,7 +6,7 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libhqgraft.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 HQ_OK = 0
 HQ_COND_CLS, HQ_COND_TXT, HQ_COND_UNCOND = 0, 1, 2
@@ -36,6 +36,12 @@ class HQRunArgs(C.Structure):
                 ("cond", C.c_void_p), ("sos", C.c_void_p), ("given_top", C.c_void_p), ("given_bot", C.c_void_p),
                 ("codes_top", C.c_void_p), ("codes_bot", C.c_void_p), ("logits", C.c_void_p),
                 ("sampling", HQSamplingParams)]
+
+
+class HQS1Config(C.Structure):
+    _fields_ = [("embed_dim", C.c_int32), ("n_embed", C.c_int32), ("z_channels", C.c_int32), ("resolution", C.c_int32),
+                ("ch", C.c_int32), ("ch_mult", C.c_int32 * 8), ("n_levels", C.c_int32), ("num_res_blocks", C.c_int32),
+                ("attn_resolution", C.c_int32), ("out_ch", C.c_int32)]
 
 
 # every symbol include/hqgraft.h declares: name -> (restype, argtypes)
@@ -70,6 +76,14 @@ PROTOTYPES = {
     "hq_bench_gemm_shape": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                       C.POINTER(C.c_float), C.c_void_p]),
     "hq_bench_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
+    "hq_s1_create": (C.c_int, [C.POINTER(HQS1Config), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "hq_s1_destroy": (C.c_int, [C.c_void_p]),
+    "hq_s1_last_error": (C.c_char_p, [C.c_void_p]),
+    "hq_s1_device_bytes": (C.c_size_t, [C.c_void_p]),
+    "hq_s1_load_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, C.c_int]),
+    "hq_s1_params_complete": (C.c_int, [C.c_void_p]),
+    "hq_s1_decode_codes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "hq_s1_last_conv_flops": (C.c_double, [C.c_void_p]),
 }
 
 _lib = None
@@ -104,3 +118,9 @@ def check(rc: int, ctx=None, what: str = "") -> None:
     if rc != HQ_OK:
         msg = load().hq_last_error(ctx)
         raise HQError(f"{what or 'libhqgraft'} failed (status {rc}): {msg.decode() if msg else '?'}")
+
+
+def check_s1(rc: int, ctx, lib, what: str = "") -> None:
+    if rc != HQ_OK:
+        msg = lib.hq_s1_last_error(ctx)
+        raise HQError(f"{what or 'libhqgraft stage 1'} failed (status {rc}): {msg.decode() if msg else '?'}")

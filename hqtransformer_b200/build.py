@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhqgraft.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", "chain.cuh", os.path.join("..", "..", "include", "hqgraft.h")]
+HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", "chain.cuh", "stage1.cuh", "stage1_host.cuh", os.path.join("..", "..", "include", "hqgraft.h")]
 
 
 def _nvcc() -> str:

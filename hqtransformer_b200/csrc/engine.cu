@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <string>
@@ -2188,3 +2189,5 @@ extern "C" int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, 
   cudaFree(dbuf);
   return rc;
 }
+
+#include "stage1_host.cuh"

@@ -230,19 +230,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // out[c, y, x] = in[4c + 2 (y % 2) + (x % 2), y / 2, x / 2]), channels [E, 2E) = the bottom entry.  One CTA per bottom pixel.
 __global__ void __launch_bounds__(256)
 s1_quant_kernel(const int64_t* __restrict__ code_t, const int64_t* __restrict__ code_b, const float* __restrict__ E_t,
-                const float* __restrict__ E_b, bf16* __restrict__ out, int E, int hb /*bottom grid side*/, int n_embed, int* err) {
-  const int pix = blockIdx.x;                  // b * hb * hb + y * hb + x
-  const int b = pix / (hb * hb), q = pix % (hb * hb), y = q / hb, x = q % hb;
+                const float* __restrict__ E_b, bf16* __restrict__ out, int E, int hb /*bottom grid side*/, int n_embed) {
+  const int Wp = hb + 2;
+  const int pp = blockIdx.x;                   // padded pixel: b * Wp * Wp + yp * Wp + xp
+  const int b = pp / (Wp * Wp), q = pp % (Wp * Wp), y = q / Wp - 1, x = q % Wp - 1;
+  bf16* o = out + static_cast<size_t>(pp) * 2 * E;
   const int ht = hb / 2;
-  const int64_t ct = code_t[(static_cast<size_t>(b) * ht + y / 2) * ht + x / 2];
-  const int64_t cb = code_b[pix];
-  if (ct < 0 || ct >= n_embed || cb < 0 || cb >= n_embed) {
-    if (threadIdx.x == 0) atomicExch(err, 1);
+  int64_t ct = -1, cb = -1;
+  if (y >= 0 && y < hb && x >= 0 && x < hb) {
+    ct = code_t[(static_cast<size_t>(b) * ht + y / 2) * ht + x / 2];
+    cb = code_b[(static_cast<size_t>(b) * hb + y) * hb + x];
+  }
+  if (ct < 0 || ct >= n_embed || cb < 0 || cb >= n_embed) {      // border (or an out-of-range code: the host validates)
+    for (int c = threadIdx.x; c < 2 * E; c += blockDim.x) o[c] = __float2bfloat16_rn(0.f);
     return;
   }
   const float* et = E_t + static_cast<size_t>(ct) * 4 * E + 2 * (y & 1) + (x & 1);
   const float* eb = E_b + static_cast<size_t>(cb) * E;
-  bf16* o = out + (static_cast<size_t>(b) * (hb + 2) * (hb + 2) + static_cast<size_t>(y + 1) * (hb + 2) + (x + 1)) * 2 * E;
   for (int c = threadIdx.x; c < E; c += blockDim.x) {
     o[c] = __float2bfloat16_rn(et[4 * c]);
     o[E + c] = __float2bfloat16_rn(eb[c]);
@@ -284,12 +288,12 @@ s1_gn_stats_kernel(const float* __restrict__ x, double* __restrict__ part, int H
 
 __device__ __forceinline__ float swish_f(float v) { return v / (1.0f + expf(-v)); }
 
-// y = GroupNorm(x) (optionally * sigmoid) as bf16, interior pixels only (the border of `out` stays zero).  One CTA per
-// padded row (b, y); thread = 4 channels of a pixel.
+// y = GroupNorm(x) (optionally * sigmoid) as bf16; EVERY padded position is written, the border with zeros (the buffers are
+// reused at other resolutions: a 3x3 convolution must find zeros around its input).  One CTA per padded row (b, y).
 __global__ void __launch_bounds__(256)
 s1_gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ part, const float* __restrict__ gamma,
                    const float* __restrict__ beta, bf16* __restrict__ out, int Hp, int Wp, int C, int S, int swish) {
-  const int b = blockIdx.y, y = blockIdx.x + 1;
+  const int b = blockIdx.y, y = blockIdx.x;
   const int H = Hp - 2, W = Wp - 2, cg = C / 32;
   __shared__ float s_mean[32], s_rstd[32];
   if (threadIdx.x < 32) {
@@ -306,15 +310,18 @@ s1_gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ part,
   __syncthreads();
   const int c4 = C / 4;
   const size_t base = (static_cast<size_t>(b) * Hp + y) * Wp * C;
-  for (int i = threadIdx.x; i < W * c4; i += blockDim.x) {
-    const int xx = i / c4 + 1, c = (i % c4) * 4;
+  for (int i = threadIdx.x; i < Wp * c4; i += blockDim.x) {
+    const int xx = i / c4, c = (i % c4) * 4;
+    if (y < 1 || y > H || xx < 1 || xx > W) {
+      *reinterpret_cast<uint2*>(out + base + static_cast<size_t>(xx) * C + c) = make_uint2(0u, 0u);
+      continue;
+    }
     const float4 v = *reinterpret_cast<const float4*>(x + base + static_cast<size_t>(xx) * C + c);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
     const float4 be = *reinterpret_cast<const float4*>(beta + c);
-    const int g = c / cg;                       // cg % 4 == 0: the four channels share a group
-    const float m = s_mean[g], r = s_rstd[g];
-    float o0 = (v.x - m) * r * ga.x + be.x, o1 = (v.y - m) * r * ga.y + be.y;
-    float o2 = (v.z - m) * r * ga.z + be.z, o3 = (v.w - m) * r * ga.w + be.w;
+    const int g0 = c / cg, g1 = (c + 1) / cg, g2 = (c + 2) / cg, g3 = (c + 3) / cg;
+    float o0 = (v.x - s_mean[g0]) * s_rstd[g0] * ga.x + be.x, o1 = (v.y - s_mean[g1]) * s_rstd[g1] * ga.y + be.y;
+    float o2 = (v.z - s_mean[g2]) * s_rstd[g2] * ga.z + be.z, o3 = (v.w - s_mean[g3]) * s_rstd[g3] * ga.w + be.w;
     if (swish) { o0 = swish_f(o0); o1 = swish_f(o1); o2 = swish_f(o2); o3 = swish_f(o3); }
     uint2 u;
     __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
@@ -328,18 +335,21 @@ s1_gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ part,
 // of the level's upsample convolution.  up = 1: plain fp32 -> bf16 copy of the interior (input of a nin_shortcut 1x1 conv).
 __global__ void __launch_bounds__(256)
 s1_resample_kernel(const float* __restrict__ x, bf16* __restrict__ out, int H, int W, int C, int up) {
-  const int b = blockIdx.y, yo = blockIdx.x;           // output interior row 0 .. up*H-1
-  const int Wo = up * W, c4 = C / 4;
-  const float* src = x + ((static_cast<size_t>(b) * (H + 2) + yo / up + 1) * (W + 2)) * C;
-  bf16* dst = out + ((static_cast<size_t>(b) * (up * H + 2) + yo + 1) * (Wo + 2)) * C;
-  for (int i = threadIdx.x; i < Wo * c4; i += blockDim.x) {
-    const int xo = i / c4, c = (i % c4) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(src + static_cast<size_t>(xo / up + 1) * C + c);
-    uint2 u;
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-    u.x = *reinterpret_cast<uint32_t*>(&h0);
-    u.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(dst + static_cast<size_t>(xo + 1) * C + c) = u;
+  const int b = blockIdx.y, yp = blockIdx.x;           // output padded row 0 .. up*H+1
+  const int Ho = up * H, Wo = up * W, c4 = C / 4;
+  bf16* dst = out + ((static_cast<size_t>(b) * (Ho + 2) + yp) * (Wo + 2)) * C;
+  const bool row_in = yp >= 1 && yp <= Ho;
+  const float* src = x + ((static_cast<size_t>(b) * (H + 2) + (row_in ? (yp - 1) / up + 1 : 0)) * (W + 2)) * C;
+  for (int i = threadIdx.x; i < (Wo + 2) * c4; i += blockDim.x) {
+    const int xp = i / c4, c = (i % c4) * 4;
+    uint2 u = make_uint2(0u, 0u);
+    if (row_in && xp >= 1 && xp <= Wo) {
+      const float4 v = *reinterpret_cast<const float4*>(src + static_cast<size_t>((xp - 1) / up + 1) * C + c);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+    }
+    *reinterpret_cast<uint2*>(dst + static_cast<size_t>(xp) * C + c) = u;
   }
 }
 

@@ -287,10 +287,17 @@ class ImageGPT2:
     Stage 1 (HQ-VAE decoder) is outside this path; attach any module with the reference's
     `decode_code(code_t [B,8,8], code_b [B,16,16])` as `.stage1` to get pixels out of `sample()`."""
 
-    def __init__(self, config, **engine_opts) -> None:
+    def __init__(self, config, with_stage1: bool = False, stage1_max_batch: int = 16, **engine_opts) -> None:
         self.config = config
         self.stage1 = None
         self.stage2 = iHQGPT(**engine_kwargs(config), **engine_opts)
+        if with_stage1:
+            # the `decode_code` half of the HQ-VAE (hqvae/models/__init__.py:96-101 builds the whole generator)
+            from .stage1 import HQVAEDecoder
+            s1 = getattr(config, "stage1", None)
+            if s1 is None:
+                raise KeyError("with_stage1=True needs a `stage1` section in the config")
+            self.stage1 = HQVAEDecoder.from_stage1_config(s1, max_batch=stage1_max_batch, device=self.stage2.device)
         self.use_cls_cond = config.stage2.use_cls_cond
         self.use_txt_cond = config.stage2.use_txt_cond
         self.type = config.stage2.type
@@ -300,6 +307,8 @@ class ImageGPT2:
         """`measure_throughput.load_model` (measure_throughput/__main__.py:25-31): config only, random-init weights."""
         model = cls(load_config(path), **engine_opts)
         model.stage2.init_weights(seed=0)
+        if model.stage1 is not None:
+            model.stage1.init_weights(seed=1)
         return model
 
     @classmethod
@@ -311,9 +320,13 @@ class ImageGPT2:
         return model
 
     def load_state_dict(self, state_dict, strict: bool = True):
-        """Accepts the full Lightning state_dict: 'stage2.*' keys feed the engine, 'stage1.*' keys are skipped
-        (stage 1 is not on this path)."""
+        """Accepts the full Lightning state_dict: 'stage2.*' keys feed the sampler engine; 'stage1.*' keys feed the stage-1
+        decoder when one was built (`with_stage1=True`), else they are skipped."""
         s2 = {k[len("stage2."):]: v for k, v in state_dict.items() if k.startswith("stage2.")}
+        if self.stage1 is not None and hasattr(self.stage1, "load_state_dict"):
+            s1 = {k: v for k, v in state_dict.items() if k.startswith("stage1.")}
+            if s1 or strict:
+                self.stage1.load_state_dict(s1, strict=strict)
         other = [k for k in state_dict if not k.startswith(("stage1.", "stage2."))]
         if strict and other:
             raise KeyError(f"unexpected key(s) in state_dict: {other[:5]}")

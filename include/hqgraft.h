@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HQ_ABI_VERSION 4
+#define HQ_ABI_VERSION 5
 
 enum hq_status {
   HQ_OK = 0,
@@ -241,6 +241,46 @@ int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, unsigned lo
  * sweep before each launch.  Per-launch CUDA-event times; mean and min in microseconds. */
 int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int flush, int copies, float* usec_mean,
                         float* usec_min, void* stream);
+
+/* ---- stage-1 decode of the sampled code grids ----
+ * Stands behind `SimRQGAN2Generator.decode_code(code_t [B,h,w], code_b [B,2h,2w])` (hqvae/models/stage1/generator.py:323-367)
+ * as the scripts call it after sampling (sampling_hqmodel.py:197, measure_throughput/__main__.py:108-111: one image at a
+ * time there, batched here), for the shipped HQ-VAE configuration: `decoding_type: concat`, `upsample: pixelshuffle`,
+ * `use_init_downsample / use_mid_block / use_attn: True` (the `stage1` section of the stage-2 YAMLs). */
+typedef struct hq_s1_config {
+  int32_t embed_dim;        /* stage1.embed_dim: bottom codebook width; the top codebook is 4x as wide (PixelShuffle(2)) */
+  int32_t n_embed;          /* stage1.n_embed */
+  int32_t z_channels;       /* hparams.z_channels */
+  int32_t resolution;       /* hparams.resolution (pixels) */
+  int32_t ch;               /* hparams.ch */
+  int32_t ch_mult[8];       /* hparams.ch_mult[0 .. n_levels) */
+  int32_t n_levels;         /* len(ch_mult); the bottom grid is resolution / 2^n_levels wide */
+  int32_t num_res_blocks;   /* hparams.num_res_blocks */
+  int32_t attn_resolution;  /* hparams.attn_resolutions[0] */
+  int32_t out_ch;           /* hparams.out_ch (3) */
+} hq_s1_config;
+
+typedef struct hq_s1_ctx hq_s1_ctx;
+
+int hq_s1_create(const hq_s1_config* cfg, int device, int max_batch, hq_s1_ctx** out);
+int hq_s1_destroy(hq_s1_ctx* ctx);
+const char* hq_s1_last_error(const hq_s1_ctx* ctx);
+size_t hq_s1_device_bytes(const hq_s1_ctx* ctx);
+
+/* `name`: key of the reference generator's state_dict without the 'stage1.' prefix, e.g. "quantize_t.embedding",
+ * "post_quant_conv_b.weight", "decoder.up.2.block.1.conv1.weight", "decoder.mid.attn_1.q.bias" (generator.py:243-250,
+ * stage1/modules/layers.py:77-186, 300-383).  Only the keys decode_code reads exist; conv weights are repacked to bf16
+ * [Cout, kh kw Cin].  hq_s1_params_complete: HQ_OK once all of them were loaded. */
+int hq_s1_load_param(hq_s1_ctx* ctx, const char* name, const void* data, int dtype, const int64_t* shape, int ndim,
+                     int is_device);
+int hq_s1_params_complete(hq_s1_ctx* ctx);
+
+/* code_t int64 [B, h, w], code_b int64 [B, 2h, 2w] -> out fp32 [B, out_ch, resolution, resolution]; DEVICE pointers,
+ * asynchronous on `stream`; B <= max_batch.  Codes must lie in [0, n_embed) (the host layer checks). */
+int hq_s1_decode_codes(hq_s1_ctx* ctx, const int64_t* code_t, const int64_t* code_b, float* out, int B, void* stream);
+
+/* 2 * MACs of the convolutions of the last hq_s1_decode_codes call (interior pixels only): the roofline numerator. */
+double hq_s1_last_conv_flops(const hq_s1_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@ Run in the build container (where /root/reference exists):
 
     python -m oracle.make_golden            # writes tests/golden/ (small models + filters)
     python -m oracle.make_golden --full-size    # only the ImageNet-L12-size golden (BASELINE config 1 at real scale)
+    python -m oracle.make_golden --stage1       # only the stage-1 decode golden (SimRQGAN2Generator.decode_code)
     python -m oracle.make_golden --variants     # only the 8f-3 model variants (reduce / 2d / top2bot / bidirectional)
     python -m oracle.make_golden --all
 
@@ -182,6 +183,27 @@ def golden_variant(cfg, name, seed, init, labels=None, B=3):
     print(name, "min greedy margin over the run", margin)
 
 
+def golden_stage1(name, seed=1, B=2):
+    """pixels of the UNMODIFIED `SimRQGAN2Generator.decode_code` (generator.py:323-367) for a small HQ-VAE
+    (oracle.s1_oracle.TINY_S1: every decoder stage present - mid attention, an attention level, channel-changing blocks
+    with nin_shortcut, four upsample convs) on random code grids; weights are regenerated from (cfg, seed)."""
+    from oracle import s1_oracle as S1
+    cfg = S1.TINY_S1
+    P = S1.make_params(cfg, seed=seed)
+    model = R.build_reference_stage1(cfg, P)
+    g = torch.Generator().manual_seed(seed + 100)
+    h = cfg.latent_res // 2
+    ct = torch.randint(0, cfg.n_embed, (B, h, h), generator=g)
+    cb = torch.randint(0, cfg.n_embed, (B, 2 * h, 2 * h), generator=g)
+    with torch.no_grad():
+        px = model.decode_code(ct, cb)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name),
+                        meta=np.array(json.dumps(dict(config=cfg.to_dict(), seed=seed, torch=torch.__version__,
+                                                      reference="SimRQGAN2Generator.decode_code, CPU fp32"))),
+                        code_t=ct.numpy(), code_b=cb.numpy(), pixels=px.numpy().astype(np.float32))
+    print(name, "pixels", tuple(px.shape), "mean |x|", float(px.abs().mean()))
+
+
 def golden_filters(name):
     """Known answers of cutoff_topk_logits / cutoff_topp_probs (sampling.py:12-37) incl. ties."""
     _, S = R.import_reference()
@@ -212,6 +234,10 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if "--stage1" in sys.argv or "--all" in sys.argv:
+        golden_stage1("s1_tiny_decode.npz")
+        if "--all" not in sys.argv:
+            return 0
     if "--variants" in sys.argv or "--all" in sys.argv:
         # seeds searched (oracle) for a greedy margin >= 2e-4 over the whole run, as for the other goldens
         V = lambda **kw: O.HQConfig(**{**O.TINY.to_dict(), **kw})

@@ -14,7 +14,7 @@ def test_library_exports_every_symbol_the_header_declares():
     from hqtransformer_b200 import _lib
     lib = _lib.load()
     header = open(os.path.join(ROOT, "include", "hqgraft.h")).read()
-    declared = set(re.findall(r"^\s*(?:const\s+)?(?:int|int64_t|size_t|char\*|const char\*)\s+\*?(hq_[a-z_0-9]+)\s*\(", header, re.M))
+    declared = set(re.findall(r"^\s*(?:const\s+)?(?:int|int64_t|size_t|double|char\*|const char\*)\s+\*?(hq_[a-z_0-9]+)\s*\(", header, re.M))
     assert len(declared) >= 17, declared
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
     raw = ctypes.CDLL(_lib.LIB_PATH)

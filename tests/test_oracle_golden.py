@@ -172,3 +172,21 @@ def test_oracle_variants_stochastic_equal_live_reference(kw):
     torch.manual_seed(5)
     ot, ob = O.sample(P, cfg, cond, 3, max_seq_len=6, **skw)
     assert torch.equal(ct, ot) and torch.equal(cb, ob)
+
+
+def test_stage1_oracle_equals_reference_golden_and_live_reference():
+    """oracle/s1_oracle.py against the pixels the unmodified SimRQGAN2Generator.decode_code produced
+    (tests/golden/s1_tiny_decode.npz), and against the live module when the reference tree is present."""
+    from oracle import s1_oracle as S1
+    g, meta = load_golden("s1_tiny_decode.npz")
+    cfg = S1.S1Config.from_dict(meta["config"])
+    P = S1.make_params(cfg, seed=meta["seed"])
+    ct, cb = torch.from_numpy(g["code_t"]), torch.from_numpy(g["code_b"])
+    px = S1.decode_code(P, cfg, ct, cb)
+    assert tuple(px.shape) == (ct.shape[0], 3, cfg.resolution, cfg.resolution)
+    assert float((px - torch.from_numpy(g["pixels"])).abs().max()) < 1e-5
+    if R.reference_available():
+        model = R.build_reference_stage1(cfg, P)
+        with torch.no_grad():
+            want = model.decode_code(ct, cb)
+        assert float((px - want).abs().max()) < 1e-5
