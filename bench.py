@@ -247,6 +247,66 @@ def reference_gpu_rate(model_name: str, B: int, device, steps: int = 2):
         return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
+def stage1_decode_extra(device, peaks, B: int = 32, iters: int = 5):
+    """SURVEY.md 8f-1 beside the headline: stage-1 decode of code grids (the "decode" half of measure_throughput's total)
+    through hq_s1_decode_codes - the shipped HQ-VAE decoder, random-init weights, batch `B` per call - and the UNMODIFIED
+    reference `decode_code` (baseline/_ref copy, PyTorch eager / cuDNN) on the same GPU, one image at a time as
+    measure_throughput/__main__.py:108-111 calls it, and batched."""
+    import torch
+    import hqtransformer_b200 as H
+    out = {}
+    try:
+        dec = H.HQVAEDecoder(max_batch=B, device=device.index or 0)
+        dec.init_weights(seed=1)
+        ct = torch.randint(0, 8192, (B, 8, 8), device=device)
+        cb = torch.randint(0, 8192, (B, 16, 16), device=device)
+        for _ in range(2):
+            dec.decode_code(ct, cb)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            dec.decode_code(ct, cb)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1) / iters
+        tf = dec.last_conv_flops / (ms * 1e-3) * 1e-12
+        out = {"value": B / (ms * 1e-3), "unit": "images/s decoded (256x256)", "ms_per_image": ms / B, "batch": B,
+               "roofline": {"bound": "tensor", "kernel": "conv_tc2_kernel (all convolutions of a decode)", "achieved": tf,
+                            "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"],
+                            "note": "2 x MACs of the convolutions over interior pixels / WHOLE decode time (GroupNorm, attention, "
+                                    "resampling included in the denominator)"},
+               "what": "hq_s1_decode_codes: implicit-GEMM tcgen05 convolutions, bf16 inputs / fp32 accumulate and residual stream"}
+        dec.close()
+        del dec
+        torch.cuda.empty_cache()
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    try:
+        from oracle import ref_shim as R, s1_oracle as S1
+        if R.reference_available():
+            model = R.build_reference_stage1(S1.IMAGENET_S1, S1.make_params(S1.IMAGENET_S1, seed=2)).to(device)
+            ref = {}
+            with torch.no_grad():
+                for name, chunks, n in (("one_image_at_a_time", 8, 8), ("batched", 1, B)):
+                    a, b = ct[:n].chunk(chunks), cb[:n].chunk(chunks)
+                    run = lambda: [model.decode_code(x, y) for x, y in zip(a, b)]
+                    run()
+                    torch.cuda.synchronize(device)
+                    e0.record()
+                    for _ in range(2):
+                        run()
+                    e1.record()
+                    torch.cuda.synchronize(device)
+                    ref[name] = {"ms_per_image": e0.elapsed_time(e1) / 2 / n, "images_per_s": n / (e0.elapsed_time(e1) / 2 * 1e-3)}
+            out["reference_same_gpu"] = dict(ref, what="unmodified SimRQGAN2Generator.decode_code, PyTorch eager (cuDNN, fp32 / TF32)")
+            del model
+            torch.cuda.empty_cache()
+    except Exception as e:
+        out["reference_same_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
@@ -488,7 +548,8 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
                                                 "over all 64 positions"}
         if world == 1 and not args.no_ref_gpu:
             del local_ct, local_cb
-            line["extras"] = {"reference_gpu_fp16_autocast": reference_gpu_rate(args.model, args.ref_gpu_batch or B, dev)}
+            line["extras"] = {"reference_gpu_fp16_autocast": reference_gpu_rate(args.model, args.ref_gpu_batch or B, dev),
+                              "stage1_decode": stage1_decode_extra(dev, peaks)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

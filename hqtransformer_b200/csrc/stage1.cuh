@@ -254,35 +254,42 @@ s1_quant_kernel(const int64_t* __restrict__ code_t, const int64_t* __restrict__ 
 }
 
 // GroupNorm(32 groups, eps 1e-6; layers.py:17-21) statistics over the interior of a padded fp32 NHWC tensor: partial (sum,
-// sum of squares) in double per (image, group, slice of rows); grid (S slices, 32 groups, B).  Deterministic: the apply
-// kernel adds the S partials in a fixed order.
+// sum of squares) per (image, group, slice of rows); grid (S slices, B).  Every element is read once, as float4 along the
+// channels (thread = channel quad x pixel lane); threads keep fp32 partials of <= a few hundred terms, the cross-thread
+// reduction runs in double in a FIXED order (deterministic), and the apply kernel adds the S slices in a fixed order too.
 __global__ void __launch_bounds__(256)
 s1_gn_stats_kernel(const float* __restrict__ x, double* __restrict__ part, int Hp, int Wp, int C, int S) {
-  const int s = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
-  const int H = Hp - 2, W = Wp - 2, cg = C / 32;
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int H = Hp - 2, W = Wp - 2, c4 = C / 4, cg = C / 32;
+  const int P = 256 / c4 > 0 ? 256 / c4 : 1;           // pixel lanes (C <= 1024)
+  const int tid = threadIdx.x, q = tid % c4, pl = tid / c4;
   const int rows_per = (H + S - 1) / S;
   const int y0 = s * rows_per, y1 = min(H, y0 + rows_per);
-  double sum = 0.0, sq = 0.0;
-  const int n = (y1 - y0) * W * cg;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int c = i % cg, px = i / cg, yy = y0 + px / W, xx = px % W;
-    const float v = x[((static_cast<size_t>(b) * Hp + yy + 1) * Wp + xx + 1) * C + g * cg + c];
-    sum += v;
-    sq += static_cast<double>(v) * v;
+  const int npx = (y1 - y0) * W;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pl < P && tid < c4 * P) {
+    for (int i = pl; i < npx; i += P) {
+      const int yy = y0 + i / W, xx = i % W;
+      const float4 v = *reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * Hp + yy + 1) * Wp + xx + 1) * C + 4 * q);
+      sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+      sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+    }
   }
-  __shared__ double ssum[8], ssq[8];
-  for (int o = 16; o > 0; o >>= 1) {
-    sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  }
-  if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = sum; ssq[threadIdx.x >> 5] = sq; }
+  __shared__ double ssum[256 * 4], ssq[256 * 4];
+  ssum[tid * 4 + 0] = sum.x; ssum[tid * 4 + 1] = sum.y; ssum[tid * 4 + 2] = sum.z; ssum[tid * 4 + 3] = sum.w;
+  ssq[tid * 4 + 0] = sq.x; ssq[tid * 4 + 1] = sq.y; ssq[tid * 4 + 2] = sq.z; ssq[tid * 4 + 3] = sq.w;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double a = 0.0, q = 0.0;
-    for (int w = 0; w < 8; ++w) { a += ssum[w]; q += ssq[w]; }
-    double* o = part + ((static_cast<size_t>(b) * 32 + g) * S + s) * 2;
+  if (tid < 32) {
+    double a = 0.0, qq = 0.0;
+    for (int p2 = 0; p2 < P; ++p2)
+      for (int c = tid * cg; c < (tid + 1) * cg; ++c) {
+        const int e = (p2 * c4 + c / 4) * 4 + (c & 3);
+        a += ssum[e];
+        qq += ssq[e];
+      }
+    double* o = part + ((static_cast<size_t>(b) * 32 + tid) * S + s) * 2;
     o[0] = a;
-    o[1] = q;
+    o[1] = qq;
   }
 }
 

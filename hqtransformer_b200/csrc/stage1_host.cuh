@@ -125,8 +125,8 @@ static int s1_make_conv(hq_s1_ctx* ctx, S1Conv* c, const std::vector<std::string
 }
 static int s1_make_norm(hq_s1_ctx* ctx, S1Norm* n, const std::string& name, int C) {
   n->C = C;
-  if (C % 32 != 0) {
-    s1_err(ctx, "GroupNorm(32) over %d channels", C);
+  if (C % 32 != 0 || C > 1024) {
+    s1_err(ctx, "GroupNorm(32) over %d channels (multiple of 32, <= 1024)", C);
     return HQ_ERR_UNSUPPORTED;
   }
   int rc;
@@ -365,7 +365,7 @@ static void s1_conv(hq_s1_ctx* ctx, cudaStream_t st, const S1Conv& c, const bf16
 static void s1_gn(hq_s1_ctx* ctx, cudaStream_t st, const S1Norm& n, const float* x, bf16* out, int B, int res, int swish) {
   const int Hp = res + 2;
   const int S = res < 64 ? res : 64;
-  s1_gn_stats_kernel<<<dim3(S, 32, B), 256, 0, st>>>(x, ctx->gn_part, Hp, Hp, n.C, S);
+  s1_gn_stats_kernel<<<dim3(S, B), 256, 0, st>>>(x, ctx->gn_part, Hp, Hp, n.C, S);
   s1_gn_apply_kernel<<<dim3(Hp, B), 256, 0, st>>>(x, ctx->gn_part, n.g, n.b, out, Hp, Hp, n.C, S, swish);
   s1_check(ctx);
 }

@@ -8,8 +8,9 @@ class per iteration, top-k / top-p None, T = 1, fp16, 64 top positions -, :147-1
 with the first `warmup` discarded, "ms/sample (ar: ..., decode: ...)").  `load_model` builds the model from the config
 only, i.e. with random-init weights (:25-31).
 
-The "ar" figure is this repo's path (libhqgraft).  "decode" is stage 1 (`model.stage1.decode_code`, :106-113), which is
-outside the path: it is timed only when a stage-1 module has been attached to the model, and reported as 0.0 otherwise.
+The "ar" figure is the sampling loop, "decode" is stage 1 (`model.stage1.decode_code`, :106-113); both run in libhqgraft.
+The reference decodes one image at a time (`codes.chunk(batch_size)`, :108-111); here the batch is decoded in one call
+(`decode_chunks=1`; `decode_chunks=<batch_size>` reproduces the one-by-one protocol).  `stage1=0` skips the decoder.
 The README of the reference spells the level key `code-level` (configs/README.md:70) while the dataclass field is
 `code_levels` (:48); both are accepted.  code_levels=3 (the 3-level `HQTransformer`) is not on this path.
 """
@@ -40,6 +41,8 @@ class Experiment:                      # measure_throughput/__main__.py:34-48
     top_resolution: int = 8
     code_levels: int = 2
     n_samples: int = 1000              # extension: images per loop (the reference hard-codes 1000, :76)
+    stage1: int = 1                    # extension: 1 = build and time the stage-1 decoder too
+    decode_chunks: int = 1             # extension: chunks the batch is decoded in (batch_size = the reference's protocol)
 
 
 def parse_cli(argv) -> Experiment:
@@ -60,10 +63,11 @@ def parse_cli(argv) -> Experiment:
     return args
 
 
-def load_model(result_path: str, device="cuda", max_batch: int = 50) -> ImageGPT2:
+def load_model(result_path: str, device="cuda", max_batch: int = 50, with_stage1: bool = True) -> ImageGPT2:
     """:25-31 - config only, no checkpoint: random-init weights of the named architecture."""
     dev = torch.device(device)
-    return ImageGPT2.from_config(result_path, device=dev.index or 0, precision="bf16", max_batch=max_batch)
+    return ImageGPT2.from_config(result_path, device=dev.index or 0, precision="bf16", max_batch=max_batch,
+                                 with_stage1=with_stage1, stage1_max_batch=min(max_batch, 32))
 
 
 def main(args: Experiment):
@@ -72,7 +76,7 @@ def main(args: Experiment):
         raise NotImplementedError("code_levels=3 (the 3-level HQTransformer, hqvae/models/stage2/hqtransformer.py) is not on "
                                   "this path; only the 2-level iHQGPT sampler is accelerated")
     device = torch.device("cuda")
-    model_ar = load_model(args.model_path, device, args.batch_size).to(device).eval()
+    model_ar = load_model(args.model_path, device, args.batch_size, with_stage1=bool(args.stage1)).to(device).eval()
     title = f"bs{args.batch_size}, sampling loops {args.warmup + 1}-{args.n_loop}"
     print(title)
     print("python: %s, torch: %s, cudnn: %s, cuda: %s, gpu: %s" % (
@@ -107,7 +111,7 @@ def main(args: Experiment):
             codes_t, codes_b = codes_to_grids(codes_t, codes_b, H=args.top_resolution)
             if model_ar.stage1 is not None:
                 pixels = torch.cat([model_ar.stage1.decode_code(ct, cb)
-                                    for ct, cb in zip(codes_t.chunk(batch_size), codes_b.chunk(batch_size))], dim=0)
+                                    for ct, cb in zip(codes_t.chunk(args.decode_chunks), codes_b.chunk(args.decode_chunks))], dim=0)
                 _ = (0.5 * pixels + 0.5).clamp(0, 1)
             ends[i].record()
         torch.cuda.synchronize(device)
@@ -118,7 +122,7 @@ def main(args: Experiment):
         print(f"{loop_idx + 1}/{n_loop} | {elapsed_time:.1f} s/loop (ar: {elapsed_time_ar:.1f}, decode: {elapsed_time_decode:.1f})")
         n = n_iter_per_loop * batch_size
         speed, speed_ar, speed_decode = (elapsed_time / n * 1000, elapsed_time_ar / n * 1000, elapsed_time_decode / n * 1000)
-        print(f"{loop_idx + 1}/{n_loop} | {speed:.1f} ms/sample (ar: {speed_ar:.1f}, decode: {speed_decode:.1f})")
+        print(f"{loop_idx + 1}/{n_loop} | {speed:.2f} ms/sample (ar: {speed_ar:.2f}, decode: {speed_decode:.2f})")
         return speed, speed_ar, speed_decode
 
     speeds, speeds_ar, speeds_decode = [], [], []
