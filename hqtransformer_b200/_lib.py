@@ -6,7 +6,7 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libhqgraft.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 HQ_OK = 0
 HQ_COND_CLS, HQ_COND_TXT, HQ_COND_UNCOND = 0, 1, 2
@@ -21,21 +21,22 @@ class HQConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "embed_dim", "n_heads", "n_layers", "n_layers_depth", "vocab_top", "vocab_bot", "vocab_txt", "n_classes",
         "ctx_len_img", "ctx_len_txt", "cond_kind", "precision", "max_seq_len", "use_cuda_graph", "use_pdl", "use_chain", "model_type", "embedding_kind",
-        "position_kind")]
+        "position_kind", "code_levels", "vocab_mid")]
 
 
 class HQSamplingParams(C.Structure):
     _fields_ = [("top_k_top", C.c_int32), ("top_k_bot", C.c_int32),
                 ("top_p_top", C.c_float), ("top_p_bot", C.c_float),
                 ("temperature_top", C.c_float), ("temperature_bot", C.c_float),
-                ("seed", C.c_uint64), ("row_offset", C.c_uint64)]
+                ("seed", C.c_uint64), ("row_offset", C.c_uint64),
+                ("top_k_mid", C.c_int32), ("top_p_mid", C.c_float), ("temperature_mid", C.c_float), ("reserved", C.c_int32)]
 
 
 class HQRunArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("seq_len", C.c_int32), ("pos_begin", C.c_int32), ("pos_end", C.c_int32),
                 ("cond", C.c_void_p), ("sos", C.c_void_p), ("given_top", C.c_void_p), ("given_bot", C.c_void_p),
                 ("codes_top", C.c_void_p), ("codes_bot", C.c_void_p), ("logits", C.c_void_p),
-                ("sampling", HQSamplingParams)]
+                ("sampling", HQSamplingParams), ("codes_mid", C.c_void_p), ("given_mid", C.c_void_p)]
 
 
 class HQS1Config(C.Structure):

@@ -161,7 +161,12 @@ struct hq_ctx {
   float *E_bot_depth = nullptr;                       // 'top2bot' only (tok_emb_bot_depth is unused by 'parallel' sampling)
   float *P_top_h = nullptr, *P_top_w = nullptr;       // position_embedding == '2d'
   int Hpos = 0;                                       // rows of pos_emb_top_h / _w = sqrt(ctx_len_img)
-  int depth_rows = 4;                                 // rows per image of the widest depth pass (5: 'bidirectional')
+  int depth_rows = 4;                                 // rows per image of the widest depth pass (5: 'bidirectional', 16: 3 levels)
+  // 3-level HQTransformer (code_levels == 3): E_top / E_bot / head_top / head_bot / lnt / lnb are levels 0 and 2
+  int levels = 2, n_stack = 5, Vm = 0;
+  float *E_mid = nullptr, *E_mid_depth = nullptr, *P_depth2 = nullptr, *lnm_g = nullptr, *lnm_b = nullptr;
+  Weight head_mid;
+  int64_t* codes_mid = nullptr;
   float *lnf_g = nullptr, *lnf_b = nullptr, *lnt_g = nullptr, *lnt_b = nullptr, *lnb_g = nullptr, *lnb_b = nullptr;
 
   // activations / state
@@ -459,7 +464,7 @@ static int reserve_impl(hq_ctx* ctx, int max_batch) {
     ctx->h = ABuf(); ctx->att = ABuf(); ctx->mlp = ABuf();
     ctx->q = nullptr; ctx->x = nullptr; ctx->yd = nullptr; ctx->logits = nullptr; ctx->splitk_ws = nullptr;
     ctx->kc = ctx->vc = ctx->kd = ctx->vd = nullptr;
-    ctx->cond = ctx->codes_top = ctx->codes_bot = nullptr;
+    ctx->cond = ctx->codes_top = ctx->codes_bot = ctx->codes_mid = nullptr;
     ctx->sos_override = nullptr;
     ctx->d_sp = nullptr;
     set_err(ctx, "hq_reserve_batch(%d) failed, the ctx holds no batch state until a reserve succeeds: %s", max_batch,
@@ -490,7 +495,7 @@ static int reserve_alloc(hq_ctx* ctx, int max_batch) {
   if ((rc = dev_alloc(ctx, &ctx->q, static_cast<size_t>(Mmax) * D * ctx->wsize))) return rc;
   if ((rc = alloc_f32(ctx, &ctx->x, static_cast<size_t>(Mx) * D))) return rc;
   if ((rc = alloc_f32(ctx, &ctx->yd, static_cast<size_t>(ctx->depth_rows) * B * D))) return rc;
-  if ((rc = alloc_f32(ctx, &ctx->logits, static_cast<size_t>(4) * B * ctx->Vmax))) return rc;
+  if ((rc = alloc_f32(ctx, &ctx->logits, static_cast<size_t>(ctx->depth_rows < 4 ? 4 : ctx->depth_rows) * B * ctx->Vmax))) return rc;
   ctx->ws_rows = Mmax;
   if (ctx->bf16 && (rc = alloc_f32(ctx, &ctx->splitk_ws, static_cast<size_t>(LN_MAXFOLD) * Mmax * D))) return rc;
   const size_t kvn = static_cast<size_t>(ctx->L) * B * ctx->Tc * D * ctx->wsize;
@@ -506,12 +511,15 @@ static int reserve_alloc(hq_ctx* ctx, int max_batch) {
       ctx->kv_maps = true;
     }
   }
-  const size_t kdn = static_cast<size_t>(ctx->Ld) * B * 5 * D * ctx->wsize;
+  const size_t kdn = static_cast<size_t>(ctx->Ld) * B * ctx->n_stack * D * ctx->wsize;
   if ((rc = dev_alloc(ctx, &ctx->kd, kdn))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->vd, kdn))) return rc;
   if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->cond), static_cast<size_t>(B) * ctx->T0 * 8))) return rc;
   if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->codes_top), static_cast<size_t>(B) * ctx->Smax * 8))) return rc;
-  if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->codes_bot), static_cast<size_t>(B) * ctx->Smax * 32))) return rc;
+  if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->codes_bot),
+                      static_cast<size_t>(B) * ctx->Smax * 8 * (ctx->levels == 3 ? 16 : 4)))) return rc;
+  if (ctx->levels == 3 &&
+      (rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->codes_mid), static_cast<size_t>(B) * ctx->Smax * 32))) return rc;
   if ((rc = alloc_f32(ctx, &ctx->sos_override, static_cast<size_t>(Mx) * D))) return rc;
   if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->d_sp), sizeof(hq_sampling_params)))) return rc;
   if (ctx->bf16) {
@@ -530,6 +538,7 @@ static int reserve_alloc(hq_ctx* ctx, int max_batch) {
     for (auto& b : ctx->depths) { add_w(b.qkv); add_w(b.proj); add_w(b.fc1); add_w(b.fc2); }
     add_w(ctx->head_top);
     add_w(ctx->head_bot);
+    if (ctx->levels == 3) add_w(ctx->head_mid);
     if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->d_maps), table.size() * sizeof(CUtensorMap)))) return rc;
     HQ_CUDA(ctx, cudaMemcpy(ctx->d_maps, table.data(), table.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
   }
@@ -553,6 +562,22 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
   ctx->Vt = cfg->vocab_top;
   ctx->Vb = cfg->vocab_bot;
   ctx->Vmax = ctx->Vt > ctx->Vb ? ctx->Vt : ctx->Vb;
+  ctx->levels = cfg->code_levels == 3 ? 3 : 2;
+  if (cfg->code_levels != 0 && cfg->code_levels != 2 && cfg->code_levels != 3) {
+    set_err(ctx, "code_levels must be 2 or 3 (got %d)", cfg->code_levels);
+    return HQ_ERR_INVALID;
+  }
+  if (ctx->levels == 3) {
+    ctx->Vm = cfg->vocab_mid;
+    ctx->n_stack = 21;
+    if (ctx->Vm > ctx->Vmax) ctx->Vmax = ctx->Vm;
+    if (ctx->Vm < 64 || ctx->Vm % 64 != 0 || cfg->cond_kind == HQ_COND_TXT || cfg->model_type != HQ_MODEL_PARALLEL ||
+        cfg->embedding_kind != HQ_EMB_TRANSFORMER1 || cfg->position_kind != HQ_POS_1D) {
+      set_err(ctx, "code_levels == 3: the 'parallel-add' HQTransformer with class / unconditional sos, 'transformer1' embedding and "
+                   "1-D positions is implemented (vocab_mid a multiple of 64)");
+      return HQ_ERR_UNSUPPORTED;
+    }
+  }
   ctx->Smax = cfg->max_seq_len;
   const bool txt = cfg->cond_kind == HQ_COND_TXT;
   ctx->T0 = txt ? cfg->ctx_len_txt : 1;
@@ -583,7 +608,7 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
     set_err(ctx, "embedding_type 'reduce' needs embed_dim %% 16 == 0 (four D/4-wide bottom embeddings)");
     return HQ_ERR_UNSUPPORTED;
   }
-  ctx->depth_rows = cfg->model_type == HQ_MODEL_BIDIRECTIONAL ? 5 : 4;
+  ctx->depth_rows = ctx->levels == 3 ? 16 : (cfg->model_type == HQ_MODEL_BIDIRECTIONAL ? 5 : 4);
   if (cfg->position_kind == HQ_POS_2D) {
     int H = 1;
     while ((H + 1) * (H + 1) <= cfg->ctx_len_img) ++H;        // int(math.sqrt(ctx_len_img)), hierarchical_ar.py:122
@@ -630,31 +655,60 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
     if ((rc = build_block(ctx, &ctx->depths[i], "depths." + std::to_string(i)))) return rc;
   if ((rc = alloc_weight(ctx, &ctx->head_top, ctx->Vt, D))) return rc;
   if ((rc = alloc_weight(ctx, &ctx->head_bot, ctx->Vb, D))) return rc;
-  reg(ctx, "head_top.weight", ctx->head_top.ptr, 1, {ctx->Vt, D});
-  reg(ctx, "head_bot.weight", ctx->head_bot.ptr, 1, {ctx->Vb, D});
   struct F32P { const char* name; float** p; std::vector<int64_t> shape; };
-  std::vector<F32P> f32s = {
-      {"sos_depth", &ctx->sos_depth, {1, 1, D}},
-      {"tok_emb_top.weight", &ctx->E_top, {ctx->Vt, D}},
-      {"tok_emb_top_depth.weight", &ctx->E_top_depth, {ctx->Vt, D}},
-      {"pos_emb_depth.weight", &ctx->P_depth, {5, D}},
-      {"ln_f.weight", &ctx->lnf_g, {D}}, {"ln_f.bias", &ctx->lnf_b, {D}},
-      {"ln_top.weight", &ctx->lnt_g, {D}}, {"ln_top.bias", &ctx->lnt_b, {D}},
-      {"ln_bot.weight", &ctx->lnb_g, {D}}, {"ln_bot.bias", &ctx->lnb_b, {D}},
-  };
-  if (cfg->embedding_kind == HQ_EMB_REDUCE) {               // hierarchical_ar.py:85-88
-    f32s.push_back({"tok_emb_bot.weight", &ctx->E_bot, {ctx->Vb, D / 4}});
-  } else {                                                   // :97-103
-    f32s.push_back({"tok_emb_bot.weight", &ctx->E_bot, {ctx->Vb, D}});
-    f32s.push_back({"pos_emb_emb.weight", &ctx->P_emb, {5, D}});
-  }
-  if (cfg->position_kind == HQ_POS_2D) {                     // :121-125
-    f32s.push_back({"pos_emb_top_h.weight", &ctx->P_top_h, {ctx->Hpos, D}});
-    f32s.push_back({"pos_emb_top_w.weight", &ctx->P_top_w, {ctx->Hpos, D}});
+  std::vector<F32P> f32s;
+  if (ctx->levels == 3) {
+    // ---- HQTransformer state_dict (hqtransformer.py:24-166), decoding_type 'parallel-add' ----
+    if ((rc = alloc_weight(ctx, &ctx->head_mid, ctx->Vm, D))) return rc;
+    reg(ctx, "head_levels.0.weight", ctx->head_top.ptr, 1, {ctx->Vt, D});
+    reg(ctx, "head_levels.1.weight", ctx->head_mid.ptr, 1, {ctx->Vm, D});
+    reg(ctx, "head_levels.2.weight", ctx->head_bot.ptr, 1, {ctx->Vb, D});
+    f32s = {
+        {"sos_depth", &ctx->sos_depth, {1, 1, D}},
+        {"tok_emb_levels.0.weight", &ctx->E_top, {ctx->Vt, D}},
+        {"tok_emb_levels.1.weight", &ctx->E_mid, {ctx->Vm, D}},
+        {"tok_emb_levels.2.weight", &ctx->E_bot, {ctx->Vb, D}},
+        {"pos_emb_emb.weight", &ctx->P_emb, {21, D}},
+        {"pos_emb_top.weight", &ctx->P_top, {cfg->ctx_len_img, D}},
+        {"tok_emb_depth_levels.0.weight", &ctx->E_top_depth, {ctx->Vt, D}},
+        {"tok_emb_depth_levels.1.weight", &ctx->E_mid_depth, {ctx->Vm, D}},
+        {"pos_emb_depths.0.weight", &ctx->P_depth, {4, D}},
+        {"pos_emb_depths.1.weight", &ctx->P_depth2, {16, D}},
+        {"ln_f.weight", &ctx->lnf_g, {D}}, {"ln_f.bias", &ctx->lnf_b, {D}},
+        {"ln_levels.0.weight", &ctx->lnt_g, {D}}, {"ln_levels.0.bias", &ctx->lnt_b, {D}},
+        {"ln_levels.1.weight", &ctx->lnm_g, {D}}, {"ln_levels.1.bias", &ctx->lnm_b, {D}},
+        {"ln_levels.2.weight", &ctx->lnb_g, {D}}, {"ln_levels.2.bias", &ctx->lnb_b, {D}},
+    };
+    // the bottom level's depth embedding exists in the state_dict and is never read when sampling (:521-524)
+    reg(ctx, "tok_emb_depth_levels.2.weight", nullptr, 0, {ctx->Vb, D}, true);
   } else {
-    f32s.push_back({"pos_emb_top.weight", &ctx->P_top, {cfg->ctx_len_img, D}});
+    reg(ctx, "head_top.weight", ctx->head_top.ptr, 1, {ctx->Vt, D});
+    reg(ctx, "head_bot.weight", ctx->head_bot.ptr, 1, {ctx->Vb, D});
+    f32s = {
+        {"sos_depth", &ctx->sos_depth, {1, 1, D}},
+        {"tok_emb_top.weight", &ctx->E_top, {ctx->Vt, D}},
+        {"tok_emb_top_depth.weight", &ctx->E_top_depth, {ctx->Vt, D}},
+        {"pos_emb_depth.weight", &ctx->P_depth, {5, D}},
+        {"ln_f.weight", &ctx->lnf_g, {D}}, {"ln_f.bias", &ctx->lnf_b, {D}},
+        {"ln_top.weight", &ctx->lnt_g, {D}}, {"ln_top.bias", &ctx->lnt_b, {D}},
+        {"ln_bot.weight", &ctx->lnb_g, {D}}, {"ln_bot.bias", &ctx->lnb_b, {D}},
+    };
+    if (cfg->embedding_kind == HQ_EMB_REDUCE) {               // hierarchical_ar.py:85-88
+      f32s.push_back({"tok_emb_bot.weight", &ctx->E_bot, {ctx->Vb, D / 4}});
+    } else {                                                   // :97-103
+      f32s.push_back({"tok_emb_bot.weight", &ctx->E_bot, {ctx->Vb, D}});
+      f32s.push_back({"pos_emb_emb.weight", &ctx->P_emb, {5, D}});
+    }
+    if (cfg->position_kind == HQ_POS_2D) {                     // :121-125
+      f32s.push_back({"pos_emb_top_h.weight", &ctx->P_top_h, {ctx->Hpos, D}});
+      f32s.push_back({"pos_emb_top_w.weight", &ctx->P_top_w, {ctx->Hpos, D}});
+    } else {
+      f32s.push_back({"pos_emb_top.weight", &ctx->P_top, {cfg->ctx_len_img, D}});
+    }
+    if (cfg->model_type == HQ_MODEL_TOP2BOT) f32s.push_back({"tok_emb_bot_depth.weight", &ctx->E_bot_depth, {ctx->Vb, D}});
+    // present in the reference state_dict, never read when sampling model_type='parallel' 
+    if (cfg->model_type != HQ_MODEL_TOP2BOT) reg(ctx, "tok_emb_bot_depth.weight", nullptr, 0, {ctx->Vb, D}, true);
   }
-  if (cfg->model_type == HQ_MODEL_TOP2BOT) f32s.push_back({"tok_emb_bot_depth.weight", &ctx->E_bot_depth, {ctx->Vb, D}});
   if (cfg->cond_kind == HQ_COND_CLS) f32s.push_back({"sos.weight", &ctx->sos_table, {cfg->n_classes, D}});
   if (cfg->cond_kind == HQ_COND_UNCOND) f32s.push_back({"sos", &ctx->sos_table, {1, 1, D}});
   if (txt) {
@@ -667,8 +721,6 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
     if ((rc = alloc_f32(ctx, f.p, n))) return rc;
     reg(ctx, f.name, *f.p, 0, f.shape);
   }
-  // present in the reference state_dict, never read when sampling model_type='parallel' 
-  if (cfg->model_type != HQ_MODEL_TOP2BOT) reg(ctx, "tok_emb_bot_depth.weight", nullptr, 0, {ctx->Vb, D}, true);
   if (txt) {
     reg(ctx, "head_txt.weight", nullptr, 0, {cfg->vocab_txt, D}, true);
     reg(ctx, "ln_txt.weight", nullptr, 0, {D}, true);
@@ -863,7 +915,7 @@ static void launch_k(hq_ctx* ctx, cudaStream_t st, const char* tag, void (*kerne
 // ------------------------------------------------------------------------------------------------
 static bool chain_enabled(const hq_ctx* ctx, int B) {
   const int min_b = ctx->dbg.chain_min_batch > 0 ? ctx->dbg.chain_min_batch : 129;   // every GEMM on CTA-pair tiles
-  return ctx->chain_ok && ctx->cfg.model_type == HQ_MODEL_PARALLEL && ctx->d_maps != nullptr && B >= min_b && ctx->D <= LN_MAXV * LN_THREADS * 4 &&
+  return ctx->chain_ok && ctx->levels == 2 && ctx->cfg.model_type == HQ_MODEL_PARALLEL && ctx->d_maps != nullptr && B >= min_b && ctx->D <= LN_MAXV * LN_THREADS * 4 &&
          ctx->chain_mode != hq_ctx::CHAIN_OFF;
 }
 
@@ -1338,7 +1390,7 @@ static void run_block(hq_ctx* ctx, cudaStream_t st, const BlockW& w, float* x, i
 }
 
 struct RunFlags {
-  int forced_top, forced_bot, sos_override;
+  int forced_top, forced_bot, sos_override, forced_mid;
   float* logits_out;
 };
 
@@ -1408,7 +1460,7 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
   SampleArgs sa;
   memset(&sa, 0, sizeof(sa));
   sa.logits = ctx->logits; sa.ldl = ctx->Vmax; sa.V = ctx->Vt; sa.R = B; sa.rows_per_b = 1; sa.slot0 = 0;
-  sa.sp = ctx->d_sp; sa.pos = pos; sa.S = S; sa.codes_top = ctx->codes_top; sa.codes_bot = ctx->codes_bot;
+  sa.sp = ctx->d_sp; sa.pos = pos; sa.S = S; sa.dst_codes = ctx->codes_top; sa.dst_w = 1; sa.n_slots = ctx->n_stack;
   sa.forced = f.forced_top; sa.logits_out = f.logits_out; sa.Vmax = ctx->Vmax;
   sa.temp_sel = 0; sa.filt_sel = 0; sa.bot_slot = -1;
   auto head = [&](const Weight& w, int rows, int V) {
@@ -1433,6 +1485,7 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
       layernorm_act<AT>(ctx, st, ctx->yd, c == 0 ? ctx->lnt_g : ctx->lnb_g, c == 0 ? ctx->lnt_b : ctx->lnb_b, h, B, &fold_y);
       head(c == 0 ? ctx->head_top : ctx->head_bot, B, c == 0 ? ctx->Vt : ctx->Vb);
       sa.V = c == 0 ? ctx->Vt : ctx->Vb; sa.slot0 = c; sa.bot_slot = c - 1;
+      sa.dst_codes = c == 0 ? ctx->codes_top : ctx->codes_bot; sa.dst_w = c == 0 ? 1 : 4;
       sa.temp_sel = sa.filt_sel = c == 0 ? 0 : 1;
       sa.forced = c == 0 ? f.forced_top : f.forced_bot;
       if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
@@ -1454,6 +1507,7 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
     fold_y = Fold();
     head(ctx->head_bot, 4 * B, ctx->Vb);
     sa.V = ctx->Vb; sa.R = 4 * B; sa.rows_per_b = 4; sa.slot0 = 1; sa.forced = f.forced_bot;
+    sa.dst_codes = ctx->codes_bot; sa.dst_w = 4;
     if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
     return;
   }
@@ -1490,12 +1544,90 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
     gemm_any<EPI_F32>(ctx, st, ctx->h, ctx->head_bot, 0, 4 * B, ctx->Vb, D, e);
   }
   sa.V = ctx->Vb; sa.R = 4 * B; sa.rows_per_b = 4; sa.slot0 = 1; sa.forced = f.forced_bot;
-  sa.temp_sel = 1; sa.filt_sel = 1;
+  sa.temp_sel = 1; sa.filt_sel = 1; sa.dst_codes = ctx->codes_bot; sa.dst_w = 4;
   if (chain) chain_end(ctx, st);
   if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
 }
 
+// One top position of the 3-level HQTransformer, decoding_type 'parallel-add' (hqtransformer.py:409-635):
+// spatial step over the 21-token stack embedding, then three depth passes - 1 top, 4 middle, 16 bottom tokens - over a
+// depth cache of 21 slots (pass 1 sees slots 0..4, pass 2 sees 0..20: the 'parallel' mask of layers.py:154-178), one head
+// and one set of (temperature, top-k, top-p) per level, 21 draws (Philox slots 0..20).
+template <typename AT>
+static void run_position3(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, const RunFlags& f) {
+  const int D = ctx->D, Tc = ctx->Tc;
+  AT* kc = static_cast<AT*>(ctx->kc);
+  AT* vc = static_cast<AT*>(ctx->vc);
+  AT* kd = static_cast<AT*>(ctx->kd);
+  AT* vd = static_cast<AT*>(ctx->vd);
+  AT* h = static_cast<AT*>(ctx->h.ptr);
+  const size_t lstride = static_cast<size_t>(ctx->max_batch) * Tc * D;
+  const size_t dstride = static_cast<size_t>(ctx->max_batch) * 21 * D;
+  const int eb = (D / 4 + 31) / 32 * 32 > 1024 ? 1024 : (D / 4 + 31) / 32 * 32;
+  Fold fold_x, fold_y;
+  ctx->full_dependency_next = true;             // one full dependency per position (see run_position)
+  Embed3Args ea;
+  ea.x = ctx->x; ea.sos_table = ctx->sos_table; ea.sos_override = f.sos_override ? ctx->sos_override : nullptr;
+  ea.cond = ctx->cond; ea.E0 = ctx->E_top; ea.E1 = ctx->E_mid; ea.E2 = ctx->E_bot; ea.P_top = ctx->P_top; ea.P_emb = ctx->P_emb;
+  ea.codes_top = ctx->codes_top; ea.codes_mid = ctx->codes_mid; ea.codes_bot = ctx->codes_bot;
+  ea.D = D; ea.S = S; ea.pos = pos; ea.cond_kind = ctx->cfg.cond_kind;
+  launch_k(ctx, st, "embed", embed3_kernel, dim3(B), dim3(eb), 0, ea);
+  const int tok = pos;                          // cache slot (no text prefix)
+  for (int l = 0; l < ctx->L; ++l)
+    run_block<AT>(ctx, st, ctx->blocks[l], ctx->x, B, 0, kc + l * lstride, vc + l * lstride, 1, Tc, tok, tok + 1, 0, &fold_x);
+  launch_k(ctx, st, "layernorm_f", fold_x.n > 3 ? layernorm_kernel<float, LN_MAXFOLD> : layernorm_kernel<float, 3>, dim3(B),
+           dim3(LN_THREADS), 0, ctx->x, ctx->lnf_g, ctx->lnf_b, ctx->sos_depth, ctx->yd, B, D, 1, 0, fold_x.partial, fold_x.n,
+           fold_x.stride, fold_x.bias, 1, 1);
+  fold_x = Fold();
+
+  SampleArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.logits = ctx->logits; sa.ldl = ctx->Vmax; sa.sp = ctx->d_sp; sa.pos = pos; sa.S = S; sa.n_slots = 21;
+  sa.logits_out = f.logits_out; sa.Vmax = ctx->Vmax; sa.bot_slot = -1;
+  auto head = [&](const Weight& w, int rows, int V) {
+    EpiParams<AT> e;
+    memset(&e, 0, sizeof(e));
+    e.outf = ctx->logits; e.ldo = ctx->Vmax;
+    gemm_any<EPI_F32>(ctx, st, ctx->h, w, 0, rows, V, D, e);
+  };
+  // ---- pass 0: top code (k, v only: softmax over one key is the identity) ----
+  for (int l = 0; l < ctx->Ld; ++l)
+    run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, B, 1, kd + l * dstride, vd + l * dstride, 1, 21, 0, 1, 0, &fold_y);
+  layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnt_g, ctx->lnt_b, h, B, &fold_y);
+  head(ctx->head_top, B, ctx->Vt);
+  sa.V = ctx->Vt; sa.R = B; sa.rows_per_b = 1; sa.slot0 = 0; sa.temp_sel = sa.filt_sel = 0;
+  sa.dst_codes = ctx->codes_top; sa.dst_w = 1; sa.forced = f.forced_top;
+  if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+  // ---- pass 1: four middle codes; y_j = E0_depth[c_top] + P1[j]; queries see slots 0..4 ----
+  launch_k(ctx, st, "embed_depth", embed_depth_kernel, dim3(B), dim3(eb), 0, ctx->yd, ctx->E_top_depth, ctx->P_depth,
+           ctx->codes_top, S, pos, D);
+  for (int l = 0; l < ctx->Ld; ++l)
+    run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, 4 * B, 2, kd + l * dstride, vd + l * dstride, 4, 21, 1, 5, 0, &fold_y);
+  layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnm_g, ctx->lnm_b, h, 4 * B, &fold_y);
+  head(ctx->head_mid, 4 * B, ctx->Vm);
+  sa.V = ctx->Vm; sa.R = 4 * B; sa.rows_per_b = 4; sa.slot0 = 1; sa.temp_sel = sa.filt_sel = 2;
+  sa.dst_codes = ctx->codes_mid; sa.dst_w = 4; sa.forced = f.forced_mid;
+  if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+  // ---- pass 2: sixteen bottom codes (raster of the 4x4 cell); queries see slots 0..20 ----
+  launch_k(ctx, st, "embed_depth2", embed_depth2_kernel, dim3(B), dim3(eb), 0, ctx->yd, ctx->E_mid_depth, ctx->E_top_depth,
+           ctx->P_depth2, ctx->codes_top, ctx->codes_mid, S, pos, D);
+  for (int l = 0; l < ctx->Ld; ++l)
+    run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, 16 * B, 2, kd + l * dstride, vd + l * dstride, 16, 21, 5, 21, 0, &fold_y);
+  layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnb_g, ctx->lnb_b, h, 16 * B, &fold_y);
+  head(ctx->head_bot, 16 * B, ctx->Vb);
+  sa.V = ctx->Vb; sa.R = 16 * B; sa.rows_per_b = 16; sa.slot0 = 5; sa.temp_sel = sa.filt_sel = 1;
+  sa.dst_codes = ctx->codes_bot; sa.dst_w = 16; sa.forced = f.forced_bot;
+  if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+}
+
 static void run_range(hq_ctx* ctx, cudaStream_t st, int B, int S, int p0, int p1, const RunFlags& f) {
+  if (ctx->levels == 3) {
+    for (int pos = p0; pos < p1; ++pos) {
+      if (ctx->bf16) run_position3<bf16>(ctx, st, B, S, pos, f);
+      else run_position3<float>(ctx, st, B, S, pos, f);
+    }
+    return;
+  }
   for (int pos = p0; pos < p1; ++pos) {
     if (ctx->bf16) run_position<bf16>(ctx, st, B, S, pos, f);
     else run_position<float>(ctx, st, B, S, pos, f);
@@ -1514,8 +1646,8 @@ static int validate_run(hq_ctx* ctx, const hq_run_args* a) {
     set_err(ctx, "bad position range [%d, %d) for seq_len %d (max_seq_len %d)", a->pos_begin, a->pos_end, a->seq_len, ctx->Smax);
     return HQ_ERR_INVALID;
   }
-  if (!a->codes_top || !a->codes_bot) {
-    set_err(ctx, "codes_top / codes_bot must not be null");
+  if (!a->codes_top || !a->codes_bot || (ctx->levels == 3 && !a->codes_mid)) {
+    set_err(ctx, "codes_top / codes_bot%s must not be null", ctx->levels == 3 ? " / codes_mid" : "");
     return HQ_ERR_INVALID;
   }
   if (a->pos_begin == 0 && !a->sos && !a->cond && ctx->cfg.cond_kind != HQ_COND_UNCOND) {
@@ -1535,7 +1667,7 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
   if (rc) return rc;
   HQ_CUDA(ctx, cudaSetDevice(ctx->device));
   const int B = a->batch, S = a->seq_len, D = ctx->D, T0 = ctx->T0;
-  const size_t nt = static_cast<size_t>(B) * S * 8, nb = nt * 4;
+  const size_t nt = static_cast<size_t>(B) * S * 8, nb = nt * (ctx->levels == 3 ? 16 : 4), nm = nt * 4;
 
   // ---- stage inputs into ctx-owned buffers (what the captured graph reads) ----
   // pageable source: the runtime stages it before returning, so back-to-back calls cannot race on it
@@ -1548,17 +1680,20 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
   } else {
     HQ_CUDA(ctx, cudaMemcpyAsync(ctx->codes_top, a->codes_top, nt, in_kind, st));
     HQ_CUDA(ctx, cudaMemcpyAsync(ctx->codes_bot, a->codes_bot, nb, in_kind, st));
+    if (ctx->levels == 3) HQ_CUDA(ctx, cudaMemcpyAsync(ctx->codes_mid, a->codes_mid, nm, in_kind, st));
   }
   if (a->given_top) HQ_CUDA(ctx, cudaMemcpyAsync(ctx->codes_top, a->given_top, nt, in_kind, st));
   if (a->given_bot) HQ_CUDA(ctx, cudaMemcpyAsync(ctx->codes_bot, a->given_bot, nb, in_kind, st));
+  if (ctx->levels == 3 && a->given_mid) HQ_CUDA(ctx, cudaMemcpyAsync(ctx->codes_mid, a->given_mid, nm, in_kind, st));
 
   RunFlags f;
   f.forced_top = a->given_top != nullptr;
   f.forced_bot = a->given_bot != nullptr;
+  f.forced_mid = ctx->levels == 3 && a->given_mid != nullptr;
   f.sos_override = a->sos != nullptr;
   f.logits_out = nullptr;
   float* dev_logits = nullptr;
-  const size_t nlog = static_cast<size_t>(B) * S * 5 * ctx->Vmax * 4;
+  const size_t nlog = static_cast<size_t>(B) * S * ctx->n_stack * ctx->Vmax * 4;
   if (a->logits) {
     if (out_kind == cudaMemcpyDeviceToHost) {
       HQ_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&dev_logits), nlog));
@@ -1605,7 +1740,8 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
     ctx->launches = 0;
   };
   if (use_graph) {
-    GraphKey key{B, S, a->pos_begin, a->pos_end, f.forced_top, f.forced_bot, f.sos_override, ctx->tracing ? 1 : 0};
+    GraphKey key{B, S, a->pos_begin, a->pos_end, f.forced_top, f.forced_bot | (f.forced_mid << 1), f.sos_override,
+                 ctx->tracing ? 1 : 0};
     auto it = ctx->graphs.find(key);
     if (it == ctx->graphs.end()) {
       plan_chains();
@@ -1656,6 +1792,7 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
 
   HQ_CUDA(ctx, cudaMemcpyAsync(a->codes_top, ctx->codes_top, nt, out_kind, st));
   HQ_CUDA(ctx, cudaMemcpyAsync(a->codes_bot, ctx->codes_bot, nb, out_kind, st));
+  if (ctx->levels == 3) HQ_CUDA(ctx, cudaMemcpyAsync(a->codes_mid, ctx->codes_mid, nm, out_kind, st));
   if (dev_logits) {
     HQ_CUDA(ctx, cudaMemcpyAsync(a->logits, dev_logits, nlog, cudaMemcpyDeviceToHost, st));
     HQ_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1815,7 +1952,7 @@ extern "C" int hq_debug_sample(const float* logits, int R, int V, float temperat
   SampleArgs sa;
   memset(&sa, 0, sizeof(sa));
   sa.logits = logits; sa.ldl = V; sa.V = V; sa.R = R; sa.rows_per_b = 1; sa.slot0 = slot; sa.sp = nullptr;
-  sa.pos = position; sa.S = 1; sa.flat_out = out_codes; sa.probs_out = out_probs; sa.Vmax = V;
+  sa.pos = position; sa.S = 1; sa.flat_out = out_codes; sa.probs_out = out_probs; sa.Vmax = V; sa.n_slots = 5; sa.dst_w = 1;
   sa.temperature = temperature; sa.top_p = top_p; sa.top_k = top_k; sa.seed = seed; sa.row_offset = row_offset;
   sa.bot_slot = -1;
   launch_sample(&tmp, static_cast<cudaStream_t>(stream), sa);

@@ -135,6 +135,92 @@ embed_depth_kernel(int trace_id, float* y, const float* E_top_depth, const float
   }
 }
 
+// 3-level HQTransformer, spatial input token (hqtransformer.py:453-487, emb_blocks empty):
+//   pos == 0 : x[b] = sos row;  pos > 0 : x[b] = mean_21( {E0[c_top] + P_top[pos-1], E1[c_mid 0..3], E2[c_bot 0..15]} + P_emb[0..20] )
+struct Embed3Args {
+  float* x;
+  const float* sos_table; const float* sos_override; const int64_t* cond;
+  const float* E0; const float* E1; const float* E2; const float* P_top; const float* P_emb;
+  const int64_t* codes_top;   // [B, S]
+  const int64_t* codes_mid;   // [B, S, 4]
+  const int64_t* codes_bot;   // [B, S, 16]
+  int D, S, pos, cond_kind;
+};
+__global__ void __launch_bounds__(1024) embed3_kernel(int trace_id, Embed3Args a) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  float4* xo = reinterpret_cast<float4*>(a.x + static_cast<size_t>(b) * a.D);
+  const int n4 = a.D / 4;
+  if (a.pos == 0) {
+    const float* src;
+    if (a.sos_override != nullptr) src = a.sos_override + static_cast<size_t>(b) * a.D;
+    else if (a.cond_kind == HQ_COND_CLS) src = a.sos_table + static_cast<size_t>(a.cond[b]) * a.D;
+    else src = a.sos_table;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) xo[i] = s4[i];
+    return;
+  }
+  const int p = a.pos - 1;
+  __shared__ const float* rows[21];
+  if (threadIdx.x < 21) {
+    const size_t bp = static_cast<size_t>(b) * a.S + p;
+    const int j = threadIdx.x;
+    rows[j] = j == 0 ? a.E0 + static_cast<size_t>(a.codes_top[bp]) * a.D
+            : j < 5 ? a.E1 + static_cast<size_t>(a.codes_mid[bp * 4 + (j - 1)]) * a.D
+                    : a.E2 + static_cast<size_t>(a.codes_bot[bp * 16 + (j - 5)]) * a.D;
+  }
+  __syncthreads();
+  const float4* pt = reinterpret_cast<const float4*>(a.P_top + static_cast<size_t>(p) * a.D);
+  const float4* pe = reinterpret_cast<const float4*>(a.P_emb);
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    // the order of the reference: cat([e0 + pos, e1.., e2..]) + pos_emb_emb, then mean over the 21 tokens (sequential sum)
+    const float4 t = reinterpret_cast<const float4*>(rows[0])[i], q = pt[i], e0 = pe[i];
+    float4 acc;
+    acc.x = (t.x + q.x) + e0.x; acc.y = (t.y + q.y) + e0.y; acc.z = (t.z + q.z) + e0.z; acc.w = (t.w + q.w) + e0.w;
+#pragma unroll 4
+    for (int j = 1; j < 21; ++j) {
+      const float4 e = reinterpret_cast<const float4*>(rows[j])[i], pj = pe[j * n4 + i];
+      acc.x += e.x + pj.x; acc.y += e.y + pj.y; acc.z += e.z + pj.z; acc.w += e.w + pj.w;
+    }
+    acc.x /= 21.0f; acc.y /= 21.0f; acc.z /= 21.0f; acc.w /= 21.0f;
+    xo[i] = acc;
+  }
+}
+
+// 3-level depth pass 2 input ('parallel-add', hqtransformer.py:521-548): token t of the 4x4 bottom cell (raster order):
+//   y[b*16 + t] = E1_depth[c_mid[b, parent(t)]] + P2[t] + E0_depth[c_top[b]],  parent(t) = (row/2)*2 + col/2
+__global__ void __launch_bounds__(1024)
+embed_depth2_kernel(int trace_id, float* y, const float* E1d, const float* E0d, const float* P2, const int64_t* codes_top,
+                    const int64_t* codes_mid, int S, int pos, int D) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const size_t bp = static_cast<size_t>(b) * S + pos;
+  const float4* e0 = reinterpret_cast<const float4*>(E0d + static_cast<size_t>(codes_top[bp]) * D);
+  const float4* em[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) em[j] = reinterpret_cast<const float4*>(E1d + static_cast<size_t>(codes_mid[bp * 4 + j]) * D);
+  const float4* p2 = reinterpret_cast<const float4*>(P2);
+  const int n4 = D / 4;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const float4 top = e0[i];
+    float4 m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = em[j][i];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const float4 mm = m[((t >> 2) >> 1) * 2 + ((t & 3) >> 1)];
+      const float4 pp = p2[t * n4 + i];
+      // (E1 + P2) + E0: the reference adds the position embedding first, the top-code embedding last (:531-548)
+      reinterpret_cast<float4*>(y + (static_cast<size_t>(b) * 16 + t) * D)[i] =
+          make_float4((mm.x + pp.x) + top.x, (mm.y + pp.y) + top.y, (mm.z + pp.z) + top.z, (mm.w + pp.w) + top.w);
+    }
+  }
+}
+
 // model_type 'top2bot' (hierarchical_ar.py:596-601): input of depth pass c >= 1:
 //   y[b] = E[code[b]] + P_depth[c - 1], E = tok_emb_top_depth with the top code (c == 1), tok_emb_bot_depth with bottom
 //   code c - 2 otherwise.  `codes` points at the first code (element stride `cstride` int64 between images).
@@ -1032,14 +1118,15 @@ struct SampleArgs {
   int slot0;            // 0 (top) | 1 (bottom): Philox slot / logits_out slot of the first row of a batch element
   const hq_sampling_params* sp;  // device copy
   int pos, S;
-  int64_t* codes_top;   // [B, S]      written when rows_per_b == 1
-  int64_t* codes_bot;   // [B, S, 4]   written when rows_per_b == 4
+  int64_t* dst_codes;   // code array the draws go to: [B, S, dst_w]
+  int dst_w;            // 1 (top codes), 4 (bottom codes of the 2-level model / middle codes), 16 (3-level bottom codes)
+  int n_slots;          // stack size (5 | 21): slot stride of logits_out
   int forced;           // 1: codes are given (teacher forcing): leave them untouched
   float* logits_out;    // optional [B, S, 5, Vmax]
   int Vmax;
-  int temp_sel;         // which softmax temperature: 0 = top, 1 = bottom
-  int filt_sel;         // which top-k / top-p pair:  0 = top, 1 = bottom
-  int bot_slot;         // rows_per_b == 1 only: >= 0 -> the code goes to codes_bot[b, pos, bot_slot] ('top2bot' passes 1..4)
+  int temp_sel;         // which softmax temperature: 0 = top, 1 = bottom, 2 = middle (3-level model)
+  int filt_sel;         // which top-k / top-p pair:  0 = top, 1 = bottom, 2 = middle
+  int bot_slot;         // rows_per_b == 1 only: >= 0 -> the code goes to dst_codes[b, pos, bot_slot] ('top2bot' passes 1..4)
   float* probs_out;     // optional [R, V] (debug)
   int64_t* flat_out;    // optional [R] (debug)
   // debug overrides (sp == nullptr)
@@ -1095,9 +1182,9 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 4 : 1) sample_kernel(int t
 
   float temperature, top_p; int top_k; uint64_t seed, row_offset;
   if (a.sp != nullptr) {
-    temperature = a.temp_sel == 0 ? a.sp->temperature_top : a.sp->temperature_bot;
-    top_p = a.filt_sel == 0 ? a.sp->top_p_top : a.sp->top_p_bot;
-    top_k = a.filt_sel == 0 ? a.sp->top_k_top : a.sp->top_k_bot;
+    temperature = a.temp_sel == 0 ? a.sp->temperature_top : (a.temp_sel == 1 ? a.sp->temperature_bot : a.sp->temperature_mid);
+    top_p = a.filt_sel == 0 ? a.sp->top_p_top : (a.filt_sel == 1 ? a.sp->top_p_bot : a.sp->top_p_mid);
+    top_k = a.filt_sel == 0 ? a.sp->top_k_top : (a.filt_sel == 1 ? a.sp->top_k_bot : a.sp->top_k_mid);
     seed = a.sp->seed; row_offset = a.sp->row_offset;
   } else {
     temperature = a.temperature; top_p = a.top_p; top_k = a.top_k; seed = a.seed; row_offset = a.row_offset;
@@ -1111,7 +1198,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 4 : 1) sample_kernel(int t
     z[i] = v.x; z[i + 1] = v.y; z[i + 2] = v.z; z[i + 3] = v.w;
   }
   if (a.logits_out != nullptr) {
-    float* lo = a.logits_out + ((static_cast<size_t>(b) * a.S + a.pos) * 5 + slot) * a.Vmax;
+    float* lo = a.logits_out + ((static_cast<size_t>(b) * a.S + a.pos) * a.n_slots + slot) * a.Vmax;
 #pragma unroll
     for (int i = 0; i < SMP_IPT; ++i)
       if (i < ipt && base + i < V) lo[base + i] = z[i];
@@ -1125,9 +1212,8 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 4 : 1) sample_kernel(int t
 
   int64_t* dst = a.flat_out != nullptr
                      ? a.flat_out + r
-                     : (a.rows_per_b == 1 && a.bot_slot < 0
-                            ? a.codes_top + static_cast<size_t>(b) * a.S + a.pos
-                            : a.codes_bot + (static_cast<size_t>(b) * a.S + a.pos) * 4 + (a.rows_per_b == 1 ? a.bot_slot : jj));
+                     : a.dst_codes + (static_cast<size_t>(b) * a.S + a.pos) * a.dst_w +
+                           (a.rows_per_b == 1 ? (a.bot_slot < 0 ? 0 : a.bot_slot) : jj);
 
   // ---- greedy: lowest index among the maxima ----
   float mx = -INFINITY;

@@ -24,6 +24,10 @@ class SamplingParams:
     temperature_bot: float = 1.0
     seed: int = 0
     row_offset: int = 0
+    # middle level of the 3-level HQTransformer (top = level 0, bot = level 2 there)
+    top_k_mid: Optional[int] = None
+    top_p_mid: Optional[float] = None
+    temperature_mid: float = 1.0
 
     def to_c(self) -> HQSamplingParams:
         # top_p <= 0 (not None): the reference's nucleus cut then drops every sorted entry but the first
@@ -39,7 +43,10 @@ class SamplingParams:
             top_p_top=float(self.top_p_top) if self.top_p_top is not None else 0.0,
             top_p_bot=float(self.top_p_bot) if self.top_p_bot is not None else 0.0,
             temperature_top=float(self.temperature_top), temperature_bot=float(self.temperature_bot),
-            seed=int(self.seed) & 0xFFFFFFFFFFFFFFFF, row_offset=int(self.row_offset))
+            seed=int(self.seed) & 0xFFFFFFFFFFFFFFFF, row_offset=int(self.row_offset),
+            top_k_mid=k_of(self.top_k_mid, self.top_p_mid),
+            top_p_mid=float(self.top_p_mid) if self.top_p_mid is not None else 0.0,
+            temperature_mid=float(self.temperature_mid), reserved=0)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -54,7 +61,8 @@ class Engine:
                  ctx_len_txt: int = 64, cond: str = "cls", precision: str = "bf16", max_seq_len: int = 64,
                  max_batch: int = 16, device: Union[int, str, torch.device] = 0, use_cuda_graph: bool = True,
                  use_pdl: bool = True, use_chain: bool = False, model_type: str = "parallel",
-                 embedding_type: str = "transformer1", position_embedding: str = "1d"):
+                 embedding_type: str = "transformer1", position_embedding: str = "1d", code_levels: int = 2,
+                 vocab_mid: int = 0):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
@@ -73,7 +81,10 @@ class Engine:
                        max_seq_len=max_seq_len, use_cuda_graph=1 if use_cuda_graph else 0,
                        use_pdl=1 if use_pdl else 0, use_chain=1 if use_chain else 0,
                        model_type=_lib.HQ_MODEL[model_type], embedding_kind=_lib.HQ_EMB[embedding_type],
-                       position_kind=_lib.HQ_POS[position_embedding])
+                       position_kind=_lib.HQ_POS[position_embedding], code_levels=int(code_levels), vocab_mid=int(vocab_mid))
+        self.code_levels = int(code_levels)
+        if self.code_levels == 3:
+            self.vocab_max = max(self.vocab_max, int(vocab_mid))
         check(self._lib.hq_create(C.byref(cfg), self.device.index, int(max_batch), C.byref(self._ctx)), None, "hq_create")
 
     # ---- lifetime ----
@@ -138,10 +149,11 @@ class Engine:
             cond: Optional[torch.Tensor] = None, sos: Optional[torch.Tensor] = None,
             given_top: Optional[torch.Tensor] = None, given_bot: Optional[torch.Tensor] = None,
             codes_top: torch.Tensor = None, codes_bot: torch.Tensor = None,
-            logits: Optional[torch.Tensor] = None, host: bool = False, stream: Optional[int] = None) -> None:
+            logits: Optional[torch.Tensor] = None, host: bool = False, stream: Optional[int] = None,
+            codes_mid: Optional[torch.Tensor] = None, given_mid: Optional[torch.Tensor] = None) -> None:
         """hq_run (device tensors, async on the current torch stream) or hq_run_host (CPU tensors, synchronous)."""
         tensors = dict(cond=cond, sos=sos, given_top=given_top, given_bot=given_bot, codes_top=codes_top,
-                       codes_bot=codes_bot, logits=logits)
+                       codes_bot=codes_bot, logits=logits, codes_mid=codes_mid, given_mid=given_mid)
         for k, t in tensors.items():
             if t is None:
                 continue
@@ -153,7 +165,7 @@ class Engine:
         args = HQRunArgs(batch=batch, seq_len=seq_len, pos_begin=pos_begin, pos_end=pos_end,
                          cond=_ptr(cond), sos=_ptr(sos), given_top=_ptr(given_top), given_bot=_ptr(given_bot),
                          codes_top=_ptr(codes_top), codes_bot=_ptr(codes_bot), logits=_ptr(logits),
-                         sampling=sampling.to_c())
+                         sampling=sampling.to_c(), codes_mid=_ptr(codes_mid), given_mid=_ptr(given_mid))
         if host:
             check(self._lib.hq_run_host(self._ctx, C.byref(args)), self._ctx, "hq_run_host")
         else:

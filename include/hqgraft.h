@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HQ_ABI_VERSION 5
+#define HQ_ABI_VERSION 6
 
 enum hq_status {
   HQ_OK = 0,
@@ -91,6 +91,10 @@ typedef struct hq_config {
   int32_t model_type;      /* hq_model_type */
   int32_t embedding_kind;  /* hq_embedding_kind */
   int32_t position_kind;   /* hq_position_kind */
+  int32_t code_levels;     /* 2: iHQGPT (1 top + 4 bottom codes per position); 3: the multi-level `HQTransformer`
+                              (hqvae/models/stage2/hqtransformer.py, decoding_type 'parallel-add', embedding 'transformer1'):
+                              1 top + 4 middle + 16 bottom codes per position in three depth passes.  0 is read as 2. */
+  int32_t vocab_mid;       /* code_levels == 3: vocab_sizes[1] (vocab_top = vocab_sizes[0], vocab_bot = vocab_sizes[2]) */
 } hq_config;
 
 /* Arguments of Sample(z; T, k, p) - hierarchical_ar.py:762-785 with utils/sampling.py:12-37.
@@ -108,6 +112,10 @@ typedef struct hq_sampling_params {
   float temperature_bot;   /* softmax_temperature[1] */
   uint64_t seed;
   uint64_t row_offset;     /* global index of this shard's first row */
+  int32_t top_k_mid;       /* middle level of the 3-level model: top_k[1], top_p[1], softmax_temperature[1] */
+  float top_p_mid;         /* (hqtransformer.py:626-631); top = level 0, bot = level 2 there */
+  float temperature_mid;
+  int32_t reserved;
 } hq_sampling_params;
 
 /* One call of the sampling loop over top positions [pos_begin, pos_end).
@@ -127,9 +135,12 @@ typedef struct hq_run_args {
   const int64_t* given_top;  /* optional [B, S]: forced top codes (given_top_code, sampling.py:205-208) */
   const int64_t* given_bot;  /* optional [B, S, 4]: forced bottom codes (teacher forcing, parity only) */
   int64_t* codes_top;        /* in/out [B, S] */
-  int64_t* codes_bot;        /* in/out [B, S, 4], within-stack order j = kh*2 + kw */
-  float* logits;             /* optional out [B, S, 5, max(vocab_top, vocab_bot)] raw head outputs */
+  int64_t* codes_bot;        /* in/out [B, S, 4], within-stack order j = kh*2 + kw  (code_levels == 3: [B, S, 16], raster
+                                order of the 4x4 cell) */
+  float* logits;             /* optional out [B, S, 5, max vocab] raw head outputs (code_levels == 3: [B, S, 21, max vocab]) */
   hq_sampling_params sampling;
+  int64_t* codes_mid;        /* code_levels == 3 only: in/out [B, S, 4] middle codes, raster order of the 2x2 cell */
+  const int64_t* given_mid;  /* code_levels == 3 only: optional forced middle codes (teacher forcing, parity only) */
 } hq_run_args;
 
 typedef struct hq_ctx hq_ctx;

@@ -4,6 +4,7 @@ Run in the build container (where /root/reference exists):
 
     python -m oracle.make_golden            # writes tests/golden/ (small models + filters)
     python -m oracle.make_golden --full-size    # only the ImageNet-L12-size golden (BASELINE config 1 at real scale)
+    python -m oracle.make_golden --level3       # only the 3-level HQTransformer golden
     python -m oracle.make_golden --stage1       # only the stage-1 decode golden (SimRQGAN2Generator.decode_code)
     python -m oracle.make_golden --variants     # only the 8f-3 model variants (reduce / 2d / top2bot / bidirectional)
     python -m oracle.make_golden --all
@@ -204,6 +205,37 @@ def golden_stage1(name, seed=1, B=2):
     print(name, "pixels", tuple(px.shape), "mean |x|", float(px.abs().mean()))
 
 
+def golden_level3(cfg, name, seed, labels, S=24):
+    """greedy code grids of the unmodified 3-level `HQTransformer` (decoding_type 'parallel-add') through the
+    reference's own `sampling_hqtransformer` (scalar class) and, row by row with per-row classes, its `sampling_step`."""
+    from oracle import hq3_oracle as O3
+    P = O3.make_params(cfg, seed=seed)
+    model = R.build_reference_hq3(cfg, P)
+    g3 = dict(top_k=[1, 1, 1], top_p=[1.0, 1.0, 1.0], softmax_temperature=[1.0, 1.0, 1.0])
+    labels_t = torch.tensor(labels, dtype=torch.long)
+    sos = model.sos(labels_t).unsqueeze(1)
+    levels, past = None, None
+    for cnt in range(S):
+        if levels is None:
+            codes, pos = [None, None, None], None
+        else:
+            codes = [levels[0][:, cnt - 1:cnt], levels[1][:, cnt - 1:cnt, :], levels[2][:, cnt - 1:cnt, :]]
+            pos = torch.full((len(labels), 1), cnt - 1, dtype=torch.long)
+        step, present = model.sampling_step(sos=sos, codes=codes, pos_codes=pos, use_fp16=False, past=past, **g3)
+        present = torch.stack(present).clone()
+        past = [present] if past is None else past + [present]
+        levels = step if levels is None else [torch.cat([a, b], 1) for a, b in zip(levels, step)]
+    scalar = R.reference_sample_hq3(model, 2, int(labels[-1]), max_seq_len=S, **g3)
+    assert all(torch.equal(s[0], l[-1]) for s, l in zip(scalar, levels))
+    _, lg = O3.sample(P, cfg, labels_t, len(labels), top_k=(1, 1, 1), max_seq_len=S, return_logits=True)
+    margin = min(min_margin(lg[:, :, 0, : cfg.vocab_sizes[0]]), min_margin(lg[:, :, 1:5, : cfg.vocab_sizes[1]]),
+                 min_margin(lg[:, :, 5:, : cfg.vocab_sizes[2]]))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name), meta=meta(cfg, seed, "rich", min_logit_margin=margin),
+                        labels=np.asarray(labels, dtype=np.int64), codes_top=levels[0].numpy(), codes_mid=levels[1].numpy(),
+                        codes_bot=levels[2].numpy())
+    print(name, "min greedy margin over the run", margin)
+
+
 def golden_filters(name):
     """Known answers of cutoff_topk_logits / cutoff_topp_probs (sampling.py:12-37) incl. ties."""
     _, S = R.import_reference()
@@ -234,6 +266,12 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if "--level3" in sys.argv or "--all" in sys.argv:
+        from oracle import hq3_oracle as O3
+        # 24 positions x 21 codes x 3 rows = 1512 greedy decisions; seed searched (oracle) for a margin >= 2e-4 over all of them
+        golden_level3(O3.TINY3, "tiny3_cls_greedy.npz", seed=56, labels=[3, 9, 0], S=24)
+        if "--all" not in sys.argv:
+            return 0
     if "--stage1" in sys.argv or "--all" in sys.argv:
         golden_stage1("s1_tiny_decode.npz")
         if "--all" not in sys.argv:

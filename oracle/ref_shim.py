@@ -169,3 +169,36 @@ def build_reference_stage1(cfg, state_dict):
     assert all(k.startswith(("encoder.", "quant_conv_b.", "quantize_t.cluster", "quantize_t.embedding_avg",
                              "quantize_b.cluster", "quantize_b.embedding_avg")) for k in res.missing_keys), res.missing_keys
     return model.eval()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 3-level HQTransformer
+# ---------------------------------------------------------------------------------------------------------------------
+def build_reference_hq3(cfg, state_dict):
+    """Reference `HQTransformer` (hqvae/models/stage2/hqtransformer.py:168-216), decoding_type 'parallel-add', for an
+    `oracle.hq3_oracle.HQ3Config`."""
+    import contextlib
+    import io
+    import_reference()
+    from hqvae.models.stage2.hqtransformer import HQTransformer  # noqa: E402
+    hp = make_hparams(cfg.embed_dim, cfg.n_layers, cfg.n_heads, n_classes=cfg.n_classes, ctx_len_img=cfg.ctx_len_img)
+    hp_dec = make_hparams(cfg.embed_dim, cfg.n_layers_depth, cfg.n_heads, n_classes=cfg.n_classes, ctx_len_img=cfg.ctx_len_img)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = HQTransformer(vocab_sizes=list(cfg.vocab_sizes), vocab_size_txt=16, decoding_type="parallel-add",
+                              use_cls_cond=(cfg.cond == "cls"), use_txt_cond=False, hparams=hp, hparams_dec=hp_dec)
+    res = model.load_state_dict(state_dict, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    return model.eval()
+
+
+def reference_sample_hq3(model, num_candidates, cond, **kw):
+    """The reference's own `sampling_hqtransformer` (utils/sampling.py:240-307) on CPU (its `.cuda()` calls neutralised)."""
+    import torch
+    _, ref_sampling = import_reference()
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        return ref_sampling.sampling_hqtransformer(model, num_candidates=num_candidates, cond=cond, is_tqdm=False,
+                                                   use_fp16=False, **kw)
+    finally:
+        torch.Tensor.cuda = saved

@@ -190,3 +190,25 @@ def test_stage1_oracle_equals_reference_golden_and_live_reference():
         with torch.no_grad():
             want = model.decode_code(ct, cb)
         assert float((px - want).abs().max()) < 1e-5
+
+
+def test_oracle_3level_equals_reference_golden_and_live_reference():
+    """oracle/hq3_oracle.py against the grids of the unmodified 3-level HQTransformer ('parallel-add')."""
+    from oracle import hq3_oracle as O3
+    g, meta = load_golden("tiny3_cls_greedy.npz")
+    cfg = O3.HQ3Config.from_dict(meta["config"])
+    assert meta["min_logit_margin"] >= 1e-4
+    P = O3.make_params(cfg, seed=meta["seed"])
+    labels = torch.from_numpy(g["labels"])
+    S = g["codes_top"].shape[1]
+    ct, cm, cb = O3.sample(P, cfg, labels, len(labels), top_k=(1, 1, 1), max_seq_len=S)
+    assert np.array_equal(ct.numpy(), g["codes_top"]) and np.array_equal(cm.numpy(), g["codes_mid"])
+    assert np.array_equal(cb.numpy(), g["codes_bot"])
+    if R.reference_available():
+        model = R.build_reference_hq3(cfg, P)
+        skw = dict(top_k=[8, 16, 32], top_p=[0.9, 0.95, 0.8], softmax_temperature=[0.9, 1.1, 1.0])
+        torch.manual_seed(5)
+        want = R.reference_sample_hq3(model, 3, 4, max_seq_len=5, **skw)
+        torch.manual_seed(5)
+        got = O3.sample(P, cfg, 4, 3, max_seq_len=5, **skw)
+        assert all(torch.equal(a, b) for a, b in zip(want, got))
