@@ -70,8 +70,13 @@ def engine_kwargs(config: SimpleNamespace) -> Dict[str, Any]:
     """Maps a merged config to `iHQGPT(...)` arguments the way `ImageGPT2.__init__` does
     (hqvae/models/__init__.py:123-137) and checks that the model is one this path implements."""
     s2 = config.stage2
+    if "multilevel-hq" in s2.type:       # hqvae/models/__init__.py:138-145 -> HQTransformer
+        return dict(vocab_sizes=list(s2.vocab_sizes_img), vocab_size_txt=s2.vocab_size_txt, decoding_type=s2.decoding_type,
+                    use_cls_cond=bool(s2.use_cls_cond), use_txt_cond=bool(s2.use_txt_cond), hparams=s2.hparams,
+                    hparams_dec=s2.hparams_dec)
     if "hq-transformer" not in s2.type:
-        raise NotImplementedError(f"stage2.type={s2.type!r}: only the 2-level 'hq-transformer/*' models are on this path")
+        raise NotImplementedError(f"stage2.type={s2.type!r}: 'hq-transformer/*' (2-level iHQGPT) and 'multilevel-hq' "
+                                  "(3-level HQTransformer) are on this path")
     model_type = s2.type.split("/")[-1] if "/" in s2.type else "top2bot"
     return dict(vocab_size_top=s2.vocab_size_img, vocab_size_bot=s2.vocab_size_img, vocab_size_txt=s2.vocab_size_txt,
                 ratio_bot2top=s2.ratio_bot2top, use_cls_cond=bool(s2.use_cls_cond), use_txt_cond=bool(s2.use_txt_cond),

@@ -12,7 +12,8 @@ The "ar" figure is the sampling loop, "decode" is stage 1 (`model.stage1.decode_
 The reference decodes one image at a time (`codes.chunk(batch_size)`, :108-111); here the batch is decoded in one call
 (`decode_chunks=1`; `decode_chunks=<batch_size>` reproduces the one-by-one protocol).  `stage1=0` skips the decoder.
 The README of the reference spells the level key `code-level` (configs/README.md:70) while the dataclass field is
-`code_levels` (:48); both are accepted.  code_levels=3 (the 3-level `HQTransformer`) is not on this path.
+`code_levels` (:48); both are accepted.  code_levels=3 takes a `multilevel-hq` config (the 3-level `HQTransformer`,
+configs/README.md:68-71) and times its sampler; the 3-level stage-1 decoder is not implemented, so "decode" is 0 there.
 """
 from __future__ import annotations
 
@@ -72,11 +73,13 @@ def load_model(result_path: str, device="cuda", max_batch: int = 50, with_stage1
 
 def main(args: Experiment):
     torch.set_grad_enabled(False)
-    if args.code_levels != 2:
-        raise NotImplementedError("code_levels=3 (the 3-level HQTransformer, hqvae/models/stage2/hqtransformer.py) is not on "
-                                  "this path; only the 2-level iHQGPT sampler is accelerated")
+    if args.code_levels not in (2, 3):
+        raise NotImplementedError("code_levels must be 2 (iHQGPT) or 3 (HQTransformer)")
     device = torch.device("cuda")
-    model_ar = load_model(args.model_path, device, args.batch_size, with_stage1=bool(args.stage1)).to(device).eval()
+    model_ar = load_model(args.model_path, device, args.batch_size,
+                          with_stage1=bool(args.stage1) and args.code_levels == 2).to(device).eval()
+    if (args.code_levels == 3) != hasattr(model_ar.stage2, "code_level"):
+        raise SystemExit(f"code_levels={args.code_levels} does not match the model type of {args.model_path}")
     title = f"bs{args.batch_size}, sampling loops {args.warmup + 1}-{args.n_loop}"
     print(title)
     print("python: %s, torch: %s, cudnn: %s, cuda: %s, gpu: %s" % (
@@ -89,6 +92,7 @@ def main(args: Experiment):
     n_loop = args.n_loop
     n_classes = model_ar.stage2.n_classes or 1000
     is_txt = model_ar.stage2.use_txt_cond
+    from .hqtransformer3 import sampling_hqtransformer
 
     def loop(loop_idx: int):
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(n_iter_per_loop)]
@@ -102,6 +106,13 @@ def main(args: Experiment):
                 cond = torch.randint(0, model_ar.stage2.vocab_size_txt, (batch_size, model_ar.stage2.ctx_len_txt), device=device)
             else:
                 cond = random.randint(0, n_classes - 1)
+            if args.code_levels == 3:     # measure_throughput/__main__.py:113-127: sampling_hqtransformer, top_k / top_p None
+                sampling_hqtransformer(model_ar.stage2, num_candidates=batch_size, cond=cond, top_k=[None] * 3, top_p=[None] * 3,
+                                       softmax_temperature=[1.0] * 3, use_fp16=True, is_tqdm=False,
+                                       max_seq_len=args.top_resolution * args.top_resolution)
+                middles[i].record()
+                ends[i].record()
+                continue
             codes_t, codes_b = sampling_ihqgpt(model_ar.stage2, cond=cond, num_candidates=batch_size, top_k_top=None,
                                                top_p_top=None, top_k_bot=None, top_p_bot=None,
                                                softmax_temperature=[1.0 for _ in range(args.code_levels)], use_fp16=True,

@@ -290,7 +290,12 @@ class ImageGPT2:
     def __init__(self, config, with_stage1: bool = False, stage1_max_batch: int = 16, **engine_opts) -> None:
         self.config = config
         self.stage1 = None
-        self.stage2 = iHQGPT(**engine_kwargs(config), **engine_opts)
+        if "multilevel-hq" in config.stage2.type:               # hqvae/models/__init__.py:138-145
+            from .hqtransformer3 import HQTransformer
+            engine_opts.pop("use_chain", None)
+            self.stage2 = HQTransformer(**engine_kwargs(config), **engine_opts)
+        else:
+            self.stage2 = iHQGPT(**engine_kwargs(config), **engine_opts)
         if with_stage1:
             # the `decode_code` half of the HQ-VAE (hqvae/models/__init__.py:96-101 builds the whole generator)
             from .stage1 import HQVAEDecoder
