@@ -6,7 +6,7 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libhqgraft.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 HQ_OK = 0
 HQ_COND_CLS, HQ_COND_TXT, HQ_COND_UNCOND = 0, 1, 2
@@ -36,7 +36,8 @@ class HQRunArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("seq_len", C.c_int32), ("pos_begin", C.c_int32), ("pos_end", C.c_int32),
                 ("cond", C.c_void_p), ("sos", C.c_void_p), ("given_top", C.c_void_p), ("given_bot", C.c_void_p),
                 ("codes_top", C.c_void_p), ("codes_bot", C.c_void_p), ("logits", C.c_void_p),
-                ("sampling", HQSamplingParams), ("codes_mid", C.c_void_p), ("given_mid", C.c_void_p)]
+                ("sampling", HQSamplingParams), ("codes_mid", C.c_void_p), ("given_mid", C.c_void_p),
+                ("shared_prefix", C.c_int32), ("reserved", C.c_int32)]
 
 
 class HQS1Config(C.Structure):

@@ -1391,6 +1391,7 @@ static void run_block(hq_ctx* ctx, cudaStream_t st, const BlockW& w, float* x, i
 
 struct RunFlags {
   int forced_top, forced_bot, sos_override, forced_mid;
+  int shared_prefix;    // text models: every row has the same prompt - prefill image 0 only, broadcast its cache rows
   float* logits_out;
 };
 
@@ -1400,7 +1401,9 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
   const int D = ctx->D, T0 = ctx->T0, Tc = ctx->Tc;
   const bool txt = ctx->cfg.cond_kind == HQ_COND_TXT;
   const bool prefill = txt && pos == 0;
-  const int M = prefill ? B * T0 : B;
+  const bool shared = prefill && f.shared_prefix && B > 1;
+  const int Bp = shared ? 1 : B;                      // images the prefill runs for
+  const int M = prefill ? Bp * T0 : B;
   AT* kc = static_cast<AT*>(ctx->kc);
   AT* vc = static_cast<AT*>(ctx->vc);
   AT* kd = static_cast<AT*>(ctx->kd);
@@ -1452,10 +1455,13 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
   } else {
     launch_k(ctx, st, "layernorm_f", fold_x.n > 3 ? layernorm_kernel<float, LN_MAXFOLD> : layernorm_kernel<float, 3>, dim3(B),
              dim3(LN_THREADS), 0, ctx->x, ctx->lnf_g, ctx->lnf_b,
-             ctx->sos_depth, ctx->yd, B, D, prefill ? T0 : 1, prefill ? T0 - 1 : 0, fold_x.partial, fold_x.n, fold_x.stride,
+             ctx->sos_depth, ctx->yd, prefill ? Bp : B, D, prefill ? T0 : 1, prefill ? T0 - 1 : 0, fold_x.partial, fold_x.n, fold_x.stride,
              fold_x.bias, 1, ctx->cfg.model_type == HQ_MODEL_BIDIRECTIONAL ? 5 : 1);
   }
   fold_x = Fold();
+  if (shared)    // one prompt, B samples: image 0's prefix cache rows (all layers) and depth start token -> images 1..B-1
+    launch_k(ctx, st, "broadcast_prefix", broadcast_prefix_kernel<AT>, dim3(T0, ctx->L, B - 1), dim3(256), 0, kc, vc, ctx->yd,
+             ctx->max_batch, Tc, D);
 
   SampleArgs sa;
   memset(&sa, 0, sizeof(sa));
@@ -1690,6 +1696,8 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
   f.forced_top = a->given_top != nullptr;
   f.forced_bot = a->given_bot != nullptr;
   f.forced_mid = ctx->levels == 3 && a->given_mid != nullptr;
+  f.shared_prefix = a->shared_prefix != 0 && ctx->cfg.cond_kind == HQ_COND_TXT && a->sos == nullptr &&
+                    ctx->cfg.model_type != HQ_MODEL_BIDIRECTIONAL;
   f.sos_override = a->sos != nullptr;
   f.logits_out = nullptr;
   float* dev_logits = nullptr;
@@ -1740,7 +1748,7 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
     ctx->launches = 0;
   };
   if (use_graph) {
-    GraphKey key{B, S, a->pos_begin, a->pos_end, f.forced_top, f.forced_bot | (f.forced_mid << 1), f.sos_override,
+    GraphKey key{B, S, a->pos_begin, a->pos_end, f.forced_top, f.forced_bot | (f.forced_mid << 1) | (f.shared_prefix << 2), f.sos_override,
                  ctx->tracing ? 1 : 0};
     auto it = ctx->graphs.find(key);
     if (it == ctx->graphs.end()) {

@@ -221,6 +221,28 @@ embed_depth2_kernel(int trace_id, float* y, const float* E1d, const float* E0d, 
   }
 }
 
+// Shared text prefix (one prompt sampled N times, e.g. the reference notebook repeats a prompt 8x): the prefill
+// ran for image 0 only; its T0 cached key / value rows of every layer and its depth start token are broadcast to images 1..B-1.
+// K / V: [L][Bmax][Tc][D]; grid (T0, L, B - 1).
+template <typename AT>
+__global__ void __launch_bounds__(256)
+broadcast_prefix_kernel(int trace_id, AT* K, AT* V, float* yd, int Bmax, int Tc, int D) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = blockIdx.x, l = blockIdx.y, b = blockIdx.z + 1;
+  const size_t src = (static_cast<size_t>(l) * Bmax * Tc + t) * D;
+  const size_t dst = ((static_cast<size_t>(l) * Bmax + b) * Tc + t) * D;
+  constexpr int V8 = 16 / static_cast<int>(sizeof(AT));
+  for (int i = threadIdx.x * V8; i < D; i += blockDim.x * V8) {
+    *reinterpret_cast<uint4*>(K + dst + i) = *reinterpret_cast<const uint4*>(K + src + i);
+    *reinterpret_cast<uint4*>(V + dst + i) = *reinterpret_cast<const uint4*>(V + src + i);
+  }
+  if (t == 0 && l == 0)
+    for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4)
+      *reinterpret_cast<float4*>(yd + static_cast<size_t>(b) * D + i) = *reinterpret_cast<const float4*>(yd + i);
+}
+
 // model_type 'top2bot' (hierarchical_ar.py:596-601): input of depth pass c >= 1:
 //   y[b] = E[code[b]] + P_depth[c - 1], E = tok_emb_top_depth with the top code (c == 1), tok_emb_bot_depth with bottom
 //   code c - 2 otherwise.  `codes` points at the first code (element stride `cstride` int64 between images).

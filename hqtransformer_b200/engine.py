@@ -150,7 +150,8 @@ class Engine:
             given_top: Optional[torch.Tensor] = None, given_bot: Optional[torch.Tensor] = None,
             codes_top: torch.Tensor = None, codes_bot: torch.Tensor = None,
             logits: Optional[torch.Tensor] = None, host: bool = False, stream: Optional[int] = None,
-            codes_mid: Optional[torch.Tensor] = None, given_mid: Optional[torch.Tensor] = None) -> None:
+            codes_mid: Optional[torch.Tensor] = None, given_mid: Optional[torch.Tensor] = None,
+            shared_prefix: bool = False) -> None:
         """hq_run (device tensors, async on the current torch stream) or hq_run_host (CPU tensors, synchronous)."""
         tensors = dict(cond=cond, sos=sos, given_top=given_top, given_bot=given_bot, codes_top=codes_top,
                        codes_bot=codes_bot, logits=logits, codes_mid=codes_mid, given_mid=given_mid)
@@ -165,7 +166,8 @@ class Engine:
         args = HQRunArgs(batch=batch, seq_len=seq_len, pos_begin=pos_begin, pos_end=pos_end,
                          cond=_ptr(cond), sos=_ptr(sos), given_top=_ptr(given_top), given_bot=_ptr(given_bot),
                          codes_top=_ptr(codes_top), codes_bot=_ptr(codes_bot), logits=_ptr(logits),
-                         sampling=sampling.to_c(), codes_mid=_ptr(codes_mid), given_mid=_ptr(given_mid))
+                         sampling=sampling.to_c(), codes_mid=_ptr(codes_mid), given_mid=_ptr(given_mid),
+                         shared_prefix=1 if shared_prefix else 0, reserved=0)
         if host:
             check(self._lib.hq_run_host(self._ctx, C.byref(args)), self._ctx, "hq_run_host")
         else:

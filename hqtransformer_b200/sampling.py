@@ -20,7 +20,7 @@ def sampling_ihqgpt(model, num_candidates: int, cond, top_k_top: Optional[float]
                     top_p_bot: Optional[float] = None, softmax_temperature: List[float] = [1.0, 1.0],
                     is_tqdm: bool = True, use_fp16: bool = True, max_seq_len: int = 256, model_stage1=None,
                     given_top_code: Optional[torch.Tensor] = None, *, seed: Optional[int] = None,
-                    row_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                    row_offset: int = 0, shared_prefix: Optional[bool] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """utils/sampling.py:164-237.
 
     cond: class id (int, broadcast to the batch as in the reference :183-186, or an int64 [B] tensor for per-row
@@ -30,7 +30,10 @@ def sampling_ihqgpt(model, num_candidates: int, cond, top_k_top: Optional[float]
     seed: Philox key of the draws.  Default: a fresh 63-bit value drawn from torch's default CPU generator on every
     call - like the reference's `torch.multinomial`, consecutive calls advance the global generator (the scripts call
     the sampler many times per class with identical arguments, sampling_hqmodel.py:180-193) and `set_seed`
-    (utils/utils.py:6-10) reproduces the whole run."""
+    (utils/utils.py:6-10) reproduces the whole run.
+    shared_prefix (text models): one prompt sampled B times (the reference notebook repeats a prompt 8x) - the 64-token
+    prefill runs once and its KV-cache rows are broadcast.  None = detect (all rows of `cond` equal); results are
+    identical either way."""
     if max_seq_len > model.max_seq_len:
         raise ValueError(f"max_seq_len={max_seq_len} exceeds the engine's {model.max_seq_len} top positions "
                          "(the scripts pass 64 for 8x8 top codes)")
@@ -53,9 +56,25 @@ def sampling_ihqgpt(model, num_candidates: int, cond, top_k_top: Optional[float]
             raise ValueError(f"given_top_code must be [B, >= {max_seq_len}], got {tuple(given_top_code.shape)}")
         if int(given.min()) < 0 or int(given.max()) >= model.vocab_size_top:
             raise IndexError(f"given_top_code out of range [0, {model.vocab_size_top})")
+    if shared_prefix is None:
+        shared_prefix = bool(model.use_txt_cond and cond_t is not None and B > 1 and bool((cond_t == cond_t[:1]).all()))
     eng.run(batch=B, seq_len=max_seq_len, pos_begin=0, pos_end=max_seq_len, sampling=sp, cond=cond_t,
-            given_top=given, codes_top=codes_top, codes_bot=codes_bot)
+            given_top=given, codes_top=codes_top, codes_bot=codes_bot, shared_prefix=bool(shared_prefix))
     return codes_top, codes_bot
+
+
+def encode_prompts(tokenizer, texts, context_length: int = 64) -> torch.Tensor:
+    """Text front-end of the txt2img scripts (hqvae/datasets/__init__.py:145-152, sampling_hqmodel_txt2img.py): pad with
+    "[PAD]" / truncate every prompt to `context_length` tokens with a HuggingFace `tokenizers` tokenizer built as
+    hqvae/tokenizers/__init__.py:15-38 does (`create_tokenizer('bpe16k_huggingface', lowercase=True, dropout=None)`; the
+    vocabulary files ship with the reference, not with this repo).  Returns int64 [len(texts), context_length]: the `cond`
+    of `sampling_ihqgpt` for a text-conditional model."""
+    tokenizer.add_special_tokens(["[PAD]"])
+    tokenizer.enable_padding(length=context_length, pad_id=tokenizer.token_to_id("[PAD]"))
+    tokenizer.enable_truncation(max_length=context_length)
+    if isinstance(texts, str):
+        texts = [texts]
+    return torch.tensor([tokenizer.encode(t).ids for t in texts], dtype=torch.int64)
 
 
 @torch.no_grad()

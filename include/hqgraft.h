@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HQ_ABI_VERSION 6
+#define HQ_ABI_VERSION 7
 
 enum hq_status {
   HQ_OK = 0,
@@ -141,6 +141,10 @@ typedef struct hq_run_args {
   hq_sampling_params sampling;
   int64_t* codes_mid;        /* code_levels == 3 only: in/out [B, S, 4] middle codes, raster order of the 2x2 cell */
   const int64_t* given_mid;  /* code_levels == 3 only: optional forced middle codes (teacher forcing, parity only) */
+  int32_t shared_prefix;     /* text models, pos_begin == 0: 1 = every row of `cond` is the SAME prompt (one prompt sampled B
+                                times, as the reference notebook does): the 64-token prefill runs for row 0 only and its
+                                cached keys / values are broadcast to the other rows.  Results are identical to 0. */
+  int32_t reserved;
 } hq_run_args;
 
 typedef struct hq_ctx hq_ctx;

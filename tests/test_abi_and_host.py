@@ -30,7 +30,7 @@ def test_struct_layouts_match_header_sizes():
     from hqtransformer_b200 import _lib
     assert ctypes.sizeof(_lib.HQConfig) == 21 * 4
     assert ctypes.sizeof(_lib.HQSamplingParams) == 56
-    assert ctypes.sizeof(_lib.HQRunArgs) == 16 + 7 * 8 + 56 + 2 * 8
+    assert ctypes.sizeof(_lib.HQRunArgs) == 16 + 7 * 8 + 56 + 2 * 8 + 8
 
 
 def test_philox_known_answers():
@@ -168,3 +168,17 @@ def test_committed_bench_evidence_carries_the_contract_keys():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     ra = d["roofline_attention"]
     assert ra["bound"] == "hbm" and abs(ra["frac"] - ra["achieved"] / ra["peak"]) < 1e-9
+
+
+def test_encode_prompts_pads_and_truncates_like_the_reference_dataset():
+    """hqvae/datasets/__init__.py:145-152: "[PAD]" padding to the context length + truncation, int64 [N, 64]."""
+    tokenizers = pytest.importorskip("tokenizers")
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from hqtransformer_b200.sampling import encode_prompts
+    vocab = {"[UNK]": 0, "a": 1, "photo": 2, "of": 3, "cat": 4, "dog": 5}
+    tok = Tokenizer(models.WordLevel(vocab, unk_token="[UNK]"))
+    tok.pre_tokenizer = pre_tokenizers.Whitespace()
+    ids = encode_prompts(tok, ["a photo of a cat", "dog " * 100], context_length=8)
+    assert ids.dtype == torch.int64 and tuple(ids.shape) == (2, 8)
+    pad = tok.token_to_id("[PAD]")
+    assert ids[0].tolist() == [1, 2, 3, 1, 4, pad, pad, pad] and ids[1].tolist() == [5] * 8

@@ -366,3 +366,24 @@ def test_errors_are_loud():
                           given_top_code=torch.full((2, 64), cfg.vocab_top, dtype=torch.int64))
     with pytest.raises(RuntimeError, match="no bf16 engine"):   # fp32-only model asked for the bf16 path
         H.sampling_ihqgpt(model, 2, 0, max_seq_len=64, use_fp16=True)
+
+
+def test_shared_text_prefix_equals_per_row_prefill():
+    """one prompt sampled B times - the prefill runs for one row and its KV-cache rows are broadcast
+    (hq_run_args.shared_prefix); grids are identical to prefilling every row, greedy and stochastic, fp32 and bf16."""
+    import hqtransformer_b200 as H
+    from dataclasses import replace
+    cfg = replace(O.ASYM, cond="txt")
+    P = O.make_params(cfg, seed=6, init="rich")
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, cfg.vocab_txt, (1, cfg.ctx_len_txt), generator=g).repeat(7, 1)
+    for precision, fp16 in (("fp32", False), ("bf16", True)):
+        model = build_model(cfg, P, precision=precision, max_batch=7, max_seq_len=6)
+        for kw in (dict(top_k_top=1, top_k_bot=1), dict(top_k_top=20, top_k_bot=30, softmax_temperature=[0.9, 1.1])):
+            a = H.sampling_ihqgpt(model, 7, ids, max_seq_len=6, is_tqdm=False, use_fp16=fp16, seed=5, shared_prefix=False, **kw)
+            b = H.sampling_ihqgpt(model, 7, ids, max_seq_len=6, is_tqdm=False, use_fp16=fp16, seed=5, shared_prefix=True, **kw)
+            c = H.sampling_ihqgpt(model, 7, ids, max_seq_len=6, is_tqdm=False, use_fp16=fp16, seed=5, **kw)     # auto-detected
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    # greedy + one prompt: every row identical (as in the reference)
+    gt, gb = H.sampling_ihqgpt(model, 7, ids, max_seq_len=6, is_tqdm=False, use_fp16=True, top_k_top=1, top_k_bot=1)
+    assert bool((gt == gt[:1]).all()) and bool((gb == gb[:1]).all())
