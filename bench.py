@@ -135,9 +135,11 @@ def cpu_reference_rate(model_name: str, batch: int, positions: int, steps: int, 
 
 
 def _oracle_cfg(model_name: str):
+    from dataclasses import replace
     from oracle import hq_oracle as O
     return {"imagenet_l12": O.IMAGENET_L12, "imagenet_l24": O.IMAGENET_L24, "imagenet_l42": O.IMAGENET_L42,
-            "cc15m_l12": O.CC15M_L12}[model_name]
+            "cc15m_l12": O.CC15M_L12,
+            "ffhq_l24": replace(O.IMAGENET_L24, embed_dim=1024, n_heads=16, cond="uncond", embedding_type="reduce")}[model_name]
 
 
 def reference_cpu_rates(model_name: str, plan, budget_s: float):
@@ -201,7 +203,7 @@ def run_reference_arm(args, rank: int):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": timed,
             "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.model}: {s2.cond}-conditional HQ-Transformer sampling, 64 top positions x (1 top + 4 "
+            "config": {"workload": f"{args.model}: {_oracle_cfg(args.model).cond}-conditional HQ-Transformer sampling, 64 top positions x (1 top + 4 "
                                    f"bottom codes), random-init weights, top_k=None top_p=None T=1.0; CPU sample: batch {B}, "
                                    f"{positions} positions per step",
                        "model": args.model, "batch": B, "positions": positions, "same_config_as_gpu_arm": False,
