@@ -264,10 +264,13 @@ s1_quant_kernel(const int64_t* __restrict__ code_t, const int64_t* __restrict__ 
 
 // GroupNorm(32 groups, eps 1e-6; layers.py:17-21) statistics over the interior of a padded fp32 NHWC tensor: partial (sum,
 // sum of squares) per (image, group, slice of rows); grid (S slices, B).  Every element is read once, as float4 along the
-// channels (thread = channel quad x pixel lane); threads keep fp32 partials of <= a few hundred terms, the cross-thread
-// reduction runs in double in a FIXED order (deterministic), and the apply kernel adds the S slices in a fixed order too.
+// channels (thread = channel quad x pixel lane, four loads in flight per thread); threads keep fp32 partials of <= a few
+// hundred terms, the cross-thread reduction runs in double in a FIXED order, and the LAST slice CTA of an image to finish
+// (ticket counter that wraps back to 0) adds the S slices in a fixed order and publishes (mean, rstd) per group: the
+// result does not depend on which CTA happens to be last.
 __global__ void __launch_bounds__(256)
-s1_gn_stats_kernel(const float* __restrict__ x, double* __restrict__ part, int Hp, int Wp, int C, int S) {
+s1_gn_stats_kernel(const float* __restrict__ x, double* __restrict__ part, float2* __restrict__ stat, unsigned* __restrict__ cnt,
+                   int Hp, int Wp, int C, int S) {
   const int s = blockIdx.x, b = blockIdx.y;
   const int H = Hp - 2, W = Wp - 2, c4 = C / 4, cg = C / 32;
   const int P = 256 / c4 > 0 ? 256 / c4 : 1;           // pixel lanes (C <= 1024)
@@ -277,14 +280,24 @@ s1_gn_stats_kernel(const float* __restrict__ x, double* __restrict__ part, int H
   const int npx = (y1 - y0) * W;
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), sq = make_float4(0.f, 0.f, 0.f, 0.f);
   if (pl < P && tid < c4 * P) {
-    for (int i = pl; i < npx; i += P) {
-      const int yy = y0 + i / W, xx = i % W;
-      const float4 v = *reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * Hp + yy + 1) * Wp + xx + 1) * C + 4 * q);
-      sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-      sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+    const float* xb = x + (static_cast<size_t>(b) * Hp * Wp) * C + 4 * q;
+    auto at = [&](int i) { return xb + (static_cast<size_t>(y0 + i / W + 1) * Wp + i % W + 1) * C; };
+    int i = pl;
+    for (; i + 3 * P < npx; i += 4 * P) {
+      const float4 v0 = *reinterpret_cast<const float4*>(at(i)), v1 = *reinterpret_cast<const float4*>(at(i + P));
+      const float4 v2 = *reinterpret_cast<const float4*>(at(i + 2 * P)), v3 = *reinterpret_cast<const float4*>(at(i + 3 * P));
+#define S1_ACC(v) sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w; \
+  sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+      S1_ACC(v0) S1_ACC(v1) S1_ACC(v2) S1_ACC(v3)
     }
+    for (; i < npx; i += P) {
+      const float4 v = *reinterpret_cast<const float4*>(at(i));
+      S1_ACC(v)
+    }
+#undef S1_ACC
   }
   __shared__ double ssum[256 * 4], ssq[256 * 4];
+  __shared__ unsigned s_ticket;
   ssum[tid * 4 + 0] = sum.x; ssum[tid * 4 + 1] = sum.y; ssum[tid * 4 + 2] = sum.z; ssum[tid * 4 + 3] = sum.w;
   ssq[tid * 4 + 0] = sq.x; ssq[tid * 4 + 1] = sq.y; ssq[tid * 4 + 2] = sq.z; ssq[tid * 4 + 3] = sq.w;
   __syncthreads();
@@ -299,51 +312,75 @@ s1_gn_stats_kernel(const float* __restrict__ x, double* __restrict__ part, int H
     double* o = part + ((static_cast<size_t>(b) * 32 + tid) * S + s) * 2;
     o[0] = a;
     o[1] = qq;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicInc(cnt + b, static_cast<unsigned>(S - 1));
+  __syncthreads();
+  if (s_ticket == static_cast<unsigned>(S - 1) && tid < 32) {
+    __threadfence();
+    const double* pp = part + (static_cast<size_t>(b) * 32 + tid) * S * 2;
+    double a = 0.0, qq = 0.0;
+    for (int k = 0; k < S; ++k) { a += __ldcg(pp + 2 * k); qq += __ldcg(pp + 2 * k + 1); }
+    const double n = static_cast<double>(H) * W * cg;
+    const double mean = a / n;
+    double var = qq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[b * 32 + tid] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + 1e-6)));
   }
 }
 
-__device__ __forceinline__ float swish_f(float v) { return v / (1.0f + expf(-v)); }
+// x * sigmoid(x) (layers.py:12-14) with the fast exponential / division: ~1e-6 relative, far below the bf16 rounding of the output
+__device__ __forceinline__ float swish_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 // y = GroupNorm(x) (optionally * sigmoid) as bf16; EVERY padded position is written, the border with zeros (the buffers are
-// reused at other resolutions: a 3x3 convolution must find zeros around its input).  One CTA per padded row (b, y).
+// reused at other resolutions: a 3x3 convolution must find zeros around its input).  One CTA per padded row (b, y), four
+// float4 loads in flight per thread.
 __global__ void __launch_bounds__(256)
-s1_gn_apply_kernel(const float* __restrict__ x, const double* __restrict__ part, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, bf16* __restrict__ out, int Hp, int Wp, int C, int S, int swish) {
+s1_gn_apply_kernel(const float* __restrict__ x, const float2* __restrict__ stat, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, bf16* __restrict__ out, int Hp, int Wp, int C, int swish) {
   const int b = blockIdx.y, y = blockIdx.x;
   const int H = Hp - 2, W = Wp - 2, cg = C / 32;
   __shared__ float s_mean[32], s_rstd[32];
   if (threadIdx.x < 32) {
-    const double* pp = part + (static_cast<size_t>(b) * 32 + threadIdx.x) * S * 2;
-    double a = 0.0, q = 0.0;
-    for (int s = 0; s < S; ++s) { a += pp[2 * s]; q += pp[2 * s + 1]; }
-    const double n = static_cast<double>(H) * W * cg;
-    const double mean = a / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = static_cast<float>(mean);
-    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-6));
+    const float2 st = stat[b * 32 + threadIdx.x];
+    s_mean[threadIdx.x] = st.x;
+    s_rstd[threadIdx.x] = st.y;
   }
   __syncthreads();
-  const int c4 = C / 4;
+  const int c4 = C / 4, total = Wp * c4;
   const size_t base = (static_cast<size_t>(b) * Hp + y) * Wp * C;
-  for (int i = threadIdx.x; i < Wp * c4; i += blockDim.x) {
-    const int xx = i / c4, c = (i % c4) * 4;
-    if (y < 1 || y > H || xx < 1 || xx > W) {
-      *reinterpret_cast<uint2*>(out + base + static_cast<size_t>(xx) * C + c) = make_uint2(0u, 0u);
-      continue;
+  const bool row_in = y >= 1 && y <= H;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * 256) {
+    float4 v[4];
+    int off[4];
+    bool in[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * 256, xx = i / c4;
+      off[k] = i < total ? xx * C + (i - xx * c4) * 4 : -1;
+      in[k] = i < total && row_in && xx >= 1 && xx <= W;
+      if (in[k]) v[k] = *reinterpret_cast<const float4*>(x + base + off[k]);
     }
-    const float4 v = *reinterpret_cast<const float4*>(x + base + static_cast<size_t>(xx) * C + c);
-    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
-    const float4 be = *reinterpret_cast<const float4*>(beta + c);
-    const int g0 = c / cg, g1 = (c + 1) / cg, g2 = (c + 2) / cg, g3 = (c + 3) / cg;
-    float o0 = (v.x - s_mean[g0]) * s_rstd[g0] * ga.x + be.x, o1 = (v.y - s_mean[g1]) * s_rstd[g1] * ga.y + be.y;
-    float o2 = (v.z - s_mean[g2]) * s_rstd[g2] * ga.z + be.z, o3 = (v.w - s_mean[g3]) * s_rstd[g3] * ga.w + be.w;
-    if (swish) { o0 = swish_f(o0); o1 = swish_f(o1); o2 = swish_f(o2); o3 = swish_f(o3); }
-    uint2 u;
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
-    u.x = *reinterpret_cast<uint32_t*>(&h0);
-    u.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(out + base + static_cast<size_t>(xx) * C + c) = u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (off[k] < 0) continue;
+      uint2 u = make_uint2(0u, 0u);
+      if (in[k]) {
+        const int c = (i0 + k * 256) % c4 * 4;
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+        const float4 be = *reinterpret_cast<const float4*>(beta + c);
+        int g0 = c / cg, g1 = g0, g2 = g0, g3 = g0;
+        if (cg & 3) { g1 = (c + 1) / cg; g2 = (c + 2) / cg; g3 = (c + 3) / cg; }
+        float o0 = (v[k].x - s_mean[g0]) * s_rstd[g0] * ga.x + be.x, o1 = (v[k].y - s_mean[g1]) * s_rstd[g1] * ga.y + be.y;
+        float o2 = (v[k].z - s_mean[g2]) * s_rstd[g2] * ga.z + be.z, o3 = (v[k].w - s_mean[g3]) * s_rstd[g3] * ga.w + be.w;
+        if (swish) { o0 = swish_f(o0); o1 = swish_f(o1); o2 = swish_f(o2); o3 = swish_f(o3); }
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+      }
+      *reinterpret_cast<uint2*>(out + base + off[k]) = u;
+    }
   }
 }
 
@@ -445,6 +482,201 @@ s1_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int H, int 
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AttnBlock core on the tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate): the CUDA-core kernel above needs ~410 us per
+// call at B = 32 (16 % of a decode); this one keeps a 64-query tile's scores in registers.
+//   CTA = (image, 64 queries), 4 warps x 16 queries.  Phase 1: S = Q K^T over 64-key chunks of K staged in shared memory
+//   (A = Q rows via ldmatrix.x4, B = K rows [key][channel] via ldmatrix.x2), softmax in registers (quad shuffles), P -> shared
+//   memory as bf16.  Phase 2: O = P V per 128-channel block over 64-key tiles of V (B = V^T via ldmatrix.x2.trans).
+//   N = H W <= 256 tokens (multiple of 16), C <= 512 channels (multiple of 64).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+#endif
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+// S1A_KC keys per K chunk (phase 1, ring of S1A_NKB buffers), S1A_VC keys x S1A_CB channels per V tile (phase 2, ring of
+// S1A_NVB): cp.async prefetch S1A_NKB - 1 / S1A_NVB - 1 tiles ahead (one warp per scheduler: nothing else hides the latency)
+constexpr int S1A_Q = 64, S1A_KC = 32, S1A_VC = 64, S1A_CB = 128, S1A_NMAX = 256, S1A_CMAX = 512, S1A_PAD = 8;
+constexpr int S1A_NKB = 3, S1A_NVB = 4;
+__host__ __device__ constexpr int s1a_kv_elems(int C) {
+  return S1A_NKB * S1A_KC * (C + S1A_PAD) > S1A_NVB * S1A_VC * (S1A_CB + S1A_PAD) ? S1A_NKB * S1A_KC * (C + S1A_PAD)
+                                                                                  : S1A_NVB * S1A_VC * (S1A_CB + S1A_PAD);
+}
+__host__ __device__ constexpr int s1a_smem_bytes(int C) {
+  return (S1A_Q * (C + S1A_PAD) + s1a_kv_elems(C) + S1A_Q * (S1A_NMAX + S1A_PAD)) * 2;
+}
+
+__global__ void __launch_bounds__(128, 1)
+s1_attn_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int H, int W, int C) {
+#if defined(__CUDA_ARCH__)
+  extern __shared__ __align__(16) uint8_t s1a_smem[];
+  const int N = H * W, Wp = W + 2;
+  const int qp = C + S1A_PAD, pp = S1A_NMAX + S1A_PAD, vp = S1A_CB + S1A_PAD;      // row pitches (elements)
+  bf16* Qs = reinterpret_cast<bf16*>(s1a_smem);                 // [64][C + 8]
+  bf16* KV = Qs + S1A_Q * qp;                                   // 2 x K chunk [32][C + 8]; phase 2: 2 x V tile [64][128 + 8]
+  bf16* Ps = KV + s1a_kv_elems(C);                              // [64][256 + 8]
+  const int kbuf = S1A_KC * qp, vbuf = S1A_VC * vp;
+  const int b = blockIdx.y, q0 = blockIdx.x * S1A_Q;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const size_t img = static_cast<size_t>(b) * (H + 2) * Wp;
+  __shared__ int tok[S1A_NMAX];                                 // padded-matrix row of token n (relative to the image)
+  for (int n = tid; n < N; n += 128) tok[n] = (n / W + 1) * Wp + (n % W + 1);
+  __syncthreads();
+  auto prow = [&](int n) { return img + static_cast<size_t>(tok[n]); };
+  const int c8 = C / 8;
+  // tile loaders: 16-byte cp.async per thread, rows beyond N zero-filled; a thread keeps its column and walks the rows
+  // (128 % ncol8 == 0 for C = 128 / 256 / 512; otherwise the generic index split)
+  auto load_rows = [&](bf16* dst, int pitch, int rows, int n_first, int col0, int ncol8) {
+    if (128 % ncol8 == 0) {
+      const int rstep = 128 / ncol8, c = (tid % ncol8) * 8;
+      for (int r = tid / ncol8; r < rows; r += rstep) {
+        const int n = n_first + r;
+        if (n < N) cp_async16(smem_u32(dst + r * pitch + c), qkv + prow(n) * 3 * C + col0 + c);
+        else *reinterpret_cast<uint4*>(dst + r * pitch + c) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    } else {
+      for (int i = tid; i < rows * ncol8; i += 128) {
+        const int r = i / ncol8, c = (i - r * ncol8) * 8, n = n_first + r;
+        if (n < N) cp_async16(smem_u32(dst + r * pitch + c), qkv + prow(n) * 3 * C + col0 + c);
+        else *reinterpret_cast<uint4*>(dst + r * pitch + c) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  };
+  load_rows(Qs, qp, S1A_Q, q0, 0, c8);
+#pragma unroll
+  for (int d = 0; d < S1A_NKB - 1; ++d) {                       // Q rides in the first group
+    if (d * S1A_KC < N) load_rows(KV + d * kbuf, qp, S1A_KC, d * S1A_KC, C, c8);
+    cp_async_commit();
+  }
+  float S[S1A_NMAX / 8][4];
+#pragma unroll
+  for (int i = 0; i < S1A_NMAX / 8; ++i) S[i][0] = S[i][1] = S[i][2] = S[i][3] = 0.f;
+  const uint32_t qs_u32 = smem_u32(Qs), kv_u32 = smem_u32(KV), ps_u32 = smem_u32(Ps);
+  // ldmatrix lane addressing: A (x4): row (l & 7) + ((l >> 3) & 1) * 8, col (l >> 4) * 8;  B (x2): row l & 7, col ((l >> 3) & 1) * 8
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;
+  const int b_row = lane & 7, b_col = ((lane >> 3) & 1) * 8;
+  // ---- phase 1: scores ----
+#pragma unroll
+  for (int kc = 0; kc < S1A_NMAX / S1A_KC; ++kc) {
+    if (kc * S1A_KC < N) {                                      // CTA-uniform
+      if ((kc + S1A_NKB - 1) * S1A_KC < N)
+        load_rows(KV + ((kc + S1A_NKB - 1) % S1A_NKB) * kbuf, qp, S1A_KC, (kc + S1A_NKB - 1) * S1A_KC, C, c8);
+      cp_async_commit();                                        // (possibly empty) group: uniform accounting
+      cp_async_wait<S1A_NKB - 1>();
+      __syncthreads();
+      const uint32_t kb_u32 = kv_u32 + static_cast<uint32_t>((kc % S1A_NKB) * kbuf * 2);
+      for (int ks = 0; ks < C / 16; ++ks) {
+        uint32_t a0, a1, a2, a3;
+        ldsm_x4(qs_u32 + static_cast<uint32_t>(((warp * 16 + a_row) * qp + ks * 16 + a_col) * 2), a0, a1, a2, a3);
+#pragma unroll
+        for (int nb = 0; nb < S1A_KC / 8; ++nb) {
+          uint32_t b0, b1;
+          ldmatrix_x2(kb_u32 + static_cast<uint32_t>(((nb * 8 + b_row) * qp + ks * 16 + b_col) * 2), b0, b1);
+          mma_bf16_16816(S[kc * (S1A_KC / 8) + nb], a0, a1, a2, a3, b0, b1);
+        }
+      }
+      __syncthreads();                                          // chunk consumed: its buffer may be refilled
+    }
+  }
+  // first V tiles in flight behind the softmax
+  const int nvc = (N + S1A_VC - 1) / S1A_VC, ntile = (C / S1A_CB) * nvc;
+  auto load_v = [&](int ti) {
+    const int cb1 = ti / nvc, vc1 = ti - cb1 * nvc;
+    load_rows(KV + (ti % S1A_NVB) * vbuf, vp, S1A_VC, vc1 * S1A_VC, 2 * C + cb1 * S1A_CB, S1A_CB / 8);
+  };
+#pragma unroll
+  for (int d = 0; d < S1A_NVB - 1; ++d) {
+    if (d < ntile) load_v(d);
+    cp_async_commit();
+  }
+  // ---- softmax over the keys (w_ = softmax(q k^T C^-1/2), layers.py:175-177); rows g and g + 8 of the warp's 16 ----
+  const float scale = rsqrtf(static_cast<float>(C));
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < S1A_NMAX / 8; ++i) {
+    const int col = i * 8 + 2 * t;
+    S[i][0] = col < N ? S[i][0] * scale : -INFINITY;
+    S[i][1] = col + 1 < N ? S[i][1] * scale : -INFINITY;
+    S[i][2] = col < N ? S[i][2] * scale : -INFINITY;
+    S[i][3] = col + 1 < N ? S[i][3] * scale : -INFINITY;
+    m0 = fmaxf(m0, fmaxf(S[i][0], S[i][1]));
+    m1 = fmaxf(m1, fmaxf(S[i][2], S[i][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < S1A_NMAX / 8; ++i) {
+    S[i][0] = expf(S[i][0] - m0); S[i][1] = expf(S[i][1] - m0);
+    S[i][2] = expf(S[i][2] - m1); S[i][3] = expf(S[i][3] - m1);
+    l0 += S[i][0] + S[i][1];
+    l1 += S[i][2] + S[i][3];
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+  for (int i = 0; i < S1A_NMAX / 8; ++i) {
+    const int col = i * 8 + 2 * t;
+    *reinterpret_cast<__nv_bfloat162*>(Ps + (warp * 16 + g) * pp + col) = __floats2bfloat162_rn(S[i][0] * i0, S[i][1] * i0);
+    *reinterpret_cast<__nv_bfloat162*>(Ps + (warp * 16 + g + 8) * pp + col) = __floats2bfloat162_rn(S[i][2] * i1, S[i][3] * i1);
+  }
+  // ---- phase 2: O = P V, one 128-channel block at a time, V tiles of 64 keys double-buffered ----
+  float O[S1A_CB / 8][4];
+  for (int ti = 0; ti < ntile; ++ti) {
+    const int cb = ti / nvc, vc = ti - cb * nvc;
+    if (ti + S1A_NVB - 1 < ntile) load_v(ti + S1A_NVB - 1);
+    cp_async_commit();
+    cp_async_wait<S1A_NVB - 1>();
+    __syncthreads();                                            // tile ti landed (and, first time, P written)
+    if (vc == 0) {
+#pragma unroll
+      for (int i = 0; i < S1A_CB / 8; ++i) O[i][0] = O[i][1] = O[i][2] = O[i][3] = 0.f;
+    }
+    const uint32_t vb_u32 = kv_u32 + static_cast<uint32_t>((ti % S1A_NVB) * vbuf * 2);
+#pragma unroll
+    for (int ks = 0; ks < S1A_VC / 16; ++ks) {
+      uint32_t a0, a1, a2, a3;
+      ldsm_x4(ps_u32 + static_cast<uint32_t>(((warp * 16 + a_row) * pp + vc * S1A_VC + ks * 16 + a_col) * 2), a0, a1, a2, a3);
+#pragma unroll
+      for (int nb = 0; nb < S1A_CB / 8; ++nb) {
+        uint32_t b0, b1;
+        // V tile is [key][channel]: the transposing load turns 8 keys x 8 channels into the [n][k] fragment
+        ldmatrix_x2_trans(vb_u32 + static_cast<uint32_t>(((ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * vp + nb * 8) * 2), b0, b1);
+        mma_bf16_16816(O[nb], a0, a1, a2, a3, b0, b1);
+      }
+    }
+    if (vc == nvc - 1) {
+      const int n0 = q0 + warp * 16 + g, n1 = n0 + 8;
+#pragma unroll
+      for (int nb = 0; nb < S1A_CB / 8; ++nb) {
+        const int col = cb * S1A_CB + nb * 8 + 2 * t;
+        if (n0 < N) *reinterpret_cast<__nv_bfloat162*>(out + prow(n0) * C + col) = __floats2bfloat162_rn(O[nb][0], O[nb][1]);
+        if (n1 < N) *reinterpret_cast<__nv_bfloat162*>(out + prow(n1) * C + col) = __floats2bfloat162_rn(O[nb][2], O[nb][3]);
+      }
+    }
+    __syncthreads();                                            // tile consumed
+  }
+#endif
 }
 
 // conv weight [Cout, Cin, k, k] (fp32 / bf16 / fp16 source already converted to fp32) -> bf16 [CoutPad, k*k*Cin] tap-major

@@ -40,7 +40,9 @@ struct hq_s1_ctx {
   std::map<std::string, S1Slot> params;
   float *X = nullptr, *T = nullptr, *S = nullptr;
   bf16 *H = nullptr, *H2 = nullptr, *QKV = nullptr;
-  double* gn_part = nullptr;
+  double* gn_part = nullptr;      // [B][32 groups][<= 64 row slices][sum, sum of squares]
+  float2* gn_stat = nullptr;      // [B][32] (mean, rstd) published by the last slice CTA
+  unsigned* gn_cnt = nullptr;     // [B] ticket counters (wrap to 0)
   size_t act_elems = 0;                 // elements of X / T / S / H / H2 per buffer
   size_t device_bytes = 0;
   std::vector<void*> allocs;
@@ -167,6 +169,7 @@ static int s1_create_impl(hq_s1_ctx* ctx, const hq_s1_config* cfg, int device, i
   S1_CUDA(ctx, cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
   S1_CUDA(ctx, cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES));
   S1_CUDA(ctx, cudaFuncSetAttribute(s1_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  S1_CUDA(ctx, cudaFuncSetAttribute(s1_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int L = cfg->n_levels, E = cfg->embed_dim;
   if (L < 1 || L > 8 || max_batch < 1 || cfg->resolution % (1 << L) != 0 || E % 64 != 0 || cfg->out_ch < 1 || cfg->out_ch > 32) {
     s1_err(ctx, "unsupported stage-1 configuration");
@@ -224,6 +227,8 @@ static int s1_create_impl(hq_s1_ctx* ctx, const hq_s1_config* cfg, int device, i
   if ((rc = s1_alloc(ctx, reinterpret_cast<void**>(&ctx->QKV),
                      static_cast<size_t>(max_batch) * (att_res + 2) * (att_res + 2) * 3 * top * 2))) return rc;
   if ((rc = s1_alloc(ctx, reinterpret_cast<void**>(&ctx->gn_part), static_cast<size_t>(max_batch) * 32 * 64 * 2 * 8))) return rc;
+  if ((rc = s1_alloc(ctx, reinterpret_cast<void**>(&ctx->gn_stat), static_cast<size_t>(max_batch) * 32 * 8))) return rc;
+  if ((rc = s1_alloc(ctx, reinterpret_cast<void**>(&ctx->gn_cnt), static_cast<size_t>(max_batch) * 4))) return rc;
   return HQ_OK;
 }
 
@@ -365,8 +370,8 @@ static void s1_conv(hq_s1_ctx* ctx, cudaStream_t st, const S1Conv& c, const bf16
 static void s1_gn(hq_s1_ctx* ctx, cudaStream_t st, const S1Norm& n, const float* x, bf16* out, int B, int res, int swish) {
   const int Hp = res + 2;
   const int S = res < 64 ? res : 64;
-  s1_gn_stats_kernel<<<dim3(S, B), 256, 0, st>>>(x, ctx->gn_part, Hp, Hp, n.C, S);
-  s1_gn_apply_kernel<<<dim3(Hp, B), 256, 0, st>>>(x, ctx->gn_part, n.g, n.b, out, Hp, Hp, n.C, S, swish);
+  s1_gn_stats_kernel<<<dim3(S, B), 256, 0, st>>>(x, ctx->gn_part, ctx->gn_stat, ctx->gn_cnt, Hp, Hp, n.C, S);
+  s1_gn_apply_kernel<<<dim3(Hp, B), 256, 0, st>>>(x, ctx->gn_stat, n.g, n.b, out, Hp, Hp, n.C, swish);
   s1_check(ctx);
 }
 
@@ -396,8 +401,15 @@ static void s1_attnblock(hq_s1_ctx* ctx, cudaStream_t st, const S1Attn& a, int B
   s1_gn(ctx, st, a.n, ctx->X, ctx->H, B, res, 0);
   s1_conv(ctx, st, a.qkv, ctx->H, B, res, S1_OUT_BF16, nullptr, ctx->QKV, nullptr);
   const int N = res * res;
-  const size_t smem = static_cast<size_t>(S1_ATT_Q) * (C + N) * 4;
-  s1_attn_kernel<<<dim3((N + S1_ATT_Q - 1) / S1_ATT_Q, B), 256, smem, st>>>(ctx->QKV, ctx->H2, res, res, C);
+  static const bool no_mma = getenv("HQ_DEBUG") != nullptr && getenv("HQ_S1_ATTN_SIMT") != nullptr;
+  if (!no_mma && N % 16 == 0 && N <= S1A_NMAX && C % S1A_CB == 0 && C <= S1A_CMAX) {
+    // tensor-core path: 64 queries per CTA
+    const size_t smem = static_cast<size_t>(s1a_smem_bytes(C));
+    s1_attn_mma_kernel<<<dim3((N + S1A_Q - 1) / S1A_Q, B), 128, smem, st>>>(ctx->QKV, ctx->H2, res, res, C);
+  } else {
+    const size_t smem = static_cast<size_t>(S1_ATT_Q) * (C + N) * 4;
+    s1_attn_kernel<<<dim3((N + S1_ATT_Q - 1) / S1_ATT_Q, B), 256, smem, st>>>(ctx->QKV, ctx->H2, res, res, C);
+  }
   s1_check(ctx);
   s1_conv(ctx, st, a.proj, ctx->H2, B, res, S1_OUT_F32, ctx->X, nullptr, ctx->X);
 }
