@@ -6,7 +6,7 @@ import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libhqgraft.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 HQ_OK = 0
 HQ_COND_CLS, HQ_COND_TXT, HQ_COND_UNCOND = 0, 1, 2
@@ -21,7 +21,7 @@ class HQConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "embed_dim", "n_heads", "n_layers", "n_layers_depth", "vocab_top", "vocab_bot", "vocab_txt", "n_classes",
         "ctx_len_img", "ctx_len_txt", "cond_kind", "precision", "max_seq_len", "use_cuda_graph", "use_pdl", "use_chain", "model_type", "embedding_kind",
-        "position_kind", "code_levels", "vocab_mid")]
+        "position_kind", "code_levels", "vocab_mid", "fuse_head_sampler")]
 
 
 class HQSamplingParams(C.Structure):

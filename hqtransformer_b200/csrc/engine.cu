@@ -173,6 +173,7 @@ struct hq_ctx {
   ABuf h, att, mlp;
   void* q = nullptr;
   float *x = nullptr, *yd = nullptr, *logits = nullptr;
+  float2* samp_part = nullptr;     // fused head + sampler: [depth_rows * B, Vmax / 32] (log-sum-exp, drawn index) per 32-column chunk
   float* splitk_ws = nullptr;   // [LN_MAXFOLD][rows][D] fp32 partial sums of split-K fc2 GEMMs (folded in by the next LayerNorm)
   unsigned int* att_sched = nullptr;   // [2] work-ticket / finished-CTA counters of attention_decode_mma_kernel (rest at 0)
   CUtensorMap kmap, vmap;              // spatial KV cache as [rows = L*B*Tc][heads][64] bf16, box {64, hpc, 8}, SWIZZLE_128B
@@ -367,12 +368,12 @@ static int set_gemm_attrs(hq_ctx* ctx) {
   int rc;
 #define HQ_SET(BN, EPI) \
   if ((rc = set_smem(ctx, gemm_tc_kernel<BN, EPI, bf16>, TcCfg<BN>::SMEM_BYTES))) return rc;
-  HQ_SET(64, EPI_QKV) HQ_SET(64, EPI_RESID) HQ_SET(64, EPI_GELU) HQ_SET(64, EPI_F32)
-  HQ_SET(128, EPI_QKV) HQ_SET(128, EPI_RESID) HQ_SET(128, EPI_GELU) HQ_SET(128, EPI_F32)
+  HQ_SET(64, EPI_QKV) HQ_SET(64, EPI_RESID) HQ_SET(64, EPI_GELU) HQ_SET(64, EPI_F32) HQ_SET(64, EPI_SAMPLE)
+  HQ_SET(128, EPI_QKV) HQ_SET(128, EPI_RESID) HQ_SET(128, EPI_GELU) HQ_SET(128, EPI_F32) HQ_SET(128, EPI_SAMPLE)
 #undef HQ_SET
 #define HQ_SET2(BN, EPI) \
   if ((rc = set_smem(ctx, gemm_tc2_kernel<BN, EPI, bf16>, Tc2Cfg<BN>::SMEM_BYTES))) return rc;
-#define HQ_SET2_ALL(BN) HQ_SET2(BN, EPI_QKV) HQ_SET2(BN, EPI_RESID) HQ_SET2(BN, EPI_GELU) HQ_SET2(BN, EPI_F32)
+#define HQ_SET2_ALL(BN) HQ_SET2(BN, EPI_QKV) HQ_SET2(BN, EPI_RESID) HQ_SET2(BN, EPI_GELU) HQ_SET2(BN, EPI_F32) HQ_SET2(BN, EPI_SAMPLE)
   HQ_SET2_ALL(32) HQ_SET2_ALL(64) HQ_SET2_ALL(96) HQ_SET2_ALL(128) HQ_SET2_ALL(192) HQ_SET2_ALL(256)
 #undef HQ_SET2_ALL
 #undef HQ_SET2
@@ -462,7 +463,7 @@ static int reserve_impl(hq_ctx* ctx, int max_batch) {
     ctx->ws_rows = 0;
     ctx->kv_maps = false;
     ctx->h = ABuf(); ctx->att = ABuf(); ctx->mlp = ABuf();
-    ctx->q = nullptr; ctx->x = nullptr; ctx->yd = nullptr; ctx->logits = nullptr; ctx->splitk_ws = nullptr;
+    ctx->q = nullptr; ctx->x = nullptr; ctx->yd = nullptr; ctx->logits = nullptr; ctx->samp_part = nullptr; ctx->splitk_ws = nullptr;
     ctx->kc = ctx->vc = ctx->kd = ctx->vd = nullptr;
     ctx->cond = ctx->codes_top = ctx->codes_bot = ctx->codes_mid = nullptr;
     ctx->sos_override = nullptr;
@@ -496,6 +497,11 @@ static int reserve_alloc(hq_ctx* ctx, int max_batch) {
   if ((rc = alloc_f32(ctx, &ctx->x, static_cast<size_t>(Mx) * D))) return rc;
   if ((rc = alloc_f32(ctx, &ctx->yd, static_cast<size_t>(ctx->depth_rows) * B * D))) return rc;
   if ((rc = alloc_f32(ctx, &ctx->logits, static_cast<size_t>(ctx->depth_rows < 4 ? 4 : ctx->depth_rows) * B * ctx->Vmax))) return rc;
+  {
+    float* sp2 = nullptr;
+    if ((rc = alloc_f32(ctx, &sp2, static_cast<size_t>(ctx->depth_rows < 4 ? 4 : ctx->depth_rows) * B * ((ctx->Vmax + 31) / 32) * 2))) return rc;
+    ctx->samp_part = reinterpret_cast<float2*>(sp2);
+  }
   ctx->ws_rows = Mmax;
   if (ctx->bf16 && (rc = alloc_f32(ctx, &ctx->splitk_ws, static_cast<size_t>(LN_MAXFOLD) * Mmax * D))) return rc;
   const size_t kvn = static_cast<size_t>(ctx->L) * B * ctx->Tc * D * ctx->wsize;
@@ -1392,8 +1398,38 @@ static void run_block(hq_ctx* ctx, cudaStream_t st, const BlockW& w, float* x, i
 struct RunFlags {
   int forced_top, forced_bot, sos_override, forced_mid;
   int shared_prefix;    // text models: every row has the same prompt - prefill image 0 only, broadcast its cache rows
+  int fuse_mask;        // bit filt_sel (0 top, 1 bottom, 2 middle): that filter pair is (None, None) -> head GEMM draws in its epilogue
   float* logits_out;
 };
+
+// Head GEMM of the draw described by `sa` (hierarchical_ar.py:695 / 715).  When the draw has no top-k / top-p cut (the
+// measure_throughput protocol) the bf16 engine samples inside the GEMM epilogue (gemm.cuh: EPI_SAMPLE) and the [rows, V]
+// logits are never written; otherwise the logits go to ctx->logits for sample_kernel.  Returns whether it fused.
+template <typename AT>
+static bool head_gemm(hq_ctx* ctx, cudaStream_t st, const Weight& w, int rows, int V, const SampleArgs& sa, const RunFlags& f) {
+  const bool fuse = sizeof(AT) == 2 && !ctx->recording && ((f.fuse_mask >> sa.filt_sel) & 1) && !sa.forced &&
+                    sa.logits_out == nullptr && V % 32 == 0;
+  EpiParams<AT> e;
+  memset(&e, 0, sizeof(e));
+  if (fuse) {
+    e.sp = sa.sp; e.samp_part = ctx->samp_part; e.temp_sel = sa.temp_sel; e.rows_per_b = sa.rows_per_b; e.slot0 = sa.slot0;
+    e.pos = sa.pos;
+    ctx->gemm_tag_override = "gemm_head_sample";
+    gemm_any<EPI_SAMPLE>(ctx, st, ctx->h, w, 0, rows, V, ctx->D, e);
+  } else {
+    e.outf = ctx->logits; e.ldo = ctx->Vmax;
+    gemm_any<EPI_F32>(ctx, st, ctx->h, w, 0, rows, V, ctx->D, e);
+  }
+  return fuse;
+}
+
+static void draw(hq_ctx* ctx, cudaStream_t st, const SampleArgs& sa, bool fused) {
+  if (fused)
+    launch_k(ctx, st, "sample_finalize", sample_finalize_kernel, dim3((sa.R + SMPF_WARPS - 1) / SMPF_WARPS), dim3(SMPF_WARPS * 32),
+             0, sa, static_cast<const float2*>(ctx->samp_part), sa.V / 32);
+  else if (!(sa.forced && sa.logits_out == nullptr))
+    launch_sample(ctx, st, sa);
+}
 
 // One top position: spatial step, depth pass 0, draw top, depth pass 1, draw 4 bottoms.
 template <typename AT>
@@ -1469,13 +1505,6 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
   sa.sp = ctx->d_sp; sa.pos = pos; sa.S = S; sa.dst_codes = ctx->codes_top; sa.dst_w = 1; sa.n_slots = ctx->n_stack;
   sa.forced = f.forced_top; sa.logits_out = f.logits_out; sa.Vmax = ctx->Vmax;
   sa.temp_sel = 0; sa.filt_sel = 0; sa.bot_slot = -1;
-  auto head = [&](const Weight& w, int rows, int V) {
-    EpiParams<AT> e;
-    memset(&e, 0, sizeof(e));
-    e.outf = ctx->logits; e.ldo = ctx->Vmax;
-    gemm_any<EPI_F32>(ctx, st, ctx->h, w, 0, rows, V, D, e);
-  };
-
   if (ctx->cfg.model_type == HQ_MODEL_TOP2BOT) {
     // ---- 'top2bot' (sampling_depth_baseline, hierarchical_ar.py:565-664): five sequential single-token passes over the
     //      depth blocks with a growing cache [Ld][B][5][D]; pass c writes slot c and attends over slots 0..c ----
@@ -1489,12 +1518,11 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
       for (int l = 0; l < ctx->Ld; ++l)
         run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, B, 0, kd + l * dstride, vd + l * dstride, 1, 5, c, c + 1, 0, &fold_y);
       layernorm_act<AT>(ctx, st, ctx->yd, c == 0 ? ctx->lnt_g : ctx->lnb_g, c == 0 ? ctx->lnt_b : ctx->lnb_b, h, B, &fold_y);
-      head(c == 0 ? ctx->head_top : ctx->head_bot, B, c == 0 ? ctx->Vt : ctx->Vb);
       sa.V = c == 0 ? ctx->Vt : ctx->Vb; sa.slot0 = c; sa.bot_slot = c - 1;
       sa.dst_codes = c == 0 ? ctx->codes_top : ctx->codes_bot; sa.dst_w = c == 0 ? 1 : 4;
       sa.temp_sel = sa.filt_sel = c == 0 ? 0 : 1;
       sa.forced = c == 0 ? f.forced_top : f.forced_bot;
-      if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+      draw(ctx, st, sa, head_gemm<AT>(ctx, st, c == 0 ? ctx->head_top : ctx->head_bot, B, sa.V, sa, f));
     }
     return;
   }
@@ -1506,15 +1534,13 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
     for (int l = 0; l < ctx->Ld; ++l)
       run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, 5 * B, 2, kd + l * dstride, vd + l * dstride, 5, 5, 0, 5, 0, &fold_y);
     layernorm_rows<AT>(ctx, st, "layernorm", ctx->yd, ctx->lnt_g, ctx->lnt_b, nullptr, h, B, 1, 5, 0, 1, fold_y);
-    head(ctx->head_top, B, ctx->Vt);
     sa.temp_sel = 0; sa.filt_sel = 1;
-    if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+    draw(ctx, st, sa, head_gemm<AT>(ctx, st, ctx->head_top, B, ctx->Vt, sa, f));
     layernorm_rows<AT>(ctx, st, "layernorm", ctx->yd, ctx->lnb_g, ctx->lnb_b, nullptr, h, 4 * B, 4, 5, 1, 1, fold_y);
     fold_y = Fold();
-    head(ctx->head_bot, 4 * B, ctx->Vb);
     sa.V = ctx->Vb; sa.R = 4 * B; sa.rows_per_b = 4; sa.slot0 = 1; sa.forced = f.forced_bot;
     sa.dst_codes = ctx->codes_bot; sa.dst_w = 4;
-    if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+    draw(ctx, st, sa, head_gemm<AT>(ctx, st, ctx->head_bot, 4 * B, ctx->Vb, sa, f));
     return;
   }
 
@@ -1523,13 +1549,10 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
     run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, B, 1, kd + l * dstride, vd + l * dstride, 1, 5, 0, 1, 0, &fold_y);
   layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnt_g, ctx->lnt_b, h, B, &fold_y);
   {
-    EpiParams<AT> e;
-    memset(&e, 0, sizeof(e));
-    e.outf = ctx->logits; e.ldo = ctx->Vmax;
-    gemm_any<EPI_F32>(ctx, st, ctx->h, ctx->head_top, 0, B, ctx->Vt, D, e);
+    const bool fused = head_gemm<AT>(ctx, st, ctx->head_top, B, ctx->Vt, sa, f);
+    if (chain) chain_end(ctx, st);
+    draw(ctx, st, sa, fused);
   }
-  if (chain) chain_end(ctx, st);
-  if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
 
   // ---- depth pass 1 -> 4 bottom logits ----
   if (chain) {
@@ -1543,16 +1566,13 @@ static void run_position(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, co
   for (int l = 0; l < ctx->Ld; ++l)
     run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, 4 * B, 2, kd + l * dstride, vd + l * dstride, 4, 5, 1, 5, 0, &fold_y);
   layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnb_g, ctx->lnb_b, h, 4 * B, &fold_y);
-  {
-    EpiParams<AT> e;
-    memset(&e, 0, sizeof(e));
-    e.outf = ctx->logits; e.ldo = ctx->Vmax;
-    gemm_any<EPI_F32>(ctx, st, ctx->h, ctx->head_bot, 0, 4 * B, ctx->Vb, D, e);
-  }
   sa.V = ctx->Vb; sa.R = 4 * B; sa.rows_per_b = 4; sa.slot0 = 1; sa.forced = f.forced_bot;
   sa.temp_sel = 1; sa.filt_sel = 1; sa.dst_codes = ctx->codes_bot; sa.dst_w = 4;
-  if (chain) chain_end(ctx, st);
-  if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+  {
+    const bool fused = head_gemm<AT>(ctx, st, ctx->head_bot, 4 * B, ctx->Vb, sa, f);
+    if (chain) chain_end(ctx, st);
+    draw(ctx, st, sa, fused);
+  }
 }
 
 // One top position of the 3-level HQTransformer, decoding_type 'parallel-add' (hqtransformer.py:409-635):
@@ -1590,40 +1610,31 @@ static void run_position3(hq_ctx* ctx, cudaStream_t st, int B, int S, int pos, c
   memset(&sa, 0, sizeof(sa));
   sa.logits = ctx->logits; sa.ldl = ctx->Vmax; sa.sp = ctx->d_sp; sa.pos = pos; sa.S = S; sa.n_slots = 21;
   sa.logits_out = f.logits_out; sa.Vmax = ctx->Vmax; sa.bot_slot = -1;
-  auto head = [&](const Weight& w, int rows, int V) {
-    EpiParams<AT> e;
-    memset(&e, 0, sizeof(e));
-    e.outf = ctx->logits; e.ldo = ctx->Vmax;
-    gemm_any<EPI_F32>(ctx, st, ctx->h, w, 0, rows, V, D, e);
-  };
   // ---- pass 0: top code (k, v only: softmax over one key is the identity) ----
   for (int l = 0; l < ctx->Ld; ++l)
     run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, B, 1, kd + l * dstride, vd + l * dstride, 1, 21, 0, 1, 0, &fold_y);
   layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnt_g, ctx->lnt_b, h, B, &fold_y);
-  head(ctx->head_top, B, ctx->Vt);
   sa.V = ctx->Vt; sa.R = B; sa.rows_per_b = 1; sa.slot0 = 0; sa.temp_sel = sa.filt_sel = 0;
   sa.dst_codes = ctx->codes_top; sa.dst_w = 1; sa.forced = f.forced_top;
-  if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+  draw(ctx, st, sa, head_gemm<AT>(ctx, st, ctx->head_top, B, ctx->Vt, sa, f));
   // ---- pass 1: four middle codes; y_j = E0_depth[c_top] + P1[j]; queries see slots 0..4 ----
   launch_k(ctx, st, "embed_depth", embed_depth_kernel, dim3(B), dim3(eb), 0, ctx->yd, ctx->E_top_depth, ctx->P_depth,
            ctx->codes_top, S, pos, D);
   for (int l = 0; l < ctx->Ld; ++l)
     run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, 4 * B, 2, kd + l * dstride, vd + l * dstride, 4, 21, 1, 5, 0, &fold_y);
   layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnm_g, ctx->lnm_b, h, 4 * B, &fold_y);
-  head(ctx->head_mid, 4 * B, ctx->Vm);
   sa.V = ctx->Vm; sa.R = 4 * B; sa.rows_per_b = 4; sa.slot0 = 1; sa.temp_sel = sa.filt_sel = 2;
   sa.dst_codes = ctx->codes_mid; sa.dst_w = 4; sa.forced = f.forced_mid;
-  if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+  draw(ctx, st, sa, head_gemm<AT>(ctx, st, ctx->head_mid, 4 * B, ctx->Vm, sa, f));
   // ---- pass 2: sixteen bottom codes (raster of the 4x4 cell); queries see slots 0..20 ----
   launch_k(ctx, st, "embed_depth2", embed_depth2_kernel, dim3(B), dim3(eb), 0, ctx->yd, ctx->E_mid_depth, ctx->E_top_depth,
            ctx->P_depth2, ctx->codes_top, ctx->codes_mid, S, pos, D);
   for (int l = 0; l < ctx->Ld; ++l)
     run_block<AT>(ctx, st, ctx->depths[l], ctx->yd, 16 * B, 2, kd + l * dstride, vd + l * dstride, 16, 21, 5, 21, 0, &fold_y);
   layernorm_act<AT>(ctx, st, ctx->yd, ctx->lnb_g, ctx->lnb_b, h, 16 * B, &fold_y);
-  head(ctx->head_bot, 16 * B, ctx->Vb);
   sa.V = ctx->Vb; sa.R = 16 * B; sa.rows_per_b = 16; sa.slot0 = 5; sa.temp_sel = sa.filt_sel = 1;
   sa.dst_codes = ctx->codes_bot; sa.dst_w = 16; sa.forced = f.forced_bot;
-  if (!(sa.forced && sa.logits_out == nullptr)) launch_sample(ctx, st, sa);
+  draw(ctx, st, sa, head_gemm<AT>(ctx, st, ctx->head_bot, 16 * B, ctx->Vb, sa, f));
 }
 
 static void run_range(hq_ctx* ctx, cudaStream_t st, int B, int S, int p0, int p1, const RunFlags& f) {
@@ -1699,6 +1710,14 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
   f.shared_prefix = a->shared_prefix != 0 && ctx->cfg.cond_kind == HQ_COND_TXT && a->sos == nullptr &&
                     ctx->cfg.model_type != HQ_MODEL_BIDIRECTIONAL;
   f.sos_override = a->sos != nullptr;
+  f.fuse_mask = 0;
+  if (ctx->cfg.fuse_head_sampler && ctx->bf16) {
+    const hq_sampling_params& q = a->sampling;
+    auto none = [](int k, float p2, int V) { return (k <= 0 || k >= V) && !(p2 > 0.f && p2 < 1.f); };
+    if (none(q.top_k_top, q.top_p_top, ctx->Vt)) f.fuse_mask |= 1;
+    if (none(q.top_k_bot, q.top_p_bot, ctx->Vb)) f.fuse_mask |= 2;
+    if (ctx->levels == 3 && none(q.top_k_mid, q.top_p_mid, ctx->Vm)) f.fuse_mask |= 4;
+  }
   f.logits_out = nullptr;
   float* dev_logits = nullptr;
   const size_t nlog = static_cast<size_t>(B) * S * ctx->n_stack * ctx->Vmax * 4;
@@ -1748,7 +1767,7 @@ static int run_impl(hq_ctx* ctx, const hq_run_args* a, cudaStream_t st, cudaMemc
     ctx->launches = 0;
   };
   if (use_graph) {
-    GraphKey key{B, S, a->pos_begin, a->pos_end, f.forced_top, f.forced_bot | (f.forced_mid << 1) | (f.shared_prefix << 2), f.sos_override,
+    GraphKey key{B, S, a->pos_begin, a->pos_end, f.forced_top, f.forced_bot | (f.forced_mid << 1) | (f.shared_prefix << 2) | (f.fuse_mask << 3), f.sos_override,
                  ctx->tracing ? 1 : 0};
     auto it = ctx->graphs.find(key);
     if (it == ctx->graphs.end()) {

@@ -11,13 +11,16 @@
 //   EPI_RESID  x += acc + bias                (layers.py:190 + :326/:327 residual adds)
 //   EPI_GELU   out = gelu_erf(acc + bias)     (layers.py:312-314)
 //   EPI_F32    out = acc                      (head_top / head_bot, hierarchical_ar.py:695, 715)
+//   EPI_SAMPLE head + Sample(z; T, None, None) (hierarchical_ar.py:695 / 715 + 762-785 with no top-k / top-p cut): the
+//              [rows, V] logits never leave the SM - see epilogue_sample_tile
 #pragma once
 
 #include "common.cuh"
+#include "../../include/hqgraft.h"
 
 namespace hq {
 
-enum { EPI_QKV = 0, EPI_RESID = 1, EPI_GELU = 2, EPI_F32 = 3 };
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_GELU = 2, EPI_F32 = 3, EPI_SAMPLE = 4 };
 
 template <typename AT>
 struct EpiParams {
@@ -36,6 +39,10 @@ struct EpiParams {
   float* outf;        // [M, ldo]; split-K: slice blockIdx.z of the K range writes outf + blockIdx.z * split_stride
   int ldo;
   size_t split_stride;
+  // EPI_SAMPLE
+  const hq_sampling_params* sp;   // device copy (temperature, seed, row offset)
+  float2* samp_part;              // [M, N / 32]: per 32-column chunk (log-sum-exp, index drawn inside the chunk as int bits)
+  int temp_sel, rows_per_b, slot0, pos;
 };
 
 
@@ -206,6 +213,77 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, uint8_t* slab_
 #endif
 
 // ------------------------------------------------------------------------------------------------
+// EPI_SAMPLE: the categorical draw of Sample(z; T, None, None) without materialising the logits.  Exact two-stage sampling
+// over 32-column chunks (one tcgen05.ld: thread = row, 32 consecutive logits in registers):
+//   stage 1 (here): chunk c of row m -> L_c = log sum_j exp(z_j / T) and ONE index drawn inside the chunk from
+//                   softmax(z_chunk / T) by inverse CDF with its own Philox uniform;
+//   stage 2 (sample_finalize_kernel): chunk drawn from softmax(L) with one more uniform; the code is that chunk's index.
+// P(i) = P(chunk) P(i | chunk) = exp(z_i / T) / sum exp(z / T).  Every (row, chunk) result depends only on that chunk's 32
+// accumulators and on a Philox counter made of (global row, position, slot, chunk): independent of the tile shape, of the
+// kernel (pair / single-CTA) and of how the batch is sharded over GPUs.
+// Philox counters: (row, row >> 32, pos | (chunk / 4 + 1) << 16, slot | 0x200) -> uniform [chunk % 4] for stage 1,
+//                  (row, row >> 32, pos, slot | 0x100) -> [0] for stage 2; the unfused sampler uses (row, ., pos, slot).
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+template <int BN, typename AT, int NW>
+__device__ __forceinline__ void epilogue_sample_tile(uint32_t tmem_base, int warp, int lane, int m0, int n0, int M, int N,
+                                                     const EpiParams<AT>& ep, uint64_t* tmem_full_bar, uint32_t full_parity,
+                                                     int ew) {
+  const int quarter = warp & 3;
+  if (ew < 0) ew = quarter;
+  const int half = ew >> 2;
+  const int m = m0 + quarter * 32 + lane;
+  const hq_sampling_params* sp = ep.sp;
+  const float temperature = ep.temp_sel == 0 ? sp->temperature_top : (ep.temp_sel == 1 ? sp->temperature_bot : sp->temperature_mid);
+  const float inv_t = 1.0f / temperature;
+  const uint64_t seed = sp->seed;
+  const int b = m / ep.rows_per_b;
+  const uint32_t slot = static_cast<uint32_t>(ep.slot0 + (m - b * ep.rows_per_b)) | 0x200u;
+  const uint64_t grow = sp->row_offset + static_cast<uint64_t>(b);
+  const int n_chunks = N >> 5;
+  mbar_wait(tmem_full_bar, full_parity);
+  tc_fence_after();
+  uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+  int rnd_grp = -1;
+#pragma unroll 1
+  for (int c = (NW == 8 ? half : 0); c < BN / 32; c += (NW == 8 ? 2 : 1)) {
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c * 32), r);
+    const int gc = (n0 >> 5) + c;                               // chunk index within the row
+    if ((gc >> 2) != rnd_grp) {
+      rnd_grp = gc >> 2;
+      philox4x32_10(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(grow),
+                    static_cast<uint32_t>(grow >> 32), static_cast<uint32_t>(ep.pos) | (static_cast<uint32_t>(rnd_grp + 1) << 16),
+                    slot, rnd);
+    }
+    const int sel = gc & 3;
+    const float u = u01_from_bits(sel == 0 ? rnd[0] : (sel == 1 ? rnd[1] : (sel == 2 ? rnd[2] : rnd[3])));
+    tmem_ld_wait();
+    float cm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float z = __uint_as_float(r[j]) * inv_t;
+      r[j] = __float_as_uint(z);
+      cm = fmaxf(cm, z);
+    }
+    float run = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {                              // r[j] <- inclusive prefix of exp(z - max), index order
+      run += __expf(__uint_as_float(r[j]) - cm);
+      r[j] = __float_as_uint(run);
+    }
+    const float target = u * run;
+    int idx = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) idx += (__uint_as_float(r[j]) <= target) ? 1 : 0;   // first j whose prefix exceeds the target
+    idx = idx > 31 ? 31 : idx;
+    if (m < M)
+      ep.samp_part[static_cast<size_t>(m) * n_chunks + gc] = make_float2(cm + logf(run), __int_as_float(n0 + c * 32 + idx));
+  }
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // tcgen05 / TMA GEMM.  One CTA computes a 128 x BN tile; grid = (ceil(N/BN), ceil(M/128)).
 //   warp 0: TMA producer (one lane)      warp 1: tcgen05.mma issuer (one lane)
 //   warps 2-5: epilogue (TMEM lane quarter = warp % 4); warp 2 also owns the TMEM allocation
@@ -316,7 +394,8 @@ gemm_tc_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __gr
   } else {
     // ---- epilogue: TMEM -> registers -> warp-private smem slab -> coalesced global ----
     pdl_wait();
-    epilogue_tile<BN, EPI, AT>(tmem_base, sA, sbias, warp, lane, m0, n0, M, N, ep, tmem_full_bar);
+    if (EPI == EPI_SAMPLE) epilogue_sample_tile<BN, AT, 4>(tmem_base, warp, lane, m0, n0, M, N, ep, tmem_full_bar, 0, -1);
+    else epilogue_tile<BN, EPI, AT>(tmem_base, sA, sbias, warp, lane, m0, n0, M, N, ep, tmem_full_bar);
     tc_fence_before();
   }
   __syncthreads();
@@ -497,9 +576,13 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
       const int n0 = (rem % nt) * BN;
       EpiParams<AT> ept = ep;
       if (EPI == EPI_F32) ept.outf = ep.outf + static_cast<size_t>(z) * ep.split_stride;
-      epilogue_tile<BN, EPI, AT, C::EPI_WARPS>(tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS), slab, sbias, warp, lane, m0,
-                                               n0, M, N, ept, &tmem_full_bar[buf], (it >> 1) & 1,
-                                               (warp & 3) + ((warp - 2) >> 2) * 4);
+      if (EPI == EPI_SAMPLE)
+        epilogue_sample_tile<BN, AT, C::EPI_WARPS>(tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS), warp, lane, m0, n0, M, N,
+                                                   ept, &tmem_full_bar[buf], (it >> 1) & 1, (warp & 3) + ((warp - 2) >> 2) * 4);
+      else
+        epilogue_tile<BN, EPI, AT, C::EPI_WARPS>(tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS), slab, sbias, warp, lane, m0,
+                                                 n0, M, N, ept, &tmem_full_bar[buf], (it >> 1) & 1,
+                                                 (warp & 3) + ((warp - 2) >> 2) * 4);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[buf], 0);   // this warp is done with the accumulator

@@ -1395,4 +1395,55 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 4 : 1) sample_kernel(int t
   if (tid == 0) *dst = cand;
 }
 
+// Stage 2 of the fused head + sampler (gemm.cuh: epilogue_sample_tile): one warp per logits row draws the 32-column chunk
+// from softmax(L_chunk) by inverse CDF in chunk order and emits that chunk's pre-drawn index.  `part`: [R, n_chunks]
+// (log-sum-exp, index bits).  Destination logic as in sample_kernel.
+constexpr int SMPF_WARPS = 8;
+__global__ void __launch_bounds__(SMPF_WARPS * 32) sample_finalize_kernel(int trace_id, SampleArgs a, const float2* __restrict__ part,
+                                                                          int n_chunks) {
+  TraceScope trace_scope(trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * SMPF_WARPS + (threadIdx.x >> 5);
+  if (r >= a.R) return;
+  const int b = r / a.rows_per_b, jj = r % a.rows_per_b;
+  const int slot = a.slot0 + jj;
+  const float2* p = part + static_cast<size_t>(r) * n_chunks;
+  const int per = (n_chunks + 31) / 32;                         // contiguous chunks per lane: prefix order == index order
+  const int c0 = lane * per, c1 = min(n_chunks, c0 + per);
+  float mx = -INFINITY;
+  for (int c = c0; c < c1; ++c) mx = fmaxf(mx, p[c].x);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float local = 0.f;
+  for (int c = c0; c < c1; ++c) local += expf(p[c].x - mx);
+  float incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  const float total = __shfl_sync(0xffffffffu, incl, 31);
+  const uint64_t seed = a.sp->seed, grow = a.sp->row_offset + static_cast<uint64_t>(b);
+  uint32_t rnd[4];
+  philox4x32_10(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(grow),
+                static_cast<uint32_t>(grow >> 32), static_cast<uint32_t>(a.pos), static_cast<uint32_t>(slot) | 0x100u, rnd);
+  const float target = u01_from_bits(rnd[0]) * total;
+  int cand = -1;
+  float run = incl - local;
+  for (int c = c0; c < c1; ++c) {
+    const float w = expf(p[c].x - mx);
+    if (w > 0.f && run <= target) cand = c;
+    run += w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cand = max(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+  if (lane == 0) {
+    int64_t* dst = a.dst_codes + (static_cast<size_t>(b) * a.S + a.pos) * a.dst_w +
+                   (a.rows_per_b == 1 ? (a.bot_slot < 0 ? 0 : a.bot_slot) : jj);
+    *dst = static_cast<int64_t>(__float_as_int(p[cand < 0 ? 0 : cand].y));
+  }
+}
+
 }  // namespace hq

@@ -62,7 +62,7 @@ class Engine:
                  max_batch: int = 16, device: Union[int, str, torch.device] = 0, use_cuda_graph: bool = True,
                  use_pdl: bool = True, use_chain: bool = False, model_type: str = "parallel",
                  embedding_type: str = "transformer1", position_embedding: str = "1d", code_levels: int = 2,
-                 vocab_mid: int = 0):
+                 vocab_mid: int = 0, fuse_head_sampler: bool = True):
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
         dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
@@ -81,7 +81,8 @@ class Engine:
                        max_seq_len=max_seq_len, use_cuda_graph=1 if use_cuda_graph else 0,
                        use_pdl=1 if use_pdl else 0, use_chain=1 if use_chain else 0,
                        model_type=_lib.HQ_MODEL[model_type], embedding_kind=_lib.HQ_EMB[embedding_type],
-                       position_kind=_lib.HQ_POS[position_embedding], code_levels=int(code_levels), vocab_mid=int(vocab_mid))
+                       position_kind=_lib.HQ_POS[position_embedding], code_levels=int(code_levels), vocab_mid=int(vocab_mid),
+                       fuse_head_sampler=1 if fuse_head_sampler else 0)
         self.code_levels = int(code_levels)
         if self.code_levels == 3:
             self.vocab_max = max(self.vocab_max, int(vocab_mid))

@@ -23,7 +23,7 @@ class HQTransformer:
     def __init__(self, vocab_sizes: Sequence[int], vocab_size_txt: int, decoding_type: Optional[str], use_cls_cond: bool,
                  use_txt_cond: bool, hparams, hparams_dec=None, *, device: Union[int, str, torch.device] = 0,
                  precision: str = "bf16", max_batch: int = 16, max_seq_len: int = 64, use_cuda_graph: bool = True,
-                 use_pdl: bool = True) -> None:
+                 use_pdl: bool = True, fuse_head_sampler: bool = True) -> None:
         if len(vocab_sizes) != 3:
             raise NotImplementedError("HQTransformer: three code levels (1 + 4 + 16 codes per position) are implemented")
         if decoding_type != "parallel-add":
@@ -56,7 +56,8 @@ class HQTransformer:
                                n_layers_depth=self.n_layers_depth, vocab_top=self.vocab_sizes[0], vocab_bot=self.vocab_sizes[2],
                                vocab_mid=self.vocab_sizes[1], code_levels=3, n_classes=self.n_classes or 0,
                                ctx_len_img=self.ctx_len_img, cond=self.cond, max_seq_len=self.max_seq_len,
-                               device=self.device, use_cuda_graph=use_cuda_graph, use_pdl=use_pdl)
+                               device=self.device, use_cuda_graph=use_cuda_graph, use_pdl=use_pdl,
+                               fuse_head_sampler=fuse_head_sampler)
         self._max_batch = max_batch
         self._engines: Dict[str, Engine] = {}
         self._source = None

@@ -56,7 +56,7 @@ class iHQGPT:
                  use_cls_cond: bool, use_txt_cond: bool, model_type: str, hparams, hparams_dec=None, *,
                  device: Union[int, str, torch.device] = 0, precision: str = "bf16", max_batch: int = 16,
                  max_seq_len: int = 64, use_cuda_graph: bool = True, use_pdl: bool = True,
-                 use_chain: bool = False) -> None:
+                 use_chain: bool = False, fuse_head_sampler: bool = True) -> None:
         if model_type not in ("parallel", "top2bot", "bidirectional"):
             raise NotImplementedError(
                 f"model_type={model_type!r}: 'parallel', 'top2bot' and 'bidirectional' with a 2x2 bottom window are "
@@ -101,7 +101,8 @@ class iHQGPT:
                                vocab_txt=vocab_size_txt, n_classes=self.n_classes or 0, ctx_len_img=self.ctx_len_img,
                                ctx_len_txt=self.ctx_len_txt, cond=self.cond, max_seq_len=self.max_seq_len,
                                device=self.device, use_cuda_graph=use_cuda_graph, use_pdl=use_pdl,
-                               use_chain=use_chain, model_type=model_type, embedding_type=emb, position_embedding=pos_emb)
+                               use_chain=use_chain, model_type=model_type, embedding_type=emb, position_embedding=pos_emb,
+                               fuse_head_sampler=fuse_head_sampler)
         self._max_batch = max_batch
         self._engines: Dict[str, Engine] = {}
         self._source: Optional[Dict[str, torch.Tensor]] = None    # retained only when asked (other-precision engine)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HQ_ABI_VERSION 7
+#define HQ_ABI_VERSION 8
 
 enum hq_status {
   HQ_OK = 0,
@@ -95,6 +95,11 @@ typedef struct hq_config {
                               (hqvae/models/stage2/hqtransformer.py, decoding_type 'parallel-add', embedding 'transformer1'):
                               1 top + 4 middle + 16 bottom codes per position in three depth passes.  0 is read as 2. */
   int32_t vocab_mid;       /* code_levels == 3: vocab_sizes[1] (vocab_top = vocab_sizes[0], vocab_bot = vocab_sizes[2]) */
+  int32_t fuse_head_sampler; /* 1 (bf16 engine): a draw with top_k None and top_p None (the measure_throughput protocol) is made
+                              inside the head GEMM's epilogue - exact two-stage categorical sampling over 32-column chunks,
+                              the [rows, V] logits are never written.  Same distribution as the unfused sampler, different
+                              Philox counters (so a different, equally valid stream for a given seed); greedy, top-k, top-p,
+                              teacher-forced and logits-returning runs always use the unfused sampler.  0: always unfused. */
 } hq_config;
 
 /* Arguments of Sample(z; T, k, p) - hierarchical_ar.py:762-785 with utils/sampling.py:12-37.

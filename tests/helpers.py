@@ -32,13 +32,13 @@ def hparams_of(cfg: O.HQConfig, n_layers=None):
 
 
 def build_model(cfg: O.HQConfig, params, precision="fp32", max_batch=8, use_cuda_graph=True, max_seq_len=64,
-                use_pdl=True, use_chain=False):
+                use_pdl=True, use_chain=False, fuse_head_sampler=True):
     """hqtransformer_b200.iHQGPT for an oracle config, loaded with the oracle's (reference-named) parameters."""
     import hqtransformer_b200 as H
     model = H.iHQGPT(vocab_size_top=cfg.vocab_top, vocab_size_bot=cfg.vocab_bot, vocab_size_txt=cfg.vocab_txt,
                      ratio_bot2top=4, use_cls_cond=(cfg.cond == "cls"), use_txt_cond=(cfg.cond == "txt"),
                      model_type=getattr(cfg, "model_type", "parallel"), hparams=hparams_of(cfg), hparams_dec=hparams_of(cfg, cfg.n_layers_depth),
                      device=0, precision=precision, max_batch=max_batch, use_cuda_graph=use_cuda_graph,
-                     max_seq_len=max_seq_len, use_pdl=use_pdl, use_chain=use_chain)
+                     max_seq_len=max_seq_len, use_pdl=use_pdl, use_chain=use_chain, fuse_head_sampler=fuse_head_sampler)
     model.load_state_dict(params, strict=True)
     return model

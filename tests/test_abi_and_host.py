@@ -28,7 +28,7 @@ def test_library_exports_every_symbol_the_header_declares():
 def test_struct_layouts_match_header_sizes():
     import ctypes
     from hqtransformer_b200 import _lib
-    assert ctypes.sizeof(_lib.HQConfig) == 21 * 4
+    assert ctypes.sizeof(_lib.HQConfig) == 22 * 4
     assert ctypes.sizeof(_lib.HQSamplingParams) == 56
     assert ctypes.sizeof(_lib.HQRunArgs) == 16 + 7 * 8 + 56 + 2 * 8 + 8
 
