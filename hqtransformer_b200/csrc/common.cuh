@@ -171,6 +171,23 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 }
 
 #if defined(__CUDA_ARCH__)
+// One lane of a CONVERGED warp (the same lane every time for the same mask).  The single-thread roles (TMA producer,
+// tcgen05.mma issuer) run as warp-uniform code and issue under this predicate: inside `if (lane == 0)` ptxas must
+// assume divergence and wraps every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST "waterfall" loop - measured ~77 clk
+// per MMA and ~130 clk per TMA issue (profiles/r2_gemm_loop_prof.txt) - whereas operands computed in uniform control
+// flow stay in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
@@ -210,6 +227,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++polls > (1u << 24)) __trap();
+  }
+}
+// Waits for two barriers at once: both try_wait requests are in flight together, so a thread that needs two operands
+// (the A and the W ring of the pair GEMM) pays one ~200-clk barrier round trip per stage, not two.
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar1, uint32_t parity1, uint64_t* bar2, uint32_t parity2) {
+  uint32_t polls = 0;
+  bool d1 = false, d2 = false;
+  while (true) {
+    const bool t1 = d1 || mbar_try_wait(bar1, parity1);
+    const bool t2 = d2 || mbar_try_wait(bar2, parity2);
+    d1 = t1;
+    d2 = t2;
+    if (d1 && d2) break;
     if (++polls > (1u << 24)) __trap();
   }
 }
@@ -333,6 +364,13 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+// 3-D form: the GEMM operands viewed as [K / 64][rows][64] so that ONE instruction stages several 64-wide k-blocks
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {

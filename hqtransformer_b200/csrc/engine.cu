@@ -46,6 +46,8 @@ static void set_err(hq_ctx* ctx, const char* fmt, ...);
 // instruction (a TMA issue costs ~40 ns in the producer thread; 16-row boxes made a 256-wide tile issue-bound).
 struct PairMaps {
   CUtensorMap m[6];
+  CUtensorMap m3[6];     // the same tiles as 3-D boxes {64, BN/2, 2} over the [K/64][N][64] view (two k-blocks per instruction)
+  bool have3 = false;
   static int index(int bn) { return bn == 32 ? 0 : bn == 64 ? 1 : bn == 96 ? 2 : bn == 128 ? 3 : bn == 192 ? 4 : bn == 256 ? 5 : -1; }
   static int width(int i) { static const int w[6] = {32, 64, 96, 128, 192, 256}; return w[i]; }
 };
@@ -61,6 +63,8 @@ struct ABuf {            // a GEMM A operand buffer [rows_pad, K]
   void* ptr = nullptr;
   int rows = 0, K = 0;
   CUtensorMap map;       // bf16 only: box {64, 128}
+  CUtensorMap map3;      // bf16 only, K >= 128: 3-D box {64, 128, 2} over the [K/64][rows][64] view (pair kernel, KS = 2)
+  bool have3 = false;
   int map_idx = -1;      // index in the ctx's device tensor-map table (chain kernel)
 };
 struct BlockW {
@@ -100,6 +104,7 @@ struct DebugSwitches {
   int no_chain = 0;            // HQ_NO_CHAIN: one kernel per op even where the persistent chain kernel applies
   int chain_min_batch = 0;     // HQ_CHAIN_MIN_BATCH: smallest batch that takes the chain kernel (default 129)
   int chain_no_l2pf = 0;       // HQ_CHAIN_NO_L2PF: chain kernel without the L2 prefetch of later weight tiles
+  int gemm_ks1 = 0;            // HQ_GEMM_KS1: pair GEMM with one k-block per ring stage (2-D boxes) everywhere
 };
 
 static int env_int(const char* name) {
@@ -127,6 +132,7 @@ static DebugSwitches read_debug_switches() {
   d.no_chain = getenv("HQ_NO_CHAIN") != nullptr;
   d.chain_min_batch = env_int("HQ_CHAIN_MIN_BATCH");
   d.chain_no_l2pf = getenv("HQ_CHAIN_NO_L2PF") != nullptr;
+  d.gemm_ks1 = getenv("HQ_GEMM_KS1") != nullptr;
   return d;
 }
 
@@ -264,12 +270,32 @@ static int make_map(hq_ctx* ctx, CUtensorMap* m, void* base, uint64_t rows, uint
   return HQ_OK;
 }
 
+// [rows, cols] bf16 viewed as [cols / 64][rows][64]: one box {64, box_rows, ks} stages ks consecutive 64-wide k-blocks of
+// box_rows rows as ks consecutive SWIZZLE_128B tiles (what the UMMA descriptors of ks k-blocks expect)
+static int make_map3(hq_ctx* ctx, CUtensorMap* m, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t ks) {
+  cuuint64_t dims[3] = {64, rows, cols / 64};
+  cuuint64_t strides[2] = {cols * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, ks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_err(ctx, "cuTensorMapEncodeTiled (3-D k-block view) failed (%d) rows=%llu cols=%llu box_rows=%u", static_cast<int>(r),
+            static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols), box_rows);
+    return HQ_ERR_CUDA;
+  }
+  return HQ_OK;
+}
+
 static int make_pair_maps(hq_ctx* ctx, PairMaps* pm, void* base, uint64_t rows, uint64_t cols) {
   memset(pm, 0, sizeof(*pm));
+  pm->have3 = cols >= 128;
   for (int i = 0; i < 6; ++i) {
     if (static_cast<uint64_t>(PairMaps::width(i)) > rows) continue;   // a tile wider than the matrix is never launched
     int rc = make_map(ctx, &pm->m[i], base, rows, cols, static_cast<uint32_t>(PairMaps::width(i) / 2));
     if (rc) return rc;
+    if (pm->have3 && (rc = make_map3(ctx, &pm->m3[i], base, rows, cols, static_cast<uint32_t>(PairMaps::width(i) / 2), 2))) return rc;
   }
   return HQ_OK;
 }
@@ -307,7 +333,11 @@ static int alloc_abuf(hq_ctx* ctx, ABuf* a, int rows, int K) {
   a->K = K;
   int rc = dev_alloc(ctx, &a->ptr, static_cast<size_t>(a->rows) * K * ctx->wsize);
   if (rc) return rc;
-  if (ctx->bf16) return make_map(ctx, &a->map, a->ptr, a->rows, K, 128);
+  if (ctx->bf16) {
+    if ((rc = make_map(ctx, &a->map, a->ptr, a->rows, K, 128))) return rc;
+    a->have3 = K >= 128;
+    if (a->have3) return make_map3(ctx, &a->map3, a->ptr, a->rows, K, 128, 2);
+  }
   return HQ_OK;
 }
 static int alloc_f32(hq_ctx* ctx, float** p, size_t n) { return dev_alloc(ctx, reinterpret_cast<void**>(p), n * 4); }
@@ -372,7 +402,8 @@ static int set_gemm_attrs(hq_ctx* ctx) {
   HQ_SET(128, EPI_QKV) HQ_SET(128, EPI_RESID) HQ_SET(128, EPI_GELU) HQ_SET(128, EPI_F32) HQ_SET(128, EPI_SAMPLE)
 #undef HQ_SET
 #define HQ_SET2(BN, EPI) \
-  if ((rc = set_smem(ctx, gemm_tc2_kernel<BN, EPI, bf16>, Tc2Cfg<BN>::SMEM_BYTES))) return rc;
+  if ((rc = set_smem(ctx, gemm_tc2_kernel<BN, EPI, bf16, 1>, Tc2Cfg<BN, 1>::SMEM_BYTES))) return rc; \
+  if ((rc = set_smem(ctx, gemm_tc2_kernel<BN, EPI, bf16, 2>, Tc2Cfg<BN, 2>::SMEM_BYTES))) return rc;
 #define HQ_SET2_ALL(BN) HQ_SET2(BN, EPI_QKV) HQ_SET2(BN, EPI_RESID) HQ_SET2(BN, EPI_GELU) HQ_SET2(BN, EPI_F32) HQ_SET2(BN, EPI_SAMPLE)
   HQ_SET2_ALL(32) HQ_SET2_ALL(64) HQ_SET2_ALL(96) HQ_SET2_ALL(128) HQ_SET2_ALL(192) HQ_SET2_ALL(256)
 #undef HQ_SET2_ALL
@@ -1035,7 +1066,7 @@ static int pick_pair_bn(int M, int N, int K) {
 }
 
 template <int EPI>
-static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap& mW64,
+static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const CUtensorMap* mA3, const CUtensorMap& mW64,
                       const PairMaps& mWp, int w_row_off, int M, int N, int K, const EpiParams<bf16>& ep,
                       int splits = 1, int bn_hint = 0, int ia = -1, int iw = -1) {
   int bn = ctx->dbg.force_bn ? ctx->dbg.force_bn : bn_hint;
@@ -1069,10 +1100,16 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
   if (bn > 0 && N % bn == 0) {
     const int tiles = (N / bn) * ((M + 255) / 256) * splits;
     dim3 grid(2 * (tiles < 74 ? tiles : 74));               // persistent: at most one CTA pair per SM pair
+    // two k-blocks per ring stage (3-D boxes) whenever every tile's K range holds an even number of k-blocks
+    const bool ks2 = mA3 != nullptr && mWp.have3 && !ctx->dbg.gemm_ks1 && ((K / 64) / splits) % 2 == 0;
 #define HQ_LAUNCH2(BN)                                                                                             \
   case BN:                                                                                                         \
-    launch_k(ctx, st, tag, gemm_tc2_kernel<BN, EPI, bf16>, grid, dim3(Tc2Cfg<BN>::THREADS), Tc2Cfg<BN>::SMEM_BYTES, mA, mWp.m[PairMaps::index(BN)], M, N, K,  \
-             w_row_off, splits, ep);                                                                               \
+    if (ks2)                                                                                                       \
+      launch_k(ctx, st, tag, gemm_tc2_kernel<BN, EPI, bf16, 2>, grid, dim3(Tc2Cfg<BN, 2>::THREADS), Tc2Cfg<BN, 2>::SMEM_BYTES, *mA3,  \
+               mWp.m3[PairMaps::index(BN)], M, N, K, w_row_off, splits, ep);                                       \
+    else                                                                                                           \
+      launch_k(ctx, st, tag, gemm_tc2_kernel<BN, EPI, bf16, 1>, grid, dim3(Tc2Cfg<BN, 1>::THREADS), Tc2Cfg<BN, 1>::SMEM_BYTES, mA,  \
+               mWp.m[PairMaps::index(BN)], M, N, K, w_row_off, splits, ep);                                        \
     break;
     switch (bn) {
       HQ_LAUNCH2(32) HQ_LAUNCH2(64) HQ_LAUNCH2(96) HQ_LAUNCH2(128) HQ_LAUNCH2(192) HQ_LAUNCH2(256)
@@ -1104,7 +1141,7 @@ static void gemm_f32(hq_ctx* ctx, cudaStream_t st, const float* A, const float* 
 template <int EPI>
 static void gemm_any(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
                      const EpiParams<bf16>& ep) {
-  gemm_bf16<EPI>(ctx, st, A.map, W.map, W.mapp, w_row_off, M, N, K, ep, 1, 0, A.map_idx, W.map_idx);
+  gemm_bf16<EPI>(ctx, st, A.map, A.have3 ? &A.map3 : nullptr, W.map, W.mapp, w_row_off, M, N, K, ep, 1, 0, A.map_idx, W.map_idx);
 }
 template <int EPI>
 static void gemm_any(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const Weight& W, int w_row_off, int M, int N, int K,
@@ -1285,7 +1322,7 @@ static void gemm_fc2_split(hq_ctx* ctx, cudaStream_t st, const ABuf& A, const We
   memset(&e, 0, sizeof(e));
   e.outf = ctx->splitk_ws; e.ldo = N; e.split_stride = static_cast<size_t>(ctx->ws_rows) * N;
   ctx->gemm_tag_override = "gemm_resid";
-  gemm_bf16<EPI_F32>(ctx, st, A.map, W.map, W.mapp, 0, M, N, K, e, splits, bn, A.map_idx, W.map_idx);
+  gemm_bf16<EPI_F32>(ctx, st, A.map, A.have3 ? &A.map3 : nullptr, W.map, W.mapp, 0, M, N, K, e, splits, bn, A.map_idx, W.map_idx);
 }
 static void gemm_fc2_split(hq_ctx*, cudaStream_t, const ABuf&, const Weight&, int, int, int, int, int, float*) {}
 
@@ -1930,9 +1967,10 @@ extern "C" int hq_debug_gemm(int prec, const void* A, const void* W, float* C, i
       cudaMemsetAsync(Ap, 0, static_cast<size_t>(Mp) * K * 2, st);
       cudaMemcpyAsync(Ap, A, static_cast<size_t>(M) * K * 2, cudaMemcpyDeviceToDevice, st);
     }
-    CUtensorMap mA, mW;
+    CUtensorMap mA, mA3, mW;
     PairMaps mWp;
     if (rc == HQ_OK) rc = make_map(&tmp, &mA, Ap, Mp, K, 128);
+    if (rc == HQ_OK && K >= 128) rc = make_map3(&tmp, &mA3, Ap, Mp, K, 128, 2);
     if (rc == HQ_OK) rc = make_map(&tmp, &mW, const_cast<void*>(W), N, K, 64);
     if (rc == HQ_OK) rc = make_pair_maps(&tmp, &mWp, const_cast<void*>(W), N, K);
     if (rc == HQ_OK) {
@@ -1940,7 +1978,7 @@ extern "C" int hq_debug_gemm(int prec, const void* A, const void* W, float* C, i
       memset(&e, 0, sizeof(e));
       e.outf = C; e.ldo = N;
       tmp.dbg.force_bn = tile;
-      gemm_bf16<EPI_F32>(&tmp, st, mA, mW, mWp, 0, M, N, K, e);
+      gemm_bf16<EPI_F32>(&tmp, st, mA, K >= 128 ? &mA3 : nullptr, mW, mWp, 0, M, N, K, e);
     }
     cudaError_t se = cudaStreamSynchronize(st);
     if (Ap) cudaFree(Ap);
@@ -2217,10 +2255,12 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
   cudaMemsetAsync(A, 0, static_cast<size_t>(Mp) * K * 2, st);
   cudaMemsetAsync(W, 0, wbytes * copies, st);
   cudaMemsetAsync(flushbuf, 1, flush_bytes, st);
-  CUtensorMap mA;
+  long long* prof_buf = nullptr;
+  CUtensorMap mA, mA3;
   std::vector<CUtensorMap> mW(copies);
   std::vector<PairMaps> mWp(copies);
   rc = make_map(&tmp, &mA, A, Mp, K, 128);
+  if (rc == HQ_OK && K >= 128) rc = make_map3(&tmp, &mA3, A, Mp, K, 128, 2);
   for (int c = 0; rc == HQ_OK && c < copies; ++c) {
     rc = make_map(&tmp, &mW[c], static_cast<char*>(W) + wbytes * c, N, K, 64);
     if (rc == HQ_OK) rc = make_pair_maps(&tmp, &mWp[c], static_cast<char*>(W) + wbytes * c, N, K);
@@ -2231,17 +2271,31 @@ extern "C" int hq_bench_gemm_shape(int M, int N, int K, int tile, int iters, int
     EpiParams<bf16> e;
     memset(&e, 0, sizeof(e));
     e.outf = C; e.ldo = N; e.split_stride = static_cast<size_t>(M) * N;
+    if (getenv("HQ_GEMM_PROF") != nullptr && cudaMalloc(reinterpret_cast<void**>(&e.prof), 16 * sizeof(long long)) == cudaSuccess)
+      cudaMemsetAsync(e.prof, 0, 16 * sizeof(long long), st);
+    prof_buf = e.prof;
     tmp.dbg.force_bn = tile;
     for (int i = -3; i < iters; ++i) {
       const int c = ((i % copies) + copies) % copies;
       if (flush == 1) cudaMemsetAsync(flushbuf, i & 0xff, flush_bytes, st);
       if (flush == 2) read_sweep_kernel<<<1184, 256, 0, st>>>(static_cast<const uint4*>(flushbuf), flush_bytes / 16, sink);
       if (i >= 0) cudaEventRecord(ev[2 * i], st);
-      gemm_bf16<EPI_F32>(&tmp, st, mA, mW[c], mWp[c], 0, M, N, K, e, splits);
+      gemm_bf16<EPI_F32>(&tmp, st, mA, K >= 128 ? &mA3 : nullptr, mW[c], mWp[c], 0, M, N, K, e, splits);
       if (i >= 0) cudaEventRecord(ev[2 * i + 1], st);
     }
   }
   cudaError_t se = cudaStreamSynchronize(st);
+  if (prof_buf != nullptr) {
+    long long h[16];
+    if (cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess && h[8] > 0) {
+      const double np = h[3] > 0 ? static_cast<double>(h[3]) : 1.0, nm = static_cast<double>(h[8]);
+      fprintf(stderr,
+              "[gemm prof] M=%d N=%d K=%d tile=%d (pair 0 leader, last launch; clk per ring stage) producer: wait_empty %.0f issue %.0f "
+              "loop %.0f (n=%lld) | mma: wait_full %.0f issue %.0f commit %.0f loop %.0f (n=%lld)\n",
+              M, N, K, tile, h[0] / np, h[1] / np, h[2] / np, h[3], h[4] / nm, h[5] / nm, h[6] / nm, h[7] / nm, h[8]);
+    }
+    cudaFree(prof_buf);
+  }
   double tot = 0.0, mn = 1e30;
   for (int i = 0; i < iters; ++i) {
     float ms = 0.f;

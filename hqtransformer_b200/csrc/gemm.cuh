@@ -43,6 +43,9 @@ struct EpiParams {
   const hq_sampling_params* sp;   // device copy (temperature, seed, row offset)
   float2* samp_part;              // [M, N / 32]: per 32-column chunk (log-sum-exp, index drawn inside the chunk as int bits)
   int temp_sel, rows_per_b, slot0, pos;
+  // debug (hq_bench_gemm_shape with HQ_GEMM_PROF): clock64 sums of the producer / MMA-issuer loops of pair 0's leader
+  long long* prof;
+  long long prof_pad;   // keeps sizeof(EpiParams) (and the chain kernel's ChainOp) a multiple of 16
 };
 
 
@@ -418,22 +421,38 @@ gemm_tc_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __gr
 // tmA: [rows_pad, K] box {64,128}; tmW: [N, K] box {64, BN/2} (this CTA's half of the W tile, one load per stage); both
 // SWIZZLE_128B.
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+// KS = 64-wide k-blocks per ring stage.  The main loop of these GEMMs is NOT bound by bytes: a successful
+// mbarrier.try_wait costs ~190-230 clk in the waiting thread and a TMA issue ~130 clk (+ ~64 per further instruction)
+// whatever the box size (scripts/sm_ingest_bench.cu, profiles/r2_sm_ingest_bench.txt: 195 ns per iteration for 8, 16 or
+// 32 KB boxes, ring depth 2..16, 1 or 144 CTAs), so with one k-block per stage the producer and the MMA issuer each
+// spend ~300 ns per k-block on barrier round trips - the "78 GB/s per SM" of round 1 was that loop, not an ingest
+// limit.  With KS = 2 one 3-D TMA box ([K/64][rows][64] view, box {64, rows, 2}) stages 128 columns of K per operand
+// and the barrier waits / commits are paid once per 128 columns.  KS = 1 (2-D boxes) remains for K ranges with an odd
+// number of k-blocks.
+template <int BN, int KS = 1>
 struct Tc2Cfg {
   static constexpr int BK = 64;
-  static constexpr int A_BYTES = 128 * BK * 2;          // this CTA's 128 rows of A
-  static constexpr int B_BYTES = (BN / 2) * BK * 2;     // this CTA's half of the W tile
+  static constexpr int A_ATOM = 128 * BK * 2;           // this CTA's 128 rows of A, one k-block
+  static constexpr int B_ATOM = (BN / 2) * BK * 2;      // this CTA's half of the W tile, one k-block
+  static constexpr int A_BYTES = KS * A_ATOM;
+  static constexpr int B_BYTES = KS * B_ATOM;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // >= 120 KB of shared memory per CTA on purpose: at most ONE GEMM CTA is resident per SM.  With two (the next
   // kernel's CTA launched early by PDL next to the current one) tcgen05.alloc/dealloc of different CTA pairs interleave
   // on the same SM pair, and the sampling loop was seen to hang in that state (round-1 notes).
-  static constexpr int STAGES = (172032 / STAGE_BYTES) > 8 ? 8 : (172032 / STAGE_BYTES);
+  // One ring for both operands.  A second, deeper ring for the weight tiles with its own producer warp (requested up to
+  // the whole K range ahead, before griddepcontrol.wait) was built and measured: no gain (3 198 vs 3 240 images/s) - with
+  // the issue overhead gone these main loops run at the L2 -> SM throughput of the chip (~13-15 TB/s), not at DRAM latency.
+  static constexpr int RING_BUDGET = KS == 1 ? 172032 : 196608;
+  static constexpr int MAX_STAGES = KS == 1 ? 8 : 4;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (RING_BUDGET / STAGE_BYTES);
   static constexpr int ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // one accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;                                               // double buffered
   static constexpr int EPI_WARPS = 8;                   // two per TMEM lane quarter
   static constexpr int THREADS = (2 + EPI_WARPS) * 32;
   static constexpr int SLAB_BYTES = EPI_WARPS * 4096;   // epilogue staging: one 32-row x 128 B slab per warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + SLAB_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
+  static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
 };
 
 // arrive on the mbarrier at the same offset in CTA `cta` of the cluster
@@ -449,13 +468,13 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
 // and its mbarrier phases run on across tiles, the accumulator is double buffered in TMEM (tile i+1's MMAs start while
 // tile i is drained), so a GEMM with more tiles than pairs pays the fixed per-wave cost once.
 // tile index -> (split z, row block, column block), column block fastest.
-template <int BN, int EPI, typename AT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<BN>::THREADS, 1)
+template <int BN, int EPI, typename AT, int KS = 1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<BN, KS>::THREADS, 1)
 gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M,
                 int N, int K, int w_row_off, int splits, EpiParams<AT> ep) {
 #if defined(__CUDA_ARCH__)
   TraceScope trace_scope(trace_id);
-  using C = Tc2Cfg<BN>;
+  using C = Tc2Cfg<BN, KS>;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "pair tile width");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -469,14 +488,15 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform (role dispatch)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int nt = N / BN, mt = (M + 255) / 256;
   const int total_tiles = nt * mt * splits;
-  const int num_kb = (K / C::BK) / splits;               // k-blocks per tile
+  const int num_kb = (K / C::BK) / splits;               // 64-wide k-blocks per tile
+  const int num_st = (num_kb + KS - 1) / KS;             // ring stages per tile (KS k-blocks each; the last may be short)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -505,64 +525,100 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
 
   pdl_launch_dependents();
   if (warp == 0) {
-    if (lane == 0) {
-      // ---- TMA producer (both CTAs): own A rows + own half of the W tile, credited to the leader's full barrier.
-      //      The first ring of W tiles is requested before griddepcontrol.wait (weights never depend on the
-      //      previous kernel), the activation tiles after it. ----
-      int g = 0;                                          // k-blocks issued so far (all tiles)
-      bool first = true;
-      for (int tile = pair; tile < total_tiles; tile += npairs) {
-        const int z = tile / (nt * mt), rem = tile % (nt * mt);
-        const int m0 = (rem / nt) * 256 + static_cast<int>(rank) * 128;
-        const int wrow = w_row_off + (rem % nt) * BN + static_cast<int>(rank) * (BN / 2);
-        const int kb0 = z * num_kb;
-        int kb = 0;
-        if (first) {
-          first = false;
-          const int pre = num_kb < C::STAGES ? num_kb : C::STAGES;
-          for (; kb < pre; ++kb) {
-            if (leader) mbar_arrive_expect_tx(&full_bar[kb], 2 * C::STAGE_BYTES);
-            tma_load_2d_2sm(sB + kb * C::B_BYTES, &tmW, &full_bar[kb], (kb0 + kb) * C::BK, wrow);
+    // ---- TMA producer (both CTAs; the whole warp runs the loop, one elected lane issues): own A rows + own half of
+    //      the W tile, credited to the leader's full barrier.  The first ring of W tiles is requested before
+    //      griddepcontrol.wait (weights never depend on the previous kernel), the activation tiles after it. ----
+    int g = 0;                                          // ring stages issued so far (all tiles)
+    bool first = true;
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
+      const int z = tile / (nt * mt), rem = tile % (nt * mt);
+      const int m0 = (rem / nt) * 256 + static_cast<int>(rank) * 128;
+      const int wrow = w_row_off + (rem % nt) * BN + static_cast<int>(rank) * (BN / 2);
+      const int kb0 = z * num_kb;
+      // one instruction per operand and stage: KS = 1 a 2-D box of one k-block, KS > 1 a 3-D box of KS k-blocks
+      // (a box that runs past this tile's K range lands whole - zero-filled past the matrix - and its surplus
+      // k-blocks are simply not multiplied)
+      auto load_a = [&](int st, int slot) {
+        if (KS == 1) tma_load_2d_2sm(sA + slot * C::A_BYTES, &tmA, &full_bar[slot], (kb0 + st) * C::BK, m0);
+        else tma_load_3d_2sm(sA + slot * C::A_BYTES, &tmA, &full_bar[slot], 0, m0, kb0 + st * KS);
+      };
+      auto load_w = [&](int st, int slot) {
+        if (KS == 1) tma_load_2d_2sm(sB + slot * C::B_BYTES, &tmW, &full_bar[slot], (kb0 + st) * C::BK, wrow);
+        else tma_load_3d_2sm(sB + slot * C::B_BYTES, &tmW, &full_bar[slot], 0, wrow, kb0 + st * KS);
+      };
+      int st = 0;
+      if (first) {
+        first = false;
+        const int pre = num_st < C::STAGES ? num_st : C::STAGES;
+        if (elect_one()) {
+          for (int k2 = 0; k2 < pre; ++k2) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[k2], 2 * C::STAGE_BYTES);
+            load_w(k2, k2);
           }
-          pdl_wait();
-          for (int k2 = 0; k2 < pre; ++k2)
-            tma_load_2d_2sm(sA + k2 * C::A_BYTES, &tmA, &full_bar[k2], (kb0 + k2) * C::BK, m0);
-          g = pre;
         }
-        for (; kb < num_kb; ++kb, ++g) {
-          const int s = g % C::STAGES;
-          const uint32_t ph = (g / C::STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
-          tma_load_2d_2sm(sA + s * C::A_BYTES, &tmA, &full_bar[s], (kb0 + kb) * C::BK, m0);
-          tma_load_2d_2sm(sB + s * C::B_BYTES, &tmW, &full_bar[s], (kb0 + kb) * C::BK, wrow);
+        pdl_wait();
+        if (elect_one()) {
+          for (int k2 = 0; k2 < pre; ++k2) load_a(k2, k2);
         }
+        st = pre;
+        g = pre;
       }
+      const bool prof = ep.prof != nullptr && blockIdx.x == 0;
+      long long p_wait = 0, p_issue = 0, p_n = 0;
+      const long long p_t0 = prof ? clock64() : 0;
+      for (; st < num_st; ++st, ++g) {
+        const int s = g % C::STAGES;
+        const uint32_t ph = (g / C::STAGES) & 1;
+        const long long c0 = prof ? clock64() : 0;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const long long c1 = prof ? clock64() : 0;
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+          load_a(st, s);
+          load_w(st, s);
+        }
+        if (prof) { p_wait += c1 - c0; p_issue += clock64() - c1; ++p_n; }
+      }
+      if (prof && lane == 0) { ep.prof[0] = p_wait; ep.prof[1] = p_issue; ep.prof[2] = clock64() - p_t0; ep.prof[3] = p_n; }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
-      // ---- MMA issuer (leader CTA only) ----
+    if (leader) {
+      // ---- MMA issuer (leader CTA only; warp-uniform loop, the elected lane issues the MMAs and their commits) ----
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int g = 0, it = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
         const int buf = it & 1;
         mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);     // both CTAs drained this accumulator
         tc_fence_after();
-        const uint32_t acc = tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS);
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const uint32_t acc = tmem_u + static_cast<uint32_t>(buf * C::ACC_COLS);
+        const bool prof = ep.prof != nullptr && blockIdx.x == 0;
+        long long m_wait = 0, m_issue = 0;
+        const long long m_t0 = prof ? clock64() : 0;
+        for (int st = 0; st < num_st; ++st, ++g) {
           const int s = g % C::STAGES;
           const uint32_t ph = (g / C::STAGES) & 1;
+          const long long c0 = prof ? clock64() : 0;
           mbar_wait(&full_bar[s], ph);
+          const long long c1 = prof ? clock64() : 0;
           tc_fence_after();
-          const uint64_t da = umma_smem_desc_sw128(smem_u32(sA + s * C::A_BYTES));
-          const uint64_t db = umma_smem_desc_sw128(smem_u32(sB + s * C::B_BYTES));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < C::BK / 16; ++k)
-            umma_bf16_2sm(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[s], 0x3);   // both CTAs may refill this slot
+            for (int j = 0; j < KS; ++j) {
+              if (KS > 1 && st * KS + j >= num_kb) break;      // short last stage
+              const uint64_t da = umma_smem_desc_sw128(smem_u32(sA + s * C::A_BYTES + j * C::A_ATOM));
+              const uint64_t db = umma_smem_desc_sw128(smem_u32(sB + s * C::B_BYTES + j * C::B_ATOM));
+#pragma unroll
+              for (int k = 0; k < C::BK / 16; ++k)
+                umma_bf16_2sm(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                              (st > 0 || j > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[s], 0x3);   // both CTAs may refill this slot
+          }
+          if (prof) { m_wait += c1 - c0; m_issue += clock64() - c1; }
         }
-        umma_commit_2sm(&tmem_full_bar[buf], 0x3);   // both CTAs' accumulators of this tile are complete
+        if (prof && lane == 0) { ep.prof[4] = m_wait; ep.prof[5] = m_issue; ep.prof[6] = 0; ep.prof[7] = clock64() - m_t0; ep.prof[8] = num_st; }
+        if (elect_one()) umma_commit_2sm(&tmem_full_bar[buf], 0x3);   // both CTAs' accumulators of this tile are complete
       }
     }
   } else {

@@ -25,9 +25,12 @@ def test_gemm_tcgen05_matches_fp32_matmul(M, N, K):
 
 
 @pytest.mark.parametrize("tile", [32, 64, 96, 128, 192, 256, -64, -128])
-@pytest.mark.parametrize("M,N,K", [(256, 1536, 1536), (1024, 4608, 512), (300, 768, 128), (129, 3072, 6144)])
+@pytest.mark.parametrize("M,N,K", [(256, 1536, 1536), (1024, 4608, 512), (300, 768, 128), (129, 3072, 6144), (300, 768, 192),
+                                   (513, 1536, 320)])
 def test_gemm_tcgen05_every_tile_variant(M, N, K, tile):
-    """CTA-pair kernel (cta_group::2, 256 x tile) for every tile width, and the single-CTA kernel, incl. ragged M."""
+    """CTA-pair kernel (cta_group::2, 256 x tile) for every tile width, and the single-CTA kernel, incl. ragged M.
+    K with an even number of 64-wide k-blocks takes the two-k-blocks-per-stage instantiation (3-D TMA boxes), an odd
+    number (192, 320) the one-k-block one."""
     from hqtransformer_b200.engine import debug_gemm
     if tile > 0 and N % tile != 0:
         pytest.skip("N not a multiple of the tile width")
