@@ -105,6 +105,7 @@ struct DebugSwitches {
   int chain_min_batch = 0;     // HQ_CHAIN_MIN_BATCH: smallest batch that takes the chain kernel (default 129)
   int chain_no_l2pf = 0;       // HQ_CHAIN_NO_L2PF: chain kernel without the L2 prefetch of later weight tiles
   int gemm_ks1 = 0;            // HQ_GEMM_KS1: pair GEMM with one k-block per ring stage (2-D boxes) everywhere
+  int bn_m256 = 0;             // HQ_BN_M256: pinned pair-tile width of the unsplit GEMMs with M <= 256 (plan experiments)
 };
 
 static int env_int(const char* name) {
@@ -133,6 +134,7 @@ static DebugSwitches read_debug_switches() {
   d.chain_min_batch = env_int("HQ_CHAIN_MIN_BATCH");
   d.chain_no_l2pf = getenv("HQ_CHAIN_NO_L2PF") != nullptr;
   d.gemm_ks1 = getenv("HQ_GEMM_KS1") != nullptr;
+  d.bn_m256 = env_int("HQ_BN_M256");
   return d;
 }
 
@@ -397,7 +399,8 @@ static int set_smem(hq_ctx* ctx, K kernel, int bytes) {
 static int set_gemm_attrs(hq_ctx* ctx) {
   int rc;
 #define HQ_SET(BN, EPI) \
-  if ((rc = set_smem(ctx, gemm_tc_kernel<BN, EPI, bf16>, TcCfg<BN>::SMEM_BYTES))) return rc;
+  if ((rc = set_smem(ctx, gemm_tc_kernel<BN, EPI, bf16, 1>, TcCfg<BN, 1>::SMEM_BYTES))) return rc; \
+  if ((rc = set_smem(ctx, gemm_tc_kernel<BN, EPI, bf16, 2>, TcCfg<BN, 2>::SMEM_BYTES))) return rc;
   HQ_SET(64, EPI_QKV) HQ_SET(64, EPI_RESID) HQ_SET(64, EPI_GELU) HQ_SET(64, EPI_F32) HQ_SET(64, EPI_SAMPLE)
   HQ_SET(128, EPI_QKV) HQ_SET(128, EPI_RESID) HQ_SET(128, EPI_GELU) HQ_SET(128, EPI_F32) HQ_SET(128, EPI_SAMPLE)
 #undef HQ_SET
@@ -1071,6 +1074,7 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
                       int splits = 1, int bn_hint = 0, int ia = -1, int iw = -1) {
   int bn = ctx->dbg.force_bn ? ctx->dbg.force_bn : bn_hint;
   if (bn == 0) bn = (M > 128) ? pick_pair_bn(M, N, K) : 0;
+  if (bn_hint == 0 && !ctx->dbg.force_bn && ctx->dbg.bn_m256 > 0 && M > 128 && M <= 256 && N % ctx->dbg.bn_m256 == 0) bn = ctx->dbg.bn_m256;
   if (ctx->recording) {
     // an op of the persistent chain kernel: CTA-pair tiles only (chain_enabled guarantees M > 128)
     if (bn <= 0 || N % bn != 0 || ia < 0 || iw < 0 || (K / 64) % splits != 0) {
@@ -1120,14 +1124,24 @@ static void gemm_bf16(hq_ctx* ctx, cudaStream_t st, const CUtensorMap& mA, const
   }
   const int mt = (M + 127) / 128;
   const bool wide = bn == -128 || (bn != -64 && (N % 128 == 0) && (mt * (N / 128) >= 120));
+  const int tbn = wide ? 128 : 64;
+  // two k-blocks per ring stage: the W tile of tbn rows is the pair map of width 2 * tbn (box {64, tbn, 2})
+  const bool ks2 = mA3 != nullptr && mWp.have3 && !ctx->dbg.gemm_ks1 && ((K / 64) / splits) % 2 == 0 && N >= 2 * tbn;
+  dim3 grid(N / tbn, mt, splits);
   if (wide) {
-    dim3 grid(N / 128, mt, splits);
-    launch_k(ctx, st, tag, gemm_tc_kernel<128, EPI, bf16>, grid, dim3(192), TcCfg<128>::SMEM_BYTES, mA, mW64, M, N, K,
-             w_row_off, ep);
+    if (ks2)
+      launch_k(ctx, st, tag, gemm_tc_kernel<128, EPI, bf16, 2>, grid, dim3(192), TcCfg<128, 2>::SMEM_BYTES, *mA3,
+               mWp.m3[PairMaps::index(256)], M, N, K, w_row_off, ep);
+    else
+      launch_k(ctx, st, tag, gemm_tc_kernel<128, EPI, bf16, 1>, grid, dim3(192), TcCfg<128, 1>::SMEM_BYTES, mA, mW64, M, N, K,
+               w_row_off, ep);
   } else {
-    dim3 grid(N / 64, mt, splits);
-    launch_k(ctx, st, tag, gemm_tc_kernel<64, EPI, bf16>, grid, dim3(192), TcCfg<64>::SMEM_BYTES, mA, mW64, M, N, K,
-             w_row_off, ep);
+    if (ks2)
+      launch_k(ctx, st, tag, gemm_tc_kernel<64, EPI, bf16, 2>, grid, dim3(192), TcCfg<64, 2>::SMEM_BYTES, *mA3,
+               mWp.m3[PairMaps::index(128)], M, N, K, w_row_off, ep);
+    else
+      launch_k(ctx, st, tag, gemm_tc_kernel<64, EPI, bf16, 1>, grid, dim3(192), TcCfg<64, 1>::SMEM_BYTES, mA, mW64, M, N, K,
+               w_row_off, ep);
   }
 }
 

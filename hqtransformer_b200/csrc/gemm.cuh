@@ -292,23 +292,29 @@ __device__ __forceinline__ void epilogue_sample_tile(uint32_t tmem_base, int war
 //   warps 2-5: epilogue (TMEM lane quarter = warp % 4); warp 2 also owns the TMEM allocation
 // tmA: A as a [rows_pad, K] bf16 tensor, box {64, 128}; tmW: W as [N_pad, K], box {64, 64}; both SWIZZLE_128B.
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+// KS = 64-wide k-blocks per ring stage (see Tc2Cfg): KS = 2 takes 3-D boxes - tmA box {64, 128, 2}, tmW box {64, BN, 2}
+// (the pair maps of width 2 * BN) - one instruction per operand and stage.
+template <int BN, int KS = 1>
 struct TcCfg {
   static constexpr int BM = 128, BK = 64;
-  static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGES = (BN == 128) ? 5 : 6;   // 144-160 KB: ONE GEMM CTA per SM (see Tc2Cfg)
+  static constexpr int A_ATOM = BM * BK * 2;   // 16 KB
+  static constexpr int B_ATOM = BN * BK * 2;
+  static constexpr int A_BYTES = KS * A_ATOM;
+  static constexpr int B_BYTES = KS * B_ATOM;
+  // 144-192 KB: ONE GEMM CTA per SM (see Tc2Cfg)
+  static constexpr int STAGES = KS == 1 ? ((BN == 128) ? 5 : 6) : ((BN == 128) ? 3 : 4);
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*bias*/;
+  static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
 };
 
-template <int BN, int EPI, typename AT>
+template <int BN, int EPI, typename AT, int KS = 1>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
                int w_row_off, EpiParams<AT> ep) {
 #if defined(__CUDA_ARCH__)
   TraceScope trace_scope(trace_id);
-  using C = TcCfg<BN>;
+  using C = TcCfg<BN, KS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
@@ -319,11 +325,12 @@ gemm_tc_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform (role dispatch)
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * C::BM;
   const int n0 = blockIdx.x * BN;
   const int num_kb = (K / C::BK) / static_cast<int>(gridDim.z);        // split-K: this CTA's share of the k-blocks
+  const int num_st = (num_kb + KS - 1) / KS;                           // ring stages (the last may be short)
   const int kb0 = static_cast<int>(blockIdx.z) * num_kb;
   if (EPI == EPI_F32) ep.outf += static_cast<size_t>(blockIdx.z) * ep.split_stride;
 
@@ -350,50 +357,69 @@ gemm_tc_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __gr
 
   pdl_launch_dependents();
   if (warp == 0) {
-    if (lane == 0) {
-      // ---- TMA producer.  Weights do not depend on the previous kernel: the first ring of W tiles is requested
-      //      before griddepcontrol.wait, the activation tiles after it. ----
-      const int pre = num_kb < C::STAGES ? num_kb : C::STAGES;
-      for (int kb = 0; kb < pre; ++kb) {
-        mbar_arrive_expect_tx(&full_bar[kb], C::A_BYTES + C::B_BYTES);
+    // ---- TMA producer (warp-uniform loop, one elected lane issues: see elect_one).  Weights do not depend on the
+    //      previous kernel: the first ring of W tiles is requested before griddepcontrol.wait, the activation tiles
+    //      after it. ----
+    auto load_a = [&](int st, int slot) {
+      if (KS == 1) tma_load_2d(sA + slot * C::A_BYTES, &tmA, &full_bar[slot], (kb0 + st) * C::BK, m0);
+      else tma_load_3d(sA + slot * C::A_BYTES, &tmA, &full_bar[slot], 0, m0, kb0 + st * KS);
+    };
+    auto load_w = [&](int st, int slot) {
+      if (KS == 1) {
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
-          tma_load_2d(sB + kb * C::B_BYTES + j * (64 * 128), &tmW, &full_bar[kb], (kb0 + kb) * C::BK, w_row_off + n0 + j * 64);
+          tma_load_2d(sB + slot * C::B_BYTES + j * (64 * 128), &tmW, &full_bar[slot], (kb0 + st) * C::BK, w_row_off + n0 + j * 64);
+      } else {
+        tma_load_3d(sB + slot * C::B_BYTES, &tmW, &full_bar[slot], 0, w_row_off + n0, kb0 + st * KS);
       }
-      pdl_wait();
-      for (int kb = 0; kb < pre; ++kb) tma_load_2d(sA + kb * C::A_BYTES, &tmA, &full_bar[kb], (kb0 + kb) * C::BK, m0);
-      for (int kb = pre; kb < num_kb; ++kb) {
-        const int s = kb % C::STAGES;
-        const uint32_t ph = (kb / C::STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    };
+    const int pre = num_st < C::STAGES ? num_st : C::STAGES;
+    if (elect_one()) {
+      for (int st = 0; st < pre; ++st) {
+        mbar_arrive_expect_tx(&full_bar[st], C::A_BYTES + C::B_BYTES);
+        load_w(st, st);
+      }
+    }
+    pdl_wait();
+    if (elect_one()) {
+      for (int st = 0; st < pre; ++st) load_a(st, st);
+    }
+    for (int st = pre; st < num_st; ++st) {
+      const int s = st % C::STAGES;
+      const uint32_t ph = (st / C::STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[s], C::A_BYTES + C::B_BYTES);
-        tma_load_2d(sA + s * C::A_BYTES, &tmA, &full_bar[s], (kb0 + kb) * C::BK, m0);
-#pragma unroll
-        for (int j = 0; j < BN / 64; ++j)
-          tma_load_2d(sB + s * C::B_BYTES + j * (64 * 128), &tmW, &full_bar[s], (kb0 + kb) * C::BK, w_row_off + n0 + j * 64);
+        load_a(st, s);
+        load_w(st, s);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---- MMA issuer ----
-      constexpr uint32_t idesc = umma_idesc_bf16(C::BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % C::STAGES;
-        const uint32_t ph = (kb / C::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint64_t da = umma_smem_desc_sw128(smem_u32(sA + s * C::A_BYTES));
-        const uint64_t db = umma_smem_desc_sw128(smem_u32(sB + s * C::B_BYTES));
+    // ---- MMA issuer (warp-uniform loop, the elected lane issues the MMAs and their commits) ----
+    constexpr uint32_t idesc = umma_idesc_bf16(C::BM, BN);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    for (int st = 0; st < num_st; ++st) {
+      const int s = st % C::STAGES;
+      const uint32_t ph = (st / C::STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < C::BK / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in the >>4 address field
-          umma_bf16(tmem_base, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                    (kb > 0 || k > 0) ? 1u : 0u);
+        for (int j = 0; j < KS; ++j) {
+          if (KS > 1 && st * KS + j >= num_kb) break;        // short last stage
+          const uint64_t da = umma_smem_desc_sw128(smem_u32(sA + s * C::A_BYTES + j * C::A_ATOM));
+          const uint64_t db = umma_smem_desc_sw128(smem_u32(sB + s * C::B_BYTES + j * C::B_ATOM));
+#pragma unroll
+          for (int k = 0; k < C::BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in the >>4 address field
+            umma_bf16(tmem_u, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                      (st > 0 || j > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
     }
+    if (elect_one()) umma_commit(tmem_full_bar);    // accumulator complete
   } else {
     // ---- epilogue: TMEM -> registers -> warp-private smem slab -> coalesced global ----
     pdl_wait();

@@ -48,7 +48,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform (role dispatch)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -85,20 +85,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---- TMA producer: tap (ky, kx) of a 3x3 kernel reads the activation matrix (ky-1) Wp + (kx-1) rows below the
-      //      output row; rows outside [0, R) are zero-filled by TMA.  Column tile fastest: the pairs working on the same
-      //      row block at the same time share its A tiles through L2. ----
-      const uint32_t stage_tx = 2u * static_cast<uint32_t>(CH_A_BYTES + bn * 64);
-      uint32_t g = 0;
-      for (int tile = pair; tile < total_tiles; tile += npairs) {
-        const int m0 = (tile / nt) * 256 + static_cast<int>(rank) * 128;
-        const int wrow = (tile % nt) * bn + static_cast<int>(rank) * (bn / 2);
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const int tap = kb / kpt, kc = kb - tap * kpt;
-          const int off = p.taps == 9 ? (tap / 3 - 1) * p.Wp + (tap % 3 - 1) : 0;
-          const int s = static_cast<int>(g % CH_STAGES);
-          mbar_wait(&empty_bar[s], ((g / CH_STAGES) & 1) ^ 1);
+    // ---- TMA producer (warp-uniform loop, one elected lane issues: see elect_one in common.cuh): tap (ky, kx) of a 3x3
+    //      kernel reads the activation matrix (ky-1) Wp + (kx-1) rows below the output row; rows outside [0, R) are
+    //      zero-filled by TMA.  Column tile fastest: the pairs working on the same row block at the same time share its
+    //      A tiles through L2. ----
+    const uint32_t stage_tx = 2u * static_cast<uint32_t>(CH_A_BYTES + bn * 64);
+    uint32_t g = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
+      const int m0 = (tile / nt) * 256 + static_cast<int>(rank) * 128;
+      const int wrow = (tile % nt) * bn + static_cast<int>(rank) * (bn / 2);
+      for (int kb = 0; kb < num_kb; ++kb, ++g) {
+        const int tap = kb / kpt, kc = kb - tap * kpt;
+        const int off = p.taps == 9 ? (tap / 3 - 1) * p.Wp + (tap % 3 - 1) : 0;
+        const int s = static_cast<int>(g % CH_STAGES);
+        mbar_wait(&empty_bar[s], ((g / CH_STAGES) & 1) ^ 1);
+        if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(&full_bar[s], stage_tx);
           tma_load_2d_2sm(smem + s * CH_STAGE_BYTES, &tmA, &full_bar[s], kc * 64, m0 + off);
           tma_load_2d_2sm(smem + s * CH_STAGE_BYTES + CH_A_BYTES, &tmW, &full_bar[s], kb * 64, wrow);
@@ -106,27 +107,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
+      // ---- MMA issuer (warp-uniform loop, the elected lane issues the MMAs and their commits) ----
       const uint32_t idesc = umma_idesc_bf16(256, bn);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t g = 0, it = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
         const uint32_t buf = it & 1;
         mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t acc = tmem_base + buf * CH_ACC_COLS;
+        const uint32_t acc = tmem_u + buf * CH_ACC_COLS;
         for (int kb = 0; kb < num_kb; ++kb, ++g) {
           const int s = static_cast<int>(g % CH_STAGES);
           mbar_wait(&full_bar[s], (g / CH_STAGES) & 1);
           tc_fence_after();
-          const uint64_t da = umma_smem_desc_sw128(smem_u32(smem + s * CH_STAGE_BYTES));
-          const uint64_t db = umma_smem_desc_sw128(smem_u32(smem + s * CH_STAGE_BYTES + CH_A_BYTES));
+          if (elect_one()) {
+            const uint64_t da = umma_smem_desc_sw128(smem_u32(smem + s * CH_STAGE_BYTES));
+            const uint64_t db = umma_smem_desc_sw128(smem_u32(smem + s * CH_STAGE_BYTES + CH_A_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_2sm(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[s], 0x3);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_2sm(acc, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[s], 0x3);
+          }
         }
-        umma_commit_2sm(&tmem_full_bar[buf], 0x3);
+        if (elect_one()) umma_commit_2sm(&tmem_full_bar[buf], 0x3);
       }
     }
   } else {
