@@ -75,6 +75,8 @@ PROTOTYPES = {
     "hq_bench_attention": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "hq_trace_run": (C.c_int, [C.c_void_p, C.POINTER(HQRunArgs), C.c_void_p, C.POINTER(C.c_uint64), C.c_char_p, C.c_int,
                                C.POINTER(C.c_int)]),
+    "hq_debug_gemm_phases": (C.c_int, [C.c_void_p, C.POINTER(HQRunArgs), C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_int,
+                                       C.POINTER(C.c_uint64), C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
     "hq_bench_gemm_shape": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                       C.POINTER(C.c_float), C.c_void_p]),
     "hq_bench_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
@@ -104,7 +106,10 @@ def load() -> C.CDLL:
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python hqtransformer_b200/build.py` "
             "(hqtransformer_b200 has no CPU or PyTorch fallback path)")
-    lib = C.CDLL(LIB_PATH)
+    path = LIB_PATH
+    if os.environ.get("HQ_DEBUG", "0") not in ("", "0") and os.environ.get("HQGRAFT_LIB"):
+        path = os.environ["HQGRAFT_LIB"]          # experiments only: an instrumented twin of the library (build.py --phase-stamps)
+    lib = C.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res

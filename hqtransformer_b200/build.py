@@ -35,22 +35,27 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, phase_stamps: bool = False) -> str:
+    """phase_stamps: the instrumented twin `libhqgraft_phases.so` (-DHQ_PHASE_STAMPS: per-CTA phase stamps of one GEMM launch
+    for scripts/gemm_phases.py, loaded with HQ_DEBUG=1 HQGRAFT_LIB=...; never the product library - the stamps cost 6 %)."""
+    out = LIB_PATH.replace(".so", "_phases.so") if phase_stamps else LIB_PATH
+    if not phase_stamps and not force and not needs_build():
         return LIB_PATH
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared"]
+    if phase_stamps:
+        cmd += ["-DHQ_PHASE_STAMPS"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB_PATH + ".tmp"]
+    cmd += [os.path.join(CSRC, f) for f in SOURCES] + ["-o", out + ".tmp"]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libhqgraft.so:\n" + res.stderr[-4000:])
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    return LIB_PATH
+    os.replace(out + ".tmp", out)
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, phase_stamps="--phase-stamps" in sys.argv))

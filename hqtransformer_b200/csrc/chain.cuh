@@ -207,7 +207,7 @@ __device__ __forceinline__ void chain_epilogue_tile(uint32_t tmem_base, uint8_t*
           bf16* dst;
           bf16* dup = nullptr;
           if (EPI == EPI_GELU) {
-            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+            v.x = gelu_bf16out(v.x); v.y = gelu_bf16out(v.y); v.z = gelu_bf16out(v.z); v.w = gelu_bf16out(v.w);   // bf16 output, as the per-op path
             dst = ep.out + row_a[it] + col;
           } else if (sec == 0) {
             dst = ep.q + row_a[it] + col;

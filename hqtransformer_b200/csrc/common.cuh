@@ -158,6 +158,23 @@ __device__ __forceinline__ void phase_mark(int p) {
 #endif
 }
 
+// The same stamps for ONE launch of a traced run (hq_debug_gemm_phases): the launch whose trace id is g_hq_phase_id.
+// Compiled in only with -DHQ_PHASE_STAMPS (python hqtransformer_b200/build.py --phase-stamps): a lane-dependent branch
+// inside the warp-uniform producer / MMA loops costs 6 % of the whole sampling step even when it is never taken (ptxas
+// falls back to the ELECT / R2UR waterfall around every UTCHMMA; 3 277 vs 3 065 images/s, profiles/r2_epilogue_ab.txt).
+// (its own buffer: other kernels stamp g_hq_phase unconditionally while it is set)
+__device__ int g_hq_phase_id = -1;
+__device__ unsigned long long* g_hq_gemm_phase = nullptr;
+__device__ __forceinline__ void phase_mark_if(bool on, int p) {
+#if defined(__CUDA_ARCH__) && defined(HQ_PHASE_STAMPS)
+  if (on && g_hq_gemm_phase != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_hq_gemm_phase[blockIdx.x * 16 + p] = t;
+  }
+#endif
+}
+
 // Programmatic dependent launch: wait for the producer grid's memory / let the dependent grid start its prologue
 __device__ __forceinline__ void pdl_wait() {
 #if defined(__CUDA_ARCH__)

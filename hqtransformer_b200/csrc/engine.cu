@@ -2422,4 +2422,34 @@ extern "C" int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, 
   return rc;
 }
 
+// hq_debug_gemm_phases: hq_trace_run in which ONE launch (trace id `launch_id`, a CTA-pair GEMM) also stamps its per-CTA
+// phases (gemm_tc2_kernel: 0 start, 1 prologue done, 2 dependency resolved, 3 first stage landed, 4 last MMA issued,
+// 5 accumulator complete, 6 epilogue done, 7 end); phases[cta * 8 + p] in ns of %globaltimer, 0 = not stamped.
+extern "C" int hq_debug_gemm_phases(hq_ctx* ctx, const hq_run_args* args, void* stream, int launch_id,
+                                    unsigned long long* phases, int max_ctas, unsigned long long* out_ns, char* tags,
+                                    int max_entries, int* n_entries) {
+  if (!ctx || !phases || max_ctas < 1 || launch_id < 0) return HQ_ERR_INVALID;
+  HQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  unsigned long long* dev = nullptr;
+  const size_t bytes = static_cast<size_t>(max_ctas) * 16 * sizeof(unsigned long long);
+  HQ_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&dev), bytes));
+  HQ_CUDA(ctx, cudaMemset(dev, 0, bytes));
+  HQ_CUDA(ctx, cudaMemcpyToSymbol(g_hq_gemm_phase, &dev, sizeof(dev)));
+  HQ_CUDA(ctx, cudaMemcpyToSymbol(g_hq_phase_id, &launch_id, sizeof(launch_id)));
+  int rc = hq_trace_run(ctx, args, stream, out_ns, tags, max_entries, n_entries);
+  unsigned long long* null_ptr = nullptr;
+  const int none = -1;
+  cudaMemcpyToSymbol(g_hq_gemm_phase, &null_ptr, sizeof(null_ptr));
+  cudaMemcpyToSymbol(g_hq_phase_id, &none, sizeof(none));
+  cudaError_t e = cudaSuccess;
+  if (rc == HQ_OK) e = cudaMemcpy(phases, dev, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  if (rc != HQ_OK) return rc;
+  if (e != cudaSuccess) {
+    set_err(ctx, "hq_debug_gemm_phases: %s", cudaGetErrorString(e));
+    return HQ_ERR_CUDA;
+  }
+  return HQ_OK;
+}
+
 #include "stage1_host.cuh"

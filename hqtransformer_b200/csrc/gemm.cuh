@@ -51,6 +51,27 @@ struct EpiParams {
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
+// The same function for outputs that are rounded to bf16 (the tcgen05 engine): x * Phi(x) with
+// Phi(x) = 1 - erfc(|x| / sqrt 2) / 2 (x >= 0), erfc(|x| / sqrt 2) / 2 (x < 0) and erfc by Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7 - five orders of magnitude below a bf16 ulp of the result): one rcp, one ex2 and a degree-5 Horner
+// form, ~15 instructions against ~35 for erff.  The exact-erf epilogue of fc1 was issue-bound on erff: 1.1 of the
+// 1.65 us per 32-column chunk, on the critical path of every fc1 launch (profiles/r2_gemm_phases.txt).  The fp32 engine
+// (bit-exact parity with the reference) keeps gelu_erf.
+__device__ __forceinline__ float gelu_bf16out(float v) {
+  const float z = fabsf(v) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  const float h = 0.5f * p * t * e;                                       // erfc(z) / 2
+  return v * (v >= 0.f ? 1.0f - h : h);
+}
+template <typename AT>
+__device__ __forceinline__ float gelu_for(float v) { return sizeof(AT) == 2 ? gelu_bf16out(v) : gelu_erf(v); }
+
 // 8 consecutive columns n0..n0+7 of row m (n0 % 8 == 0, all < N)
 template <int EPI, typename AT>
 __device__ __forceinline__ void epi_store8(const EpiParams<AT>& ep, int m, int n0, int N, float (&v)[8]) {
@@ -108,7 +129,7 @@ __device__ __forceinline__ void epi_store8(const EpiParams<AT>& ep, int m, int n
 template <int BN, int EPI, typename AT, int NW = 4>
 __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, uint8_t* slab_base, float* sbias, int warp, int lane,
                                               int m0, int n0, int M, int N, const EpiParams<AT>& ep,
-                                              uint64_t* tmem_full_bar, uint32_t full_parity = 0, int ew = -1) {
+                                              uint64_t* tmem_full_bar, uint32_t full_parity = 0, int ew = -1, bool pm = false) {
   const int quarter = warp & 3;
   if (ew < 0) ew = quarter;
   const int half = ew >> 2;
@@ -119,37 +140,64 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, uint8_t* slab_
     if (NW == 8) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
     for (int i = etid; i < BN; i += NW * 32) sbias[i] = (n0 + i < N) ? ep.bias[n0 + i] : 0.f;
   }
-  // rows this lane writes: it*4 + (lane >> 3) of the warp's 32; destination row offsets (elements) per row
+  // rows this lane writes: it*4 + (lane >> 3) of the warp's 32; destination row offsets (elements) per row.
+  // Computed ONCE per tile, here, while the main loop still runs, and then made opaque to the compiler: left alone,
+  // nvcc re-materialised the divisions of the KV-cache row (m / rpb, m % rpb) and of the q/k/v section inside every one
+  // of the 8 write-out iterations, each behind its own branch - ~180 dependent clocks per iteration, 0.7-1.7 us per
+  // 32-column chunk on the critical path of EVERY GEMM launch (profiles/r2_gemm_phases.txt: parked -> stored).
   const int piece = lane & 7;
   size_t row_a[8], row_b[8];
   bool row_ok[8];
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int m = m0 + quarter * 32 + it * 4 + (lane >> 3);
-    row_ok[it] = m < M;
+  {
+    const int mbase = m0 + quarter * 32 + (lane >> 3);
+    int kb = 0, kr = 0;                                          // image / row within the image of row m (EPI_QKV)
     if (EPI == EPI_QKV) {
-      row_a[it] = static_cast<size_t>(m) * ep.D;                                                        // q / vdup row
-      row_b[it] = (static_cast<size_t>(m / ep.rpb) * ep.t_stride + ep.t0 + (m % ep.rpb)) * ep.D;       // k / v row
-    } else if (EPI == EPI_F32) {
-      row_a[it] = static_cast<size_t>(m) * ep.ldo;
-      row_b[it] = 0;
-    } else {
-      row_a[it] = static_cast<size_t>(m) * N;
-      row_b[it] = 0;
+      kb = mbase / ep.rpb;
+      kr = mbase - kb * ep.rpb;
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int m = mbase + it * 4;
+      row_ok[it] = m < M;
+      if (EPI == EPI_QKV) {
+        row_a[it] = static_cast<size_t>(m) * ep.D;                                                    // q / vdup row
+        row_b[it] = (static_cast<size_t>(kb) * ep.t_stride + ep.t0 + kr) * ep.D;                      // k / v row
+        kr += 4;                                                                                       // next row: m + 4
+        while (kr >= ep.rpb) {
+          kr -= ep.rpb;
+          ++kb;
+        }
+      } else if (EPI == EPI_F32) {
+        row_a[it] = static_cast<size_t>(m) * ep.ldo;
+        row_b[it] = 0;
+      } else {
+        row_a[it] = static_cast<size_t>(m) * N;
+        row_b[it] = 0;
+      }
+      asm volatile("" : "+l"(row_a[it]), "+l"(row_b[it]));
     }
   }
   // sbias visible to all epilogue warps
   if (NW == 8) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
   mbar_wait(tmem_full_bar, full_parity);
+  if (warp == 2 && lane == 0) phase_mark_if(pm, 5);
   tc_fence_after();
 
   uint8_t* slab = slab_base + ew * 4096;                       // this warp's 32 rows x 128 B
   const uint32_t slab_u32 = smem_u32(slab);
+  // shared-memory addresses of this lane's 8 pieces (row it*4 + (lane >> 3), 16-byte piece XOR-swizzled by row)
+  uint32_t rd_addr[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + (lane >> 3);
+    rd_addr[it] = slab_u32 + row * 128 + ((piece ^ (row & 7)) << 4);
+  }
 #pragma unroll 1
   for (int c = (NW == 8 ? half : 0); c < BN / 32; c += (NW == 8 ? 2 : 1)) {
     uint32_t r[32];
     tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c * 32), r);
     tmem_ld_wait();
+    if (warp == 2 && lane == 0 && c == 0) phase_mark_if(pm, 8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {                              // row = lane; piece j -> slot j ^ (lane & 7)
       const uint32_t addr = slab_u32 + lane * 128 + ((j ^ (lane & 7)) << 4);
@@ -158,59 +206,77 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tmem_base, uint8_t* slab_
                    : "memory");
     }
     __syncwarp();
+    if (warp == 2 && lane == 0 && c == 0) phase_mark_if(pm, 9);
     const int nb = n0 + c * 32;                                // chunk base column (a chunk never straddles q/k/v)
     const int n = nb + piece * 4;
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_bias) b4 = *reinterpret_cast<const float4*>(sbias + c * 32 + piece * 4);
-    // chunk-uniform destination selection
-    int sec = 0, col = n;
+    // chunk-uniform destination: base pointer of column `col`, which of the two row-offset sets, optional second copy
+    AT* dst = nullptr;
+    AT* dup = nullptr;
+    float* dstf = nullptr;
+    bool use_b = false;
     if (EPI == EPI_QKV) {
-      sec = ep.sec0 + nb / ep.D;
-      col = nb % ep.D + piece * 4;
+      const int s1 = nb >= ep.D ? 1 : 0, s2 = nb >= 2 * ep.D ? 1 : 0;   // section within the fused columns, no division
+      const int sec = ep.sec0 + s1 + s2;
+      const int col = nb - (s1 + s2) * ep.D + piece * 4;
+      use_b = sec != 0;
+      dst = (sec == 0 ? ep.q : (sec == 1 ? ep.kdst : ep.vdst)) + col;
+      if (sec == 2 && ep.vdup != nullptr) dup = ep.vdup + col;
+    } else if (EPI == EPI_GELU) {
+      dst = ep.out + n;
+    } else if (EPI == EPI_RESID) {
+      dstf = ep.x + n;
+    } else {
+      dstf = ep.outf + n;
     }
     if (n < N) {
+      float4 v[8];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int row = it * 4 + (lane >> 3);
-        float4 v;
-        const uint32_t addr = slab_u32 + row * 128 + ((piece ^ (row & 7)) << 4);
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-        if (!row_ok[it]) continue;
-        if (EPI == EPI_F32) {
-          *reinterpret_cast<float4*>(ep.outf + row_a[it] + col) = v;
-        } else if (EPI == EPI_RESID) {
-          float4* p = reinterpret_cast<float4*>(ep.x + row_a[it] + col);
-          float4 a = *p;
-          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-          *p = a;
-        } else {
-          AT* dst;
-          AT* dup = nullptr;
-          if (EPI == EPI_GELU) {
-            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-            dst = ep.out + row_a[it] + col;
-          } else if (sec == 0) {
-            dst = ep.q + row_a[it] + col;
-          } else {
-            dst = (sec == 1 ? ep.kdst : ep.vdst) + row_b[it] + col;
-            if (sec == 2 && ep.vdup != nullptr) dup = ep.vdup + row_a[it] + col;
+      for (int it = 0; it < 8; ++it)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[it].x), "=f"(v[it].y), "=f"(v[it].z), "=f"(v[it].w) : "r"(rd_addr[it]));
+      if (EPI == EPI_RESID) {
+        float4 x4[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (row_ok[it]) x4[it] = *reinterpret_cast<const float4*>(dstf + row_a[it]);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          if (row_ok[it]) {
+            float4 a = x4[it];
+            a.x += v[it].x + b4.x; a.y += v[it].y + b4.y; a.z += v[it].z + b4.z; a.w += v[it].w + b4.w;
+            *reinterpret_cast<float4*>(dstf + row_a[it]) = a;
           }
-          if (sizeof(AT) == 4) {
-            *reinterpret_cast<float4*>(dst) = v;
-            if (dup != nullptr) *reinterpret_cast<float4*>(dup) = v;
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          float4 w = v[it];
+          w.x += b4.x; w.y += b4.y; w.z += b4.z; w.w += b4.w;
+          if (EPI == EPI_GELU) {
+            w.x = gelu_for<AT>(w.x); w.y = gelu_for<AT>(w.y); w.z = gelu_for<AT>(w.z); w.w = gelu_for<AT>(w.w);
+          }
+          if (EPI == EPI_F32) {
+            if (row_ok[it]) *reinterpret_cast<float4*>(dstf + row_a[it]) = w;
           } else {
-            uint2 u;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-            u.x = *reinterpret_cast<uint32_t*>(&h0);
-            u.y = *reinterpret_cast<uint32_t*>(&h1);
-            *reinterpret_cast<uint2*>(dst) = u;
-            if (dup != nullptr) *reinterpret_cast<uint2*>(dup) = u;
+            const size_t ro = use_b ? row_b[it] : row_a[it];
+            if (sizeof(AT) == 4) {
+              if (row_ok[it]) *reinterpret_cast<float4*>(dst + ro) = w;
+              if (row_ok[it] && dup != nullptr) *reinterpret_cast<float4*>(dup + row_a[it]) = w;
+            } else {
+              uint2 u;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(w.x, w.y), h1 = __floats2bfloat162_rn(w.z, w.w);
+              u.x = *reinterpret_cast<uint32_t*>(&h0);
+              u.y = *reinterpret_cast<uint32_t*>(&h1);
+              if (row_ok[it]) *reinterpret_cast<uint2*>(dst + ro) = u;
+              if (row_ok[it] && dup != nullptr) *reinterpret_cast<uint2*>(dup + row_a[it]) = u;
+            }
           }
         }
       }
     }
     __syncwarp();
+    if (warp == 2 && lane == 0 && c == 0) phase_mark_if(pm, 10);
   }
 }
 #endif
@@ -524,6 +590,14 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
   const int num_kb = (K / C::BK) / splits;               // 64-wide k-blocks per tile
   const int num_st = (num_kb + KS - 1) / KS;             // ring stages per tile (KS k-blocks each; the last may be short)
 
+  // hq_debug_gemm_phases: per-CTA %globaltimer stamps of this launch (0 start, 1 prologue done, 2 dependency resolved,
+  // 3 first stage landed, 4 last MMA issued, 5 accumulator complete, 6 epilogue done, 7 end)
+#if defined(HQ_PHASE_STAMPS)
+  const bool pm = trace_id >= 0 && trace_id == g_hq_phase_id;
+#else
+  constexpr bool pm = false;
+#endif
+  if (threadIdx.x == 0) phase_mark_if(pm, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
@@ -548,6 +622,7 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
   cluster_sync_all();                 // peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) phase_mark_if(pm, 1);
 
   pdl_launch_dependents();
   if (warp == 0) {
@@ -583,6 +658,7 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
           }
         }
         pdl_wait();
+        if (lane == 0) phase_mark_if(pm, 2);
         if (elect_one()) {
           for (int k2 = 0; k2 < pre; ++k2) load_a(k2, k2);
         }
@@ -627,6 +703,7 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
           const long long c0 = prof ? clock64() : 0;
           mbar_wait(&full_bar[s], ph);
           const long long c1 = prof ? clock64() : 0;
+          if (g == 0 && lane == 0) phase_mark_if(pm, 3);
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
@@ -645,6 +722,7 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
         }
         if (prof && lane == 0) { ep.prof[4] = m_wait; ep.prof[5] = m_issue; ep.prof[6] = 0; ep.prof[7] = clock64() - m_t0; ep.prof[8] = num_st; }
         if (elect_one()) umma_commit_2sm(&tmem_full_bar[buf], 0x3);   // both CTAs' accumulators of this tile are complete
+        if (lane == 0) phase_mark_if(pm, 4);
       }
     }
   } else {
@@ -664,9 +742,10 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
       else
         epilogue_tile<BN, EPI, AT, C::EPI_WARPS>(tmem_base + static_cast<uint32_t>(buf * C::ACC_COLS), slab, sbias, warp, lane, m0,
                                                  n0, M, N, ept, &tmem_full_bar[buf], (it >> 1) & 1,
-                                                 (warp & 3) + ((warp - 2) >> 2) * 4);
+                                                 (warp & 3) + ((warp - 2) >> 2) * 4, pm);
       tc_fence_before();
       __syncwarp();
+      if (warp == 2 && lane == 0) phase_mark_if(pm, 6);
       if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[buf], 0);   // this warp is done with the accumulator
     }
   }
@@ -676,6 +755,7 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
   }
+  if (threadIdx.x == 0) phase_mark_if(pm, 7);
 #endif
 }
 

@@ -193,6 +193,25 @@ class Engine:
         return [(raw[48 * i:48 * i + 48].split(b"\0")[0].decode(), int(out[2 * i]), int(out[2 * i + 1]))
                 for i in range(n.value)]
 
+    def gemm_phases(self, *, launch_id: int, batch: int, seq_len: int, pos_begin: int, pos_end: int, sampling: SamplingParams,
+                    cond: Optional[torch.Tensor], codes_top: torch.Tensor, codes_bot: torch.Tensor, max_ctas: int = 160,
+                    max_entries: int = 16384):
+        """hq_debug_gemm_phases: (timeline as trace_run, int64 [max_ctas, 16] per-CTA phase stamps of launch `launch_id`)."""
+        import numpy as np
+        args = HQRunArgs(batch=batch, seq_len=seq_len, pos_begin=pos_begin, pos_end=pos_end, cond=_ptr(cond), sos=None,
+                         given_top=None, given_bot=None, codes_top=_ptr(codes_top), codes_bot=_ptr(codes_bot),
+                         logits=None, sampling=sampling.to_c())
+        out = (C.c_uint64 * (2 * max_entries))()
+        tags = C.create_string_buffer(48 * max_entries)
+        ph = (C.c_uint64 * (max_ctas * 16))()
+        n = C.c_int()
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        check(self._lib.hq_debug_gemm_phases(self._ctx, C.byref(args), C.c_void_p(st), launch_id, ph, max_ctas, out, tags,
+                                             max_entries, C.byref(n)), self._ctx, "hq_debug_gemm_phases")
+        raw = tags.raw
+        tl = [(raw[48 * i:48 * i + 48].split(b"\0")[0].decode(), int(out[2 * i]), int(out[2 * i + 1])) for i in range(n.value)]
+        return tl, np.frombuffer(ph, dtype=np.uint64).reshape(max_ctas, 16).astype(np.int64)
+
     def bench_attention(self, batch: int, n_keys: int, iters: int = 50) -> float:
         """Mean microseconds of one single-query KV-cache attention launch (CUDA events on the current stream)."""
         us = C.c_float()

@@ -256,6 +256,13 @@ int hq_bench_gemm(hq_ctx* ctx, int kind, int M, int iters, float* usec, void* st
 int hq_trace_run(hq_ctx* ctx, const hq_run_args* args, void* stream, unsigned long long* out_ns, char* tags,
                  int max_entries, int* n_entries);
 
+/* hq_trace_run in which the launch with trace index `launch_id` (a CTA-pair GEMM) also stamps its per-CTA phases:
+ * phases[16*c + p] = %globaltimer (ns) of CTA c at p = 0 start, 1 prologue done, 2 dependency resolved (griddepcontrol.wait
+ * returned), 3 first ring stage landed, 4 last MMA issued, 5 accumulator complete, 6 epilogue done, 7 end, 8 / 9 / 10 first epilogue
+ * chunk read from TMEM / parked in shared memory / stored; 0 = not stamped.  `phases` holds 16 * max_ctas values. */
+int hq_debug_gemm_phases(hq_ctx* ctx, const hq_run_args* args, void* stream, int launch_id, unsigned long long* phases,
+                         int max_ctas, unsigned long long* out_ns, char* tags, int max_entries, int* n_entries);
+
 /* Stand-alone timing of the bf16 GEMM kernels on synthetic operands of any shape / tile (see hq_debug_gemm for
  * `tile`).  flush: 0 none (cycles `copies` weight buffers), 1 = 256 MB memset before each launch, 2 = 256 MB read
  * sweep before each launch.  Per-launch CUDA-event times; mean and min in microseconds. */

@@ -170,6 +170,76 @@ static void run(int cs, int grid, int w_rows, int shared_rows, int stages, int a
   fflush(stdout);
 }
 
+
+// ---- weight-stream mode: every CTA streams ITS OWN tiles (64 rows x 2 k-blocks = 16 KB per instruction) of a 1.2 GB
+//      [N, K = 1536] bf16 matrix once (DRAM, not L2), as the GEMMs read their W operand.  Two layouts of the same data:
+//      row-major [N][K] (a tile = 64 pieces of 256 B at a 3 KB stride) and k-block-major [K/64][N][64] (a tile = 2
+//      contiguous 8 KB pieces).
+__global__ void __launch_bounds__(64, 1)
+wstream_kernel(const __grid_constant__ CUtensorMap tmW, int STAGES, int row_blocks, int kpairs) {
+#if defined(__CUDA_ARCH__)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * 16384);
+  uint64_t* empty = full + MAXSTAGES;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int smask = STAGES - 1, sshift = 31 - __clz(STAGES);
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  int i = 0;
+  if (warp == 0) {
+    for (int rb = blockIdx.x; rb < row_blocks; rb += gridDim.x)
+      for (int kp = 0; kp < kpairs; ++kp, ++i) {
+        const int s = i & smask;
+        mbar_wait(&empty[s], ((i >> sshift) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[s], 16384);
+          tma_load_3d(smem + s * 16384, &tmW, &full[s], 0, rb * 64, kp * 2);
+        }
+      }
+  } else {
+    for (int rb = blockIdx.x; rb < row_blocks; rb += gridDim.x)
+      for (int kp = 0; kp < kpairs; ++kp, ++i) {
+        const int s = i & smask;
+        mbar_wait(&full[s], (i >> sshift) & 1);
+        if (elect_one()) mbar_arrive(&empty[s]);
+      }
+  }
+#endif
+}
+
+static void run_wstream(PFN_encodeTiled fn, void* buf, uint64_t N, uint64_t K, int packed, int stages, int grid) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {64, N, K / 64};
+  cuuint64_t strides_rm[2] = {K * 2, 128};
+  cuuint64_t strides_pk[2] = {128, N * 128};
+  cuuint32_t box[3] = {64, 64, 2};
+  cuuint32_t el[3] = {1, 1, 1};
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, buf, dims, packed ? strides_pk : strides_rm, box, el,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { printf("encode (wstream) failed %d\n", (int)r); return; }
+  const int smem = stages * 16384 + 1024 + 512;
+  CK(cudaFuncSetAttribute(wstream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(e0));
+    wstream_kernel<<<grid, 64, smem>>>(m, stages, (int)(N / 64), (int)(K / 128));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  printf("  wstream %-12s stages %2d ctas %3d: %8.3f ms  %8.1f GB/s\n", packed ? "kblock-major" : "row-major", stages, grid, best,
+         (double)N * K * 2 / best / 1e6);
+  fflush(stdout);
+}
 int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 4800;
   const int K = 1536, rows = 4096;
@@ -206,5 +276,18 @@ int main(int argc, char** argv) {
     }
   // 4. private rows instead of shared ones
   run(1, 144, 0, 0, 8, 128, iters);
+  // 5. the W operand from DRAM: row-major vs k-block-major tiles
+  {
+    const uint64_t N = 393216, K = 1536;
+    void* big;
+    CK(cudaMalloc(&big, N * K * 2));
+    CK(cudaMemset(big, 0, N * K * 2));
+    for (int packed = 0; packed < 2; ++packed)
+      for (int stages = 2; stages <= 8; stages *= 2) {
+        run_wstream(g_fn, big, N, K, packed, stages, 144);
+        run_wstream(g_fn, big, N, K, packed, stages, 288);
+      }
+    CK(cudaFree(big));
+  }
   return 0;
 }
