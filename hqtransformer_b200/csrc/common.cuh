@@ -375,6 +375,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution barrier only (no memory ordering): for a tear-down in which nothing written by this thread is read by the peer
+// afterwards.  The release form makes every thread wait for its global stores to drain before it may arrive.
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 // TMA tile load into THIS CTA's shared memory whose transaction bytes are credited to the mbarrier at the same
 // offset in the pair's leader CTA (peer bit of the shared::cluster address cleared).
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {

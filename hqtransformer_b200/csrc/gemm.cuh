@@ -746,11 +746,16 @@ gemm_tc2_kernel(int trace_id, const __grid_constant__ CUtensorMap tmA, const __g
       tc_fence_before();
       __syncwarp();
       if (warp == 2 && lane == 0) phase_mark_if(pm, 6);
-      if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[buf], 0);   // this warp is done with the accumulator
+      // this warp is done with the accumulator (nobody waits for that after the pair's last tile: no remote signal then,
+      // so that the tear-down barrier below needs no memory ordering)
+      if (lane == 0 && tile + npairs < total_tiles) mbar_arrive_remote(&tmem_empty_bar[buf], 0);
     }
   }
   __syncwarp();
-  cluster_sync_all();                 // the peer may still be reading this CTA's smem / signalling its barriers
+  // Both CTAs are done with each other's shared memory and TMEM before either frees them.  Execution barrier only: the
+  // last cross-CTA signals (the leader's multicast commits) were consumed by the waits above; with the release form every
+  // epilogue thread first waited here for its global stores to drain.
+  cluster_sync_relaxed();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);

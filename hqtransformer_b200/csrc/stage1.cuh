@@ -225,11 +225,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[buf], 0);
+      // no remote signal after the pair's last tile (nobody waits for it): the tear-down barrier below then needs no
+      // memory ordering, and the epilogue threads do not wait there for their global stores to drain (see gemm_tc2_kernel)
+      if (lane == 0 && tile + npairs < total_tiles) mbar_arrive_remote(&tmem_empty_bar[buf], 0);
     }
   }
   __syncwarp();
-  cluster_sync_all();
+  cluster_sync_relaxed();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, 2 * CH_ACC_COLS);
