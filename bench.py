@@ -58,14 +58,47 @@ def parse_args():
 # clocks
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples `nvidia-smi` SM clocks and throttle reasons of one GPU while the timed region runs."""
+    """Samples SM clocks and throttle reasons of one GPU while the timed region runs: NVML in-process every 20 ms (a short
+    timed region still gets samples), `nvidia-smi -lms 100` as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.stop_flag, self.sm, self.mx, self.reasons = None, None, False, [], None, set()
+
+    def _nvml_loop(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                for bit, name in self.NVML_REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -80,6 +113,12 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "samples": len(sm),
+                    "reasons": sorted(self.reasons), "how": "NVML, 20 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -99,7 +138,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons),
+                "how": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
