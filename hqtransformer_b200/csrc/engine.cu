@@ -106,7 +106,6 @@ struct DebugSwitches {
   int chain_no_l2pf = 0;       // HQ_CHAIN_NO_L2PF: chain kernel without the L2 prefetch of later weight tiles
   int gemm_ks1 = 0;            // HQ_GEMM_KS1: pair GEMM with one k-block per ring stage (2-D boxes) everywhere
   int bn_m256 = 0;             // HQ_BN_M256: pinned pair-tile width of the unsplit GEMMs with M <= 256 (plan experiments)
-  int no_carveout = 0;         // HQ_NO_CARVEOUT: leave the small kernels' shared-memory carve-out to the driver
 };
 
 static int env_int(const char* name) {
@@ -136,7 +135,6 @@ static DebugSwitches read_debug_switches() {
   d.chain_no_l2pf = getenv("HQ_CHAIN_NO_L2PF") != nullptr;
   d.gemm_ks1 = getenv("HQ_GEMM_KS1") != nullptr;
   d.bn_m256 = env_int("HQ_BN_M256");
-  d.no_carveout = getenv("HQ_NO_CARVEOUT") != nullptr;
   return d;
 }
 
@@ -416,31 +414,6 @@ static int set_gemm_attrs(hq_ctx* ctx) {
   return HQ_OK;
 }
 
-// The small kernels between two GEMMs (LayerNorm, depth attention, embeddings, sampler tails) ask for the SAME L1 / shared
-// memory split as the GEMMs (maximum shared memory).  With the driver's default - the smallest carve-out that fits their
-// few bytes - an SM that holds one of their CTAs cannot take the next GEMM's 200 KB CTA until it is empty and has been
-// reconfigured, so under programmatic dependent launch the GEMM CTAs only became resident around the END of the kernel
-// before them (profiles/r2_gemm_phases.txt: CTA starts spread over 3.5 us) instead of waiting, prologue done, for it.
-template <typename K>
-static void prefer_max_shared(K kernel) {
-  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-}
-static void set_carveouts(hq_ctx* ctx) {
-  if (ctx->dbg.no_carveout) return;
-  prefer_max_shared(layernorm_kernel<bf16, 3>);
-  prefer_max_shared(layernorm_kernel<bf16, LN_MAXFOLD>);
-  prefer_max_shared(layernorm_kernel<float, 3>);
-  prefer_max_shared(layernorm_kernel<float, LN_MAXFOLD>);
-  prefer_max_shared(attention_depth4_kernel<bf16>);
-  prefer_max_shared(attention_depth4_kernel<float>);
-  prefer_max_shared(attention_decode_mma_kernel);
-  prefer_max_shared(embed_kernel);
-  prefer_max_shared(embed_depth_kernel);
-  prefer_max_shared(embed_txt_kernel);
-  prefer_max_shared(sample_finalize_kernel);
-  cudaGetLastError();
-}
-
 static int get_encode_fn(hq_ctx* ctx, PFN_encodeTiled* fn) {
   void* p = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -688,7 +661,6 @@ static int create_impl(hq_ctx* ctx, const hq_config* cfg, int device, int max_ba
   if ((rc = set_smem(ctx, attention_decode_kernel<bf16>, 64 * 1024))) return rc;
   if ((rc = set_smem(ctx, attention_decode_kernel<float>, 64 * 1024))) return rc;
   if ((rc = set_smem(ctx, attention_decode_mma_kernel, 112 * 1024))) return rc;
-  set_carveouts(ctx);
   if ((rc = dev_alloc(ctx, reinterpret_cast<void**>(&ctx->att_sched), 16))) return rc;
   HQ_CUDA(ctx, cudaMemset(ctx->att_sched, 0, 16));
   HQ_CUDA(ctx, cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device));
