@@ -7,7 +7,7 @@ import torch
 import hqtransformer_b200 as H
 from hqtransformer_b200.engine import SamplingParams
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 256
 cfg = os.path.join(os.path.dirname(H.__file__), "configs", "imagenet_l12.yaml")
 model = H.ImageGPT2(H.load_config(cfg), device=0, precision="bf16", max_batch=B)
 model.stage2.init_weights(0)
@@ -36,6 +36,10 @@ for i in range(per_pos + 20, 2 * per_pos + 20):          # the middle position, 
     nxt = t2[i + 1]
     print(f"{tag}  (prev: {t2[i-1][0]}; {len(ph)} CTAs)  kernel span {(t2[i][1]-prev_end)/1e3:+.2f} .. {(t2[i][2]-prev_end)/1e3:+.2f} us; "
           f"next {nxt[0]} starts {(nxt[1]-prev_end)/1e3:+.2f} ends {(nxt[2]-prev_end)/1e3:+.2f}")
+    if "--per-cta" in sys.argv and ("gemm_qkv:256x4608" in tag or "gemm_resid:256x1536x1536" in tag or "gemm_fc1_gelu:256" in tag or "gemm_resid:256x1536x6144" in tag):
+        # CTA index -> start / dependency resolved / end: is the pair grid dispatched in index order, and how fast?
+        print("    cta: start dep_resolved end   " + "  ".join(
+            f"{c}:{(ph[c,0]-prev_end)/1e3:+.2f}/{(ph[c,2]-prev_end)/1e3:+.2f}/{(ph[c,7]-prev_end)/1e3:+.2f}" for c in range(0, len(ph), 8)))
     for p, nm in enumerate(names):
         v = ph[:, p]
         v = v[v > 0]
