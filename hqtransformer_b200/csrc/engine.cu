@@ -1352,8 +1352,12 @@ struct Fc2Plan { int bn, splits; };
 // the batch therefore makes a row's result independent of the batch it sits in - and of how a batch is sharded over GPUs.
 static int resid_splits(const hq_ctx* ctx, int N, int K, int rows_per_image) {
   static const int cand[6] = {256, 192, 128, 96, 64, 32};
-  const int max_splits = ctx->dbg.max_splitk > 0 ? ctx->dbg.max_splitk : LN_MAXFOLD;
   const int kb = K / 64;
+  // At most 3 slices where 3 divides the k-blocks (every D = 1536 model): measured on the final kernels with the factor
+  // pinned for all residual GEMMs (profiles/r2_splitk_final.txt), 3 beats the model's 6 for fc2 at 256 rows end to end
+  // (3 482 vs 3 459 images/s) - half the fp32 partial bytes, one epilogue chunk per warp, and the LayerNorm behind it is the
+  // 3-fold instantiation (112 instead of 152 registers: more of the next GEMM's CTAs become resident next to it).
+  const int max_splits = ctx->dbg.max_splitk > 0 ? ctx->dbg.max_splitk : (kb % 3 == 0 ? 3 : LN_MAXFOLD);
   int best = 1;
   double best_cost = 1e30;
   for (int bn : cand) {
