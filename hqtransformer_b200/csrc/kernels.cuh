@@ -1258,19 +1258,41 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 4 : 1) sample_kernel(int t
   }
 
   // ---- top-k: threshold = k-th largest value, ties kept (sampling.py:17-18) ----
+  // 32-step bitwise bisection on the order-preserving integer image of the logits.  The image is computed ONCE (it lives in
+  // z's registers for the duration of the search) and a step costs 32 compares, one redux.sync, one shared-memory atomic per
+  // warp and ONE __syncthreads (three rotating counters): the first version re-derived the image in every step and paid a
+  // three-barrier, two-level shuffle reduction per step - 58 us per launch at top-k 2048 (profiles/r2_configs_final.txt).
   if (top_k > 0 && top_k < V) {
+    __shared__ int cnt3[3];
+    const int lane = tid & 31;
+#pragma unroll
+    for (int i = 0; i < SMP_IPT; ++i) z[i] = __uint_as_float(float_order_key(z[i]));
+    if (tid < 3) cnt3[tid] = 0;
+    __syncthreads();
     uint32_t thr = 0;
+    int buf = 0;
     for (int bit = 31; bit >= 0; --bit) {
       const uint32_t cand = thr | (1u << bit);
       int cnt = 0;
 #pragma unroll
-      for (int i = 0; i < SMP_IPT; ++i) cnt += (float_order_key(z[i]) >= cand) ? 1 : 0;
-      cnt = block_reduce(cnt, OpSumI(), 0, iscratch);
-      if (cnt >= top_k) thr = cand;
+      for (int i = 0; i < SMP_IPT; ++i) cnt += (__float_as_uint(z[i]) >= cand) ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (lane == 0) atomicAdd(&cnt3[buf], cnt);
+      __syncthreads();
+      const int total = cnt3[buf];
+      // the counter of the step before this one was last read before this step's barrier and is next added to after the
+      // next step's barrier: thread 0 clears it in between
+      const int prev = buf == 0 ? 2 : buf - 1;
+      if (tid == 0) cnt3[prev] = 0;
+      buf = buf == 2 ? 0 : buf + 1;
+      if (total >= top_k) thr = cand;
     }
 #pragma unroll
-    for (int i = 0; i < SMP_IPT; ++i)
-      if (float_order_key(z[i]) < thr) z[i] = -INFINITY;
+    for (int i = 0; i < SMP_IPT; ++i) {
+      const uint32_t k = __float_as_uint(z[i]);
+      // back from the image: keys with the top bit set were non-negative floats (bit flipped), the others negative (all flipped)
+      z[i] = (k < thr) ? -INFINITY : __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+    }
   }
 
   // ---- softmax (F.softmax, hierarchical_ar.py:765), in place: z[] becomes the probabilities ----
@@ -1289,14 +1311,25 @@ __global__ void __launch_bounds__(NTHR, NTHR == 256 ? 4 : 1) sample_kernel(int t
   // ---- top-p (sampling.py:22-37): keep the smallest upper set {p_i >= c*} whose mass reaches p; among
   //      entries equal to c* keep, in index order, those whose preceding cumulative mass is still < p ----
   if (top_p > 0.f && top_p < 1.f) {
+    // 31-step bisection on the kept mass: per step a warp shuffle tree, one partial per warp into a double-buffered array,
+    // ONE __syncthreads, and every thread adds the partials in warp order (fixed order: deterministic)
+    __shared__ float part2[2][32];
+    const int lane_p = tid & 31, w_p = tid >> 5, nw_p = nthr >> 5;
     uint32_t cstar = 0;
+    int pbuf = 0;
     for (int bit = 30; bit >= 0; --bit) {   // probabilities are non-negative: sign bit never set
       const uint32_t cand = cstar | (1u << bit);
       float mass = 0.f;
 #pragma unroll
       for (int i = 0; i < SMP_IPT; ++i) mass += (__float_as_uint(wgt[i]) >= cand) ? wgt[i] : 0.f;
-      mass = block_reduce(mass, OpSumF(), 0.f, fscratch);
-      if (mass >= top_p) cstar = cand;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mass += __shfl_xor_sync(0xffffffffu, mass, o);
+      if (lane_p == 0) part2[pbuf][w_p] = mass;
+      __syncthreads();
+      float tot = 0.f;
+      for (int k2 = 0; k2 < nw_p; ++k2) tot += part2[pbuf][k2];
+      pbuf ^= 1;
+      if (tot >= top_p) cstar = cand;
     }
     float above = 0.f;
     int ties = 0;
