@@ -1048,8 +1048,11 @@ static double pair_gemm_cost(int M, int N, int K, int bn, int splits) {
   const int pairs = ((M + 255) / 256) * (N / bn) * splits;
   const double waves = static_cast<double>((pairs + 73) / 74);
   const double ingest = (16384.0 + 64.0 * bn) / 42.6, mma = 2.0 * bn;
+  // split-K slices also write M x N fp32 partials each (L2 write bandwidth, ~40 B/clk/SM: the term that makes 2 slices
+  // beat 3 for proj at 1024 rows, 8.3 vs 9.3 us, profiles/r2_splitk_final.txt)
+  const double partials = splits > 1 ? static_cast<double>(M) * N * 4.0 * splits / 5920.0 : 0.0;
   return waves * ((K / 64 / splits) * (ingest > mma ? ingest : mma) + 11000.0) + (splits > 1 ? 400.0 * splits : 0.0) +
-         16.0 * bn;
+         partials + 16.0 * bn;
 }
 
 // Width of the CTA-pair tile (256 x BN) for an [M, N] output
