@@ -451,6 +451,10 @@ static int attn_groups(const hq_ctx* ctx, int nh) {
   int g = 0;
   for (int cand : {4, 3, 2, 1})
     if (nh % cand == 0 && nh / cand <= ATTD_MAXHPC) { g = cand; break; }
+  // three heads per item where the head count allows it (24 heads: 8 groups, 2048 items at B = 256): the finer items balance
+  // the tail of the launch better - 13.4 -> 12.8 us at 32 keys, +0.4-1.0 % end to end; 2, 4 or 12 heads per item measured
+  // slower (profiles/r2_attn_groups_sweep.txt)
+  if (nh % 3 == 0 && nh >= 12) g = nh / 3;
   const int v = ctx->dbg.attn_groups;                       // experiments: pin the number of head groups per image
   if (v >= 1 && nh % v == 0 && nh / v <= ATTD_MAXHPC) g = v;
   return g;
