@@ -559,6 +559,9 @@ def run_graft_arm(args, rank: int, world: int, local_rank: int):
                 "us_per_launch": dom["us"], "share_of_step": dom["share"],
                 "hbm_view": {"achieved_gbs": dom["weight_gbs"], "peak_gbs": peaks["hbm_gbs"], "frac": dom["frac_hbm"]},
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                "note": "an M = 256 launch is neither tensor- nor HBM-bound: about half of it is dependency hand-over, first tile "
+                        "and tail, the main loop runs at ~320 ns per 128 columns of K (DESIGN.md 3.1 / 4, profiles/r2_gemm_phases.txt); "
+                        "roofline_gemm_all aggregates every tcgen05 GEMM launch of a position",
                 "how": "device %globaltimer per launch inside the replayed loop (hq_trace_run), top positions 30-33; "
                        "traffic IMPORTED from profiles/r2_ncu_traffic.json (ncu --set full capture of the same command, "
                        "committed; not measured in this run)"}
